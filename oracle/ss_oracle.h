@@ -1,0 +1,158 @@
+/*
+ * ss_oracle.h -- CPU ORACLE for the Summerset quorum-tally + Reed-Solomon hot path.
+ *
+ * THIS IS TEST INFRASTRUCTURE, NOT THE PRODUCT.  Only tests/, __graft_entry__.smoke()
+ * and bench.py's cpu_baseline / --impl reference legs may load it.  The product
+ * (summerset_b200/csrc, libsummerset_b200.so) never links, imports or calls it.
+ *
+ * It is a plain-C restatement of the reference's Rust path (josehu07/summerset @ 1daf80aa;
+ * paths relative to /root/reference):
+ *   src/utils/rscoding.rs            RSCodeword geometry / encode / reconstruct / verify
+ *   src/utils/bitmap.rs              Bitmap (replica-id / shard-id bitset)
+ *   src/protocols/multipaxos/messages.rs:370-443   MultiPaxos accept-reply tally
+ *   src/protocols/rspaxos/messages.rs:395-465      RSPaxos tally (majority + fault_tolerance)
+ *   src/protocols/crossword/messages.rs:15-62,481-574  coverage_under_faults + tally
+ *   src/protocols/crossword/adaptive.rs:98-106, mod.rs:866-888  balanced round-robin assignment
+ *   src/protocols/multipaxos/durability.rs:148-218 commit_bar advance
+ *   src/protocols/raft/messages.rs:243-309         match-index commit scan
+ *   src/protocols/craft/messages.rs:288-314        CRaft thresholds
+ * and of the un-vendored crate `reed-solomon-erasure ^6.0` (Cargo.toml:43; Cargo.lock is
+ * git-ignored so no exact version is pinned) -- galois_8 field, Backblaze-style
+ * Vandermonde-derived systematic matrix.
+ *
+ * PINNING STATUS (see DESIGN.md "Oracle"):
+ *   - pinned against every assertion of the reference's own unit tests for this path
+ *     (rscoding.rs:685-877, bitmap.rs:312-420): geometry, null codeword, subset/absorb,
+ *     verify-after-encode, reconstruct under erasures, error cases.
+ *   - PARITY-BYTE VALUES AND COMMIT BITMAPS: **parity unpinned** by the reference tree --
+ *     the reference holds no golden parity bytes and no handler unit tests, and it cannot be
+ *     compiled here (no cargo/rustc, no network).  They are anchored instead on the published
+ *     algorithm of the crate (Backblaze JavaReedSolomon construction) and its upstream
+ *     known-answer tests (recalled, labelled as such in tests/test_oracle_kat.py).
+ */
+#ifndef SS_ORACLE_H
+#define SS_ORACLE_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* error codes mirroring reed_solomon_erasure::Error (crate enum order) */
+enum {
+    SSOR_OK = 0,
+    SSOR_ERR_TOO_FEW_SHARDS = -1,
+    SSOR_ERR_TOO_MANY_SHARDS = -2,
+    SSOR_ERR_TOO_FEW_DATA_SHARDS = -3,
+    SSOR_ERR_TOO_MANY_DATA_SHARDS = -4,
+    SSOR_ERR_TOO_FEW_PARITY_SHARDS = -5,
+    SSOR_ERR_TOO_MANY_PARITY_SHARDS = -6,
+    SSOR_ERR_INCORRECT_SHARD_SIZE = -9,
+    SSOR_ERR_TOO_FEW_SHARDS_PRESENT = -10,
+    SSOR_ERR_EMPTY_SHARD = -11,
+    SSOR_ERR_INVALID_ARG = -20,
+    SSOR_ERR_SINGULAR = -21
+};
+
+/* ---- GF(2^8), poly 0x11D, generator 2 (crate galois_8) ---- */
+uint8_t ssor_gf_mul(uint8_t a, uint8_t b);
+uint8_t ssor_gf_div(uint8_t a, uint8_t b);          /* b != 0 */
+uint8_t ssor_gf_exp(uint8_t a, unsigned n);
+uint8_t ssor_gf_log(uint8_t a);                     /* a != 0 */
+uint8_t ssor_gf_exp_table(unsigned i);              /* EXP[i], i < 510 */
+
+/* ---- coding matrix: (d+p) x d, row-major; top d x d is identity ---- */
+int ssor_rs_build_matrix(int d, int p, uint8_t *out);
+/* invert an n x n matrix in GF(2^8) (row-major, in -> out) */
+int ssor_gf_matrix_invert(int n, const uint8_t *in, uint8_t *out);
+/* decode rows for the given present mask: picks the first d present shards (index order),
+ * writes their indices to src_idx[d] and the d x d inverse (row r = coefficients that
+ * regenerate data shard r from those d sources) to dec. */
+int ssor_rs_decode_matrix(int d, int p, const uint8_t *present, int *src_idx, uint8_t *dec);
+
+/* ---- single-codeword coder ops (crate: encode / reconstruct / reconstruct_data / verify) ----
+ * shards: array of d+p pointers to shard_len bytes each. */
+int ssor_rs_encode(int d, int p, uint8_t *const *shards, size_t shard_len);
+int ssor_rs_reconstruct(int d, int p, uint8_t *const *shards, uint8_t *present,
+                        size_t shard_len, int data_only);
+int ssor_rs_verify(int d, int p, const uint8_t *const *shards, size_t shard_len, int *ok);
+
+/* ---- RSCodeword geometry (rscoding.rs:165-220) ---- */
+size_t ssor_cw_shard_len(size_t data_len, int d);
+/* copy + zero-pad `data` into d contiguous data shards of shard_len bytes: out[d*shard_len] */
+void ssor_cw_split(const uint8_t *data, size_t data_len, int d, uint8_t *out);
+
+/* ---- batched CPU path (baseline + parity checker for the GPU batch API) ----
+ * codeword g: payload bytes data[data_off[g] .. +data_len[g]); L_g = ceil(len/d).
+ * parity shard j of codeword g is written to parity[j*plane_stride + par_off[g] .. +L_g).
+ * mode: 0 = scalar MUL_TABLE loops (crate default), 1 = AVX2 vpshufb nibble tables
+ * (what the crate's simd-accel gives), falls back to 0 if the CPU lacks AVX2.
+ * threads: OpenMP threads (<=0: all). */
+int ssor_rs_encode_batch(int d, int p, const uint8_t *data, const uint64_t *data_off,
+                         const uint32_t *data_len, uint64_t n, uint8_t *parity,
+                         uint64_t plane_stride, const uint64_t *par_off, int mode, int threads);
+/* shards laid out as shard j of codeword g at shards[j*plane_stride + off[g] .. +L_g);
+ * present[g] bitmask (bit j = shard j available). Regenerates missing data shards (and
+ * missing parity when !data_only) in place; status[g] = 0 / SSOR_ERR_TOO_FEW_SHARDS_PRESENT. */
+int ssor_rs_reconstruct_batch(int d, int p, uint8_t *shards, uint64_t plane_stride,
+                              const uint64_t *off, const uint32_t *data_len,
+                              const uint32_t *present, uint64_t n, int data_only,
+                              int32_t *status, int mode, int threads);
+int ssor_have_avx2(void);
+int ssor_max_threads(void);
+
+/* ---- quorum tallies ---- */
+/* Incremental per-ack restatement of handle_msg_accept_reply
+ * (multipaxos/messages.rs:370-443; rspaxos/messages.rs:395-465 with another threshold).
+ * State (caller-allocated, S slots per group): bal_prepared[g], inst_bal[g*S+s],
+ * status[g*S+s] (SSOR_ST_*), acks[g*S+s] (bitmask over replica ids).
+ * Records i: group rec_g[i], slot rec_s[i], peer rec_p[i], ballot rec_b[i]. */
+enum { SSOR_ST_NULL = 0, SSOR_ST_PREPARING = 1, SSOR_ST_ACCEPTING = 2,
+       SSOR_ST_COMMITTED = 3, SSOR_ST_EXECUTED = 4 };
+void ssor_tally_stream(const uint32_t *rec_g, const uint8_t *rec_s, const uint8_t *rec_p,
+                       const uint64_t *rec_b, uint64_t n_rec, uint32_t S, uint32_t population,
+                       uint32_t threshold, const uint64_t *bal_prepared, const uint64_t *inst_bal,
+                       uint8_t *status, uint16_t *acks);
+/* batch (bit-plane) form: planes[r*G+g] bit s = valid ack of replica r for slot s. */
+void ssor_tally_planes(const uint64_t *planes, uint32_t R, uint64_t G, uint32_t threshold,
+                       uint64_t *committed, uint32_t *commit_bar, int threads);
+/* per-instance vote-mask form: masks[i] = Bitmap of acks (bit r), count() >= threshold */
+void ssor_tally_masks(const uint16_t *masks, uint64_t n, uint32_t threshold, uint8_t *commit);
+/* commit_bar = length of committed prefix of the 64-slot window (durability.rs:148-218) */
+uint32_t ssor_commit_bar(uint64_t committed_word);
+
+/* ---- Crossword ---- */
+/* balanced round-robin assignment (crossword/mod.rs:866-888): replica r holds shards
+ * {(r*dj + k) mod T : k in [0,spr)}, dj = T/n.  out[r] = bitmask over shard ids. */
+void ssor_cw_brr_assignment(uint32_t n, uint32_t T, uint32_t spr, uint32_t *out);
+/* min_shards_per_replica (crossword/adaptive.rs:98-106) */
+uint32_t ssor_cw_min_spr(uint32_t d, uint32_t majority, uint32_t f, uint32_t alive);
+/* coverage_under_faults (crossword/messages.rs:15-62). ack_mask: replicas that acked;
+ * assignment[r]: shard bitmask of replica r. */
+uint32_t ssor_cw_coverage(uint32_t T, uint32_t n, uint32_t ack_mask, const uint32_t *assignment,
+                          uint32_t f, int balanced);
+/* commit predicate (crossword/messages.rs:535-542) */
+int ssor_cw_committed(uint32_t T, uint32_t n, uint32_t d, uint32_t majority, uint32_t f,
+                      uint32_t ack_mask, const uint32_t *assignment, int balanced);
+
+/* ---- Raft / CRaft match-index scan (raft/messages.rs:256-275) ----
+ * match[p] for the npeers = population-1 peers (self excluded); log entries
+ * last_commit+1 .. log_end-1 have terms terms[slot - (last_commit+1)].
+ * threshold = quorum_cnt (Raft) or majority+f / majority (CRaft). */
+uint32_t ssor_raft_scan(const uint32_t *match, uint32_t npeers, uint32_t last_commit,
+                        uint32_t log_end, uint32_t curr_term, const uint32_t *terms,
+                        uint32_t threshold);
+/* last_snap scan (raft/messages.rs:298-309): match_cnt == population */
+uint32_t ssor_raft_snap_scan(const uint32_t *match, uint32_t npeers, uint32_t last_snap,
+                             uint32_t end_slot);
+void ssor_raft_scan_batch(const uint32_t *match, uint32_t npeers, uint64_t G,
+                          const uint32_t *last_commit, const uint32_t *log_end,
+                          const uint32_t *curr_term, const uint32_t *terms, uint32_t W,
+                          uint32_t threshold, uint32_t *new_commit, int threads);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
