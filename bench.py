@@ -1,0 +1,491 @@
+#!/usr/bin/env python
+"""bench.py -- throughput of the quorum-tally + Reed-Solomon accept path on B200.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload cfg3|cfg2|cfg5]
+
+A "step" is one pass of the hot path over one batch of synthetic input.  Default workload (cfg3,
+BASELINE.json configs[2], the configuration the north-star target is quoted on): the fused RSPaxos accept
+step -- RS(3,2) encode of 2^20 groups' 4096-byte request batches + quorum tally (4 of 5) of each group's
+64-slot ack window -- ONE kernel launch per step, inputs resident in HBM.  The JSON line also carries the
+cfg2 (MultiPaxos tally only) measurement under "cfg2".
+
+  value      RS shard GB/s = (d+p)*L bytes per codeword * codewords / time   (whole job, all ranks)
+  e2e        same metric through the host-buffer C-ABI calls (pinned host memory, H2D + D2H inside)
+  roofline   algorithmic bytes per launch / CUDA-event kernel time vs MEASURED_PEAKS.json hbm_gbs
+  cpu_baseline / --impl reference: the CPU oracle port of the reference path on this box's cores
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import time
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+import numpy as np  # noqa: E402
+
+D, P, DATA_LEN = 3, 2, 4096
+R, THRESH_RSPAXOS, THRESH_MULTIPAXOS = 5, 4, 3
+G_PER_GPU = 1 << 20
+METRIC = "RS shard GB/s on the fused RSPaxos accept step (RS(3,2) encode + quorum tally); consensus slots committed/s in slots_committed_per_s"
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="cfg3", choices=["cfg3", "cfg2", "cfg5"])
+    ap.add_argument("--groups", type=int, default=G_PER_GPU, help="groups per GPU")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    return ap.parse_args()
+
+
+def measured_peaks():
+    f = ROOT / "MEASURED_PEAKS.json"
+    if f.exists():
+        j = json.loads(f.read_text())
+        return float(j["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (measured copy bandwidth)"
+    return 6650.0, "fallback 6.65 TB/s (B200_PROFILING.md)"
+
+
+def profile_traffic(workload: str):
+    """dram bytes per launch from the committed ncu --set full capture (profiles/), or None."""
+    f = ROOT / "profiles" / "traffic.json"
+    if f.exists():
+        try:
+            return json.loads(f.read_text()).get(workload)
+        except Exception:
+            return None
+    return None
+
+
+class ClockSampler:
+    """Samples nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md)."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.proc = None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "50", "-i", str(index)], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.06)
+        self.proc.terminate()
+        try:
+            out, _ = self.proc.communicate(timeout=5)
+        except Exception:
+            self.proc.kill()
+            out = ""
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in out.strip().splitlines():
+            parts = [x.strip() for x in line.split(",")]
+            if len(parts) < 6:
+                continue
+            try:
+                sm.append(float(parts[0])); mx.append(float(parts[1]))
+            except ValueError:
+                continue
+            for nme, v in zip(names, parts[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(nme)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# =================================================================================================
+# CPU arm: the oracle port of the reference path, all host threads
+# =================================================================================================
+def cpu_arm(steps: int, warmup: int, sample_cw: int, workload: str):
+    from oracle import pyoracle as oracle
+    from summerset_b200 import workloads as wl
+    threads = oracle.max_threads()
+    mode = 1 if oracle.have_avx2() else 0
+    L = oracle.cw_shard_len(DATA_LEN, D)
+    ds = (L + 15) // 16 * 16
+    data = wl.payload_uniform(sample_cw, DATA_LEN, seed_extra=7)
+    planes = wl.cfg2_planes(sample_cw, R, 0.9, seed_extra=7)
+    parity = np.zeros((P, sample_cw, ds), dtype=np.uint8)
+    off = np.arange(sample_cw, dtype=np.uint64) * np.uint64(data.shape[1])
+    lens = np.full(sample_cw, DATA_LEN, dtype=np.uint32)
+    poff = np.arange(sample_cw, dtype=np.uint64) * np.uint64(ds)
+
+    def step():
+        if workload != "cfg2":
+            oracle.rs_encode_batch(D, P, data.reshape(-1), off, lens, parity.reshape(-1), sample_cw * ds, poff, mode, threads)
+        oracle.tally_planes(planes, THRESH_RSPAXOS if workload != "cfg2" else THRESH_MULTIPAXOS, threads)
+
+    for _ in range(warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    dt = (time.perf_counter() - t0) / steps
+    gbs = (D + P) * L * sample_cw / dt / 1e9
+    slots = sample_cw * 64 / dt
+    return dict(ms_per_step=dt * 1e3, gbs=gbs, slots_per_s=slots, threads=threads,
+                path="AVX2 vpshufb nibble tables (what rse-simd enables)" if mode else "scalar MUL_TABLE",
+                sample=f"{sample_cw} codewords x {DATA_LEN} B (1/{max(1, G_PER_GPU // sample_cw)} of the workload) + their 64-slot ack windows, per step")
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    sample = 1 << 18   # 1 GiB of payload per step: large enough to amortise thread wake-ups in a VM
+    r = cpu_arm(max(1, args.steps), max(1, args.warmup), sample, args.workload)
+    value = r["gbs"] if args.workload != "cfg2" else r["slots_per_s"]
+    unit = "GB/s" if args.workload != "cfg2" else "slots/s"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": unit, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+        "config": config_dict(args, 1),
+        "slots_committed_per_s": r["slots_per_s"],
+        "cpu_baseline": {"value": value, "unit": unit, "cores": r["threads"], "kind": "port", "sample": r["sample"],
+                         "path": r["path"],
+                         "note": "C restatement of the reference's Rust path (oracle/ss_oracle.c); the reference "
+                                 "itself cannot be built here (no cargo/rustc)"},
+        "e2e": {"value": value, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+def config_dict(args, world):
+    L = (DATA_LEN + D - 1) // D
+    return {"workload": {"cfg3": "cfg3: RSPaxos (3,5) fused RS(3,2) encode + quorum tally (4 of 5), 2^20 groups x 4096 B "
+                                 "request batch + 64-slot ack window per GPU",
+                         "cfg2": "cfg2: MultiPaxos 5-replica quorum tally (3 of 5), 2^20 groups x 64 slots per GPU",
+                         "cfg5": "cfg5: Raft 7-replica match-index commit scan, 2^22 groups, 64-slot term window"}[args.workload],
+            "groups_per_gpu": args.groups, "data_len": DATA_LEN, "rs": [D, P], "shard_len": L, "replicas": R,
+            "sharding": f"groups x{world} (independent shards)" + ("" if world == 1 else " + NCCL all-to-all of shard planes and ack planes"),
+            "l2": "inputs (4 GiB payload + 2.9 GB parity per GPU) exceed the 126 MB L2; no flush needed"}
+
+
+# =================================================================================================
+# GPU arm
+# =================================================================================================
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from summerset_b200 import sharding, workloads as wl
+    from summerset_b200.api import Context, ReedSolomon, SS_RS_OUT_PADDED16
+    from summerset_b200._lib import check
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    assert torch.cuda.is_available(), "bench.py needs a GPU (no CPU fallback)"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    ctx = Context(local)
+    rs = ReedSolomon(ctx, D, P)
+    n = args.groups
+    L, ds, ps = rs.parity_layout(DATA_LEN, n)
+    peak, peak_src = measured_peaks()
+
+    # ---- synthetic inputs, generated on the device (seeded) ----
+    gen = torch.Generator(device=dev); gen.manual_seed(wl.SEED_BASE + 3 + 1000 * rank)
+    data = torch.randint(0, 256, (n, DATA_LEN), dtype=torch.uint8, device=dev, generator=gen)
+    shards = torch.zeros((D + P, n, ds), dtype=torch.uint8, device=dev) if world > 1 else None
+    parity = shards[D:] if world > 1 else torch.empty((P, n, ds), dtype=torch.uint8, device=dev)
+    # ack planes: leader always acks, followers with p = 0.9 (230/256)
+    u = torch.randint(0, 256, (R, n, 64), dtype=torch.uint8, device=dev, generator=gen) < 230
+    w = torch.tensor([1 << i for i in range(63)] + [-(1 << 63)], dtype=torch.int64, device=dev)
+    planes = (u.to(torch.int64) * w).sum(dim=2)
+    planes[0] = -1
+    del u
+    committed = torch.empty(n, dtype=torch.int64, device=dev)
+    bar = torch.empty(n, dtype=torch.int32, device=dev)
+    recv = torch.empty((R, n, ds), dtype=torch.uint8, device=dev) if world > 1 else None
+    ack_recv = torch.empty((R, n), dtype=torch.int64, device=dev) if world > 1 else None
+    rounds = sharding.exchange_rounds(R, world, rank) if world > 1 else []
+    flags = SS_RS_OUT_PADDED16 | (2 if world > 1 else 0)
+
+    def exchange():
+        # shard plane r of my groups -> rank (rank + r) % world ; then each simulated follower acks:
+        # its ack plane (seeded drop mask = my `planes[r]` of the home rank, sent along) returns home.
+        for rd in rounds:
+            ins = [shards[rd["send"][dst]] if rd["send"][dst] >= 0 else shards[0][:0] for dst in range(world)]
+            outs = [recv[rd["recv"][src]] if rd["recv"][src] >= 0 else recv[0][:0] for src in range(world)]
+            dist.all_to_all(outs, ins)
+        for rd in rounds:
+            # follower on rank dst accepted shard r from home `src`; its ack plane travels back the other way
+            ins = [planes[rd["recv"][src]] if rd["recv"][src] >= 0 else planes[0][:0] for src in range(world)]
+            outs = [ack_recv[rd["send"][dst]] if rd["send"][dst] >= 0 else ack_recv[0][:0] for dst in range(world)]
+            dist.all_to_all(outs, ins)
+
+    def step():
+        if args.workload == "cfg2":
+            ctx.tally_planes(planes, THRESH_MULTIPAXOS, True, committed, bar)
+            return
+        check(ctx.lib.ss_accept_step_fused_dev(rs.h, data.data_ptr(), DATA_LEN, DATA_LEN, n, parity.data_ptr(), ps, ds,
+                                               flags, (ack_recv if world > 1 else planes).data_ptr(), R,
+                                               THRESH_RSPAXOS, committed.data_ptr(), bar.data_ptr()))
+        if world > 1:
+            exchange()
+
+    if world > 1:
+        ack_recv.copy_(planes)
+
+    # ---- cfg5 (Raft) is a separate small harness ----
+    if args.workload == "cfg5":
+        return run_cfg5(args, ctx, dev, world, rank, peak, peak_src)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(3, args.warmup)):
+        step()
+    barrier()
+    sampler = ClockSampler(local) if rank == 0 else None
+    launches0 = ctx.launches
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    k_evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    t_start = torch.cuda.Event(enable_timing=True); t_end = torch.cuda.Event(enable_timing=True)
+    t_start.record()
+    for i in range(args.steps):
+        step()
+    t_end.record()
+    barrier()
+    total_ms = t_start.elapsed_time(t_end)
+    launches = ctx.launches - launches0
+    clocks = sampler.stop() if sampler else None
+    # kernel-only duration (CUDA events around the single launch), measured in a second pass so the events
+    # do not perturb the whole-step timing above
+    kt = []
+    for i in range(args.steps):
+        a, b = k_evs[i]
+        a.record()
+        if args.workload == "cfg2":
+            ctx.tally_planes(planes, THRESH_MULTIPAXOS, True, committed, bar)
+        else:
+            check(ctx.lib.ss_accept_step_fused_dev(rs.h, data.data_ptr(), DATA_LEN, DATA_LEN, n, parity.data_ptr(), ps, ds,
+                                                   flags, (ack_recv if world > 1 else planes).data_ptr(), R,
+                                                   THRESH_RSPAXOS, committed.data_ptr(), bar.data_ptr()))
+        b.record()
+    torch.cuda.synchronize()
+    kt = [a.elapsed_time(b) for a, b in k_evs]
+    kernel_ms = sum(kt) / len(kt)
+    if world > 1:
+        t = torch.tensor([total_ms, kernel_ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total_ms, kernel_ms = float(t[0]), float(t[1])
+    ms_per_step = total_ms / args.steps
+
+    # ---- parity spot-check of what was just timed (oracle = checker only) ----
+    check_note = None
+    if rank == 0:
+        from oracle import pyoracle as oracle
+        idx = torch.arange(0, n, max(1, n // 128), device=dev)
+        if args.workload != "cfg2":
+            want = oracle.rs_encode_uniform(D, P, data[idx].cpu().numpy(), DATA_LEN)
+            got = parity[:, idx].cpu().numpy()
+            assert (got == want).all(), "bench parity check failed"
+        src = (ack_recv if world > 1 else planes)
+        cw, bw = oracle.tally_planes(src[:, idx].cpu().numpy().view(np.uint64),
+                                     THRESH_RSPAXOS if args.workload != "cfg2" else THRESH_MULTIPAXOS)
+        assert (committed[idx].cpu().numpy().view(np.uint64) == cw).all(), "bench commit check failed"
+        check_note = f"{len(idx)} sampled groups bit-exact vs oracle"
+
+    alg_rs = (D + P) * L                       # 6830 B / codeword
+    alg_tally = (R + 1) * 8 + 4                # 48 B planes+commit word, +4 B commit_bar
+    if args.workload == "cfg2":
+        alg = alg_tally
+        value = n * world * 64 / (ms_per_step * 1e-3)
+        unit = "slots/s"
+    else:
+        alg = alg_rs + alg_tally
+        value = alg_rs * n * world / (ms_per_step * 1e-3) / 1e9
+        unit = "GB/s"
+    achieved = alg * n / (kernel_ms * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": profile_traffic(args.workload), "kernel": rs.last_kernel() if args.workload != "cfg2" else "tally_planes_kernel",
+                "kernel_ms": kernel_ms, "algorithmic_bytes_per_launch": alg * n, "peak_source": peak_src + " (burst figure; kernel timed alone)"}
+
+    extra = {}
+    if rank == 0 and args.workload == "cfg3" and world == 1:
+        # cfg2 (MultiPaxos tally only) measured beside it; 4 rotated plane sets > L2
+        extra["cfg2"] = bench_cfg2(ctx, torch, dev, n, peak)
+
+    e2e = None
+    if not args.no_e2e and world == 1:
+        e2e = bench_e2e(ctx, rs, torch, n, args)
+    elif world > 1:
+        e2e = bench_e2e(ctx, rs, torch, n, args, dist=dist, world=world, dev=dev)
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        r = cpu_arm(3, 1, 1 << 18, args.workload)
+        cpu = {"value": r["gbs"] if args.workload != "cfg2" else r["slots_per_s"], "unit": unit, "cores": r["threads"],
+               "kind": "port", "sample": r["sample"] + " x 3 steps", "path": r["path"], "slots_per_s": r["slots_per_s"]}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": unit, "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8",
+            "data": "synthetic", "config": config_dict(args, world),
+            "slots_committed_per_s": n * world * 64 / (ms_per_step * 1e-3),
+            "payload_GBps": DATA_LEN * n * world / (ms_per_step * 1e-3) / 1e9,
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
+            "parity_check": check_note,
+        }
+        line.update(extra)
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def bench_cfg2(ctx, torch, dev, n, peak):
+    sets = 4
+    gen = torch.Generator(device=dev); gen.manual_seed(1234)
+    planes = torch.randint(-(1 << 62), 1 << 62, (sets, R, n), dtype=torch.int64, device=dev, generator=gen)
+    planes[:, 0] = -1
+    committed = torch.empty((sets, n), dtype=torch.int64, device=dev)
+    bar = torch.empty((sets, n), dtype=torch.int32, device=dev)
+    for i in range(8):
+        ctx.tally_planes(planes[i % sets], THRESH_MULTIPAXOS, True, committed[i % sets], bar[i % sets])
+    torch.cuda.synchronize()
+    iters = 40
+    a = torch.cuda.Event(enable_timing=True); b = torch.cuda.Event(enable_timing=True)
+    a.record()
+    for i in range(iters):
+        ctx.tally_planes(planes[i % sets], THRESH_MULTIPAXOS, True, committed[i % sets], bar[i % sets])
+    b.record()
+    torch.cuda.synchronize()
+    ms = a.elapsed_time(b) / iters
+    alg = ((R + 1) * 8 + 4) * n
+    return {"workload": "cfg2: MultiPaxos quorum tally 3 of 5, 2^20 groups x 64 slots, 4 rotated plane sets (208 MB > L2)",
+            "slots_committed_per_s": n * 64 / (ms * 1e-3), "ms_per_step": ms,
+            "roofline": {"bound": "hbm", "achieved": alg / (ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                         "frac": alg / (ms * 1e-3) / 1e9 / peak, "traffic": None,
+                         "note": "52 B/group; ~8 us of work per launch, launch-latency bound"}}
+
+
+def bench_e2e(ctx, rs, torch, n, args, dist=None, world=1, dev=None):
+    """Same step through the host-buffer C-ABI entry points: pinned host inputs, H2D + kernel + D2H inside."""
+    L, ds, ps = rs.parity_layout(DATA_LEN, n)
+    if args.workload == "cfg2":
+        planes = torch.empty((R, n), dtype=torch.int64, pin_memory=True)
+        planes.random_(-(1 << 62), 1 << 62)
+        planes[0] = -1
+        pn = planes.numpy().view(np.uint64)
+        steps = max(3, min(args.steps, 10))
+        ctx.tally_planes_host(pn, THRESH_MULTIPAXOS)
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            ctx.tally_planes_host(pn, THRESH_MULTIPAXOS)
+        dt = (time.perf_counter() - t0) / steps
+        val = torch.tensor([dt], dtype=torch.float64)
+        return {"value": n * world * 64 / dt, "unit": "slots/s", "h2d_bytes_per_step": R * n * 8,
+                "d2h_bytes_per_step": n * 12, "steps": steps, "ms_per_step": dt * 1e3}
+    hdata = torch.empty((n, DATA_LEN), dtype=torch.uint8, pin_memory=True)
+    rng = np.random.Generator(np.random.Philox(key=99))
+    hv = hdata.numpy()
+    chunk = 1 << 16
+    for a in range(0, n, chunk):
+        hv[a:a + chunk] = rng.integers(0, 256, size=(min(chunk, n - a), DATA_LEN), dtype=np.uint8)
+    hpar = torch.empty((P, n, ds), dtype=torch.uint8, pin_memory=True)
+    hplanes = torch.empty((R, n), dtype=torch.int64, pin_memory=True)
+    hplanes.random_(-(1 << 62), 1 << 62)
+    hplanes[0] = -1
+    pn = hplanes.numpy().view(np.uint64)
+    steps = max(3, min(args.steps, 10))
+
+    def step():
+        rs.encode_uniform_host(hv, DATA_LEN, hpar.numpy())
+        return ctx.tally_planes_host(pn, THRESH_RSPAXOS)
+
+    step()
+    if dist is not None:
+        dist.barrier()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        c, b = step()
+    dt = (time.perf_counter() - t0) / steps
+    if dist is not None:
+        t = torch.tensor([dt], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dt = float(t[0])
+    # check the e2e result too
+    from oracle import pyoracle as oracle
+    idx = np.arange(0, n, max(1, n // 64))
+    want = oracle.rs_encode_uniform(D, P, hv[idx], DATA_LEN)
+    assert (hpar.numpy()[:, idx] == want).all(), "e2e parity check failed"
+    return {"value": (D + P) * L * n * world / dt / 1e9, "unit": "GB/s",
+            "h2d_bytes_per_step": n * DATA_LEN + R * n * 8, "d2h_bytes_per_step": P * n * ds + n * 12,
+            "steps": steps, "ms_per_step": dt * 1e3, "slots_committed_per_s": n * world * 64 / dt,
+            "timing": "host wall clock around blocking C-ABI calls (they return when results are in host memory)"}
+
+
+def run_cfg5(args, ctx, dev, world, rank, peak, peak_src):
+    import torch
+    import torch.distributed as dist
+    from summerset_b200 import workloads as wl
+    G = 1 << 22
+    w = wl.cfg5_raft(1 << 16, 7, 64, seed_extra=rank)
+    rep = G // (1 << 16)
+    t = lambda a, r: torch.from_numpy(np.ascontiguousarray(a).view(np.int32)).to(dev).repeat(*r)
+    match = t(w["match"], (1, rep)); lc = t(w["last_commit"], (rep,)); le = t(w["log_end"], (rep,))
+    ct = t(w["curr_term"], (rep,)); terms = t(w["terms"], (rep, 1))
+    out = torch.empty(G, dtype=torch.int32, device=dev)
+    for _ in range(max(3, args.warmup)):
+        ctx.raft_commit_scan(match, lc, le, ct, terms, 4, out)
+    torch.cuda.synchronize()
+    a = torch.cuda.Event(enable_timing=True); b = torch.cuda.Event(enable_timing=True)
+    l0 = ctx.launches
+    a.record()
+    for _ in range(args.steps):
+        ctx.raft_commit_scan(match, lc, le, ct, terms, 4, out)
+    b.record()
+    torch.cuda.synchronize()
+    ms = a.elapsed_time(b) / args.steps
+    if world > 1:
+        tt = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        ms = float(tt[0])
+    alg = 296 * G
+    if rank == 0:
+        print(json.dumps({"metric": "Raft groups scanned/s (7 replicas, 64-slot window)", "value": G * world / (ms * 1e-3),
+                          "unit": "groups/s", "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
+                          "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                          "dtype": "u32", "data": "synthetic", "config": config_dict(args, world),
+                          "roofline": {"bound": "hbm", "achieved": alg / (ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                                       "frac": alg / (ms * 1e-3) / 1e9 / peak, "traffic": None, "peak_source": peak_src},
+                          "gpu_launches": int(ctx.launches - l0), "e2e": None, "cpu_baseline": None}))
+    if world > 1:
+        dist.barrier(); dist.destroy_process_group()
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,247 @@
+/*
+ * summerset_b200.h -- C ABI of libsummerset_b200.so
+ *
+ * The B200 (sm_100a) implementation of Summerset's quorum-tally + Reed-Solomon hot path.
+ * Plain C: pointers and sizes only, no torch / C++ types.  This is the boundary a Rust
+ * `extern "C"` block binds; the GenericReplica / SmrProtocol surface
+ * (src/server/replica.rs:15-42, src/protocols/mod.rs:118-215) is untouched by it.
+ *
+ * The reference has no FFI for this path.  Each entry point states the reference
+ * interface it replaces (path:line relative to the reference tree, josehu07/summerset @ 1daf80aa).
+ *
+ * Conventions
+ *   - Ownership: the caller owns every buffer.  The library never frees or retains caller
+ *     memory (rscoding.rs:479-484, :515-517 -- encode/reconstruct mutate caller slices in place).
+ *   - Errors: `int` return, 0 = ok, negative = error.  Codes -1..-13 mirror the variants of
+ *     `reed_solomon_erasure::Error`, which the reference converts into `SummersetError(String)`
+ *     (src/utils/error.rs:6-14,59); ss_last_error() gives the message text for that conversion.
+ *   - Threading: every call may come from a different OS thread (the replica's run() task
+ *     migrates across tokio worker threads, summerset_server/src/main.rs:45-47,133-137).  No
+ *     thread-local CUDA state is assumed: each call binds its handle's device.  Calls on ONE
+ *     handle must be serialised by the caller (the reference calls from a single task).
+ *   - `_dev` entry points take DEVICE pointers and are asynchronous on the context's stream;
+ *     the others take HOST pointers, copy in/out and return when the result is in host memory.
+ *   - No CPU fallback: every compute entry point fails with SS_ERR_NO_DEVICE / SS_ERR_CUDA when
+ *     no sm_100 device is usable.
+ */
+#ifndef SUMMERSET_B200_H
+#define SUMMERSET_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SS_VERSION 100 /* 0.1.0 */
+
+/* ---- error codes ---------------------------------------------------------------------------
+ * -1..-13: reed_solomon_erasure::Error variants in declaration order. */
+enum {
+    SS_OK = 0,
+    SS_ERR_TOO_FEW_SHARDS = -1,
+    SS_ERR_TOO_MANY_SHARDS = -2,
+    SS_ERR_TOO_FEW_DATA_SHARDS = -3,
+    SS_ERR_TOO_MANY_DATA_SHARDS = -4,
+    SS_ERR_TOO_FEW_PARITY_SHARDS = -5,
+    SS_ERR_TOO_MANY_PARITY_SHARDS = -6,
+    SS_ERR_TOO_FEW_BUFFER_SHARDS = -7,
+    SS_ERR_TOO_MANY_BUFFER_SHARDS = -8,
+    SS_ERR_INCORRECT_SHARD_SIZE = -9,
+    SS_ERR_TOO_FEW_SHARDS_PRESENT = -10,
+    SS_ERR_EMPTY_SHARD = -11,
+    SS_ERR_INVALID_SHARD_FLAGS = -12,
+    SS_ERR_INVALID_INDEX = -13,
+    /* library-level */
+    SS_ERR_INVALID_ARG = -20,
+    SS_ERR_UNSUPPORTED = -21,
+    SS_ERR_OUT_OF_MEMORY = -22,
+    SS_ERR_NO_DEVICE = -30,   /* no CUDA device / not sm_100: there is NO CPU fallback */
+    SS_ERR_CUDA = -31
+};
+
+typedef struct ss_ctx ss_ctx;           /* device + stream + scratch */
+typedef struct ss_rs_coder ss_rs_coder; /* replaces reed_solomon_erasure::galois_8::ReedSolomon */
+
+int ss_version(void);
+/* Text of the most recent error in this process (copied under a lock; not thread-local).
+ * Maps to SummersetError::msg (src/utils/error.rs:6-14). */
+const char *ss_last_error(void);
+const char *ss_strerror(int code);
+
+/* ---- context ------------------------------------------------------------------------------- */
+/* Creates a context on `device` with its own non-blocking stream. */
+int ss_ctx_create(int device, ss_ctx **out);
+/* Same, but launches on a caller-owned cudaStream_t (e.g. torch's current stream). */
+int ss_ctx_create_on_stream(int device, void *cuda_stream, ss_ctx **out);
+int ss_ctx_destroy(ss_ctx *ctx);
+int ss_ctx_sync(ss_ctx *ctx);               /* cudaStreamSynchronize on the context's stream */
+void *ss_ctx_stream(ss_ctx *ctx);           /* the cudaStream_t */
+int ss_ctx_sm_count(ss_ctx *ctx);
+/* number of kernels this context has launched so far (bench.py's gpu_launches claim) */
+uint64_t ss_ctx_launch_count(ss_ctx *ctx);
+
+/* device / pinned-host memory helpers for non-CUDA callers (Rust shim) */
+int ss_dev_alloc(ss_ctx *ctx, size_t bytes, void **dptr);
+int ss_dev_free(ss_ctx *ctx, void *dptr);
+int ss_dev_memset(ss_ctx *ctx, void *dptr, int value, size_t bytes);      /* async */
+int ss_host_alloc(ss_ctx *ctx, size_t bytes, void **hptr);                /* pinned */
+int ss_host_free(ss_ctx *ctx, void *hptr);
+int ss_copy_h2d(ss_ctx *ctx, void *dst_dev, const void *src_host, size_t bytes); /* async */
+int ss_copy_d2h(ss_ctx *ctx, void *dst_host, const void *src_dev, size_t bytes); /* async */
+
+/* ---- Reed-Solomon coder --------------------------------------------------------------------
+ * Replaces ReedSolomon::new(d, p) (constructors at rspaxos/mod.rs:606, crossword/mod.rs:827,
+ * craft/mod.rs:534, benches/rse_bench.rs:51).  GF(2^8) poly 0x11D; systematic matrix
+ * M = vandermonde(d+p, d) * inverse(top d x d) -- bit-identical to the crate's.
+ * Errors: d == 0 -> TOO_FEW_DATA_SHARDS, p == 0 -> TOO_FEW_PARITY_SHARDS, d+p > 256 ->
+ * TOO_MANY_SHARDS (the crate's behaviour; Summerset special-cases p == 0 before touching the
+ * coder, rscoding.rs:454-456,498-507).  Batched kernels need d <= 32, p <= 8, d+p <= 32. */
+int ss_rs_coder_create(ss_ctx *ctx, int data_shards, int parity_shards, ss_rs_coder **out);
+int ss_rs_coder_destroy(ss_rs_coder *coder);
+int ss_rs_data_shard_count(const ss_rs_coder *coder);    /* rscoding.rs:428 */
+int ss_rs_parity_shard_count(const ss_rs_coder *coder);  /* rscoding.rs:434 */
+int ss_rs_total_shard_count(const ss_rs_coder *coder);
+/* copies the (d+p) x d coding matrix, row-major, into out */
+int ss_rs_coder_matrix(const ss_rs_coder *coder, uint8_t *out);
+
+/* -- one codeword, HOST slices: the four crate methods RSCodeword calls ----------------------
+ * shards: n_shards (= d+p) pointers to shard_len bytes each.
+ * ss_rs_encode            replaces rs.encode(slices)             (rscoding.rs:484)
+ * ss_rs_reconstruct       replaces rs.reconstruct(&mut shards)   (rscoding.rs:517)
+ * ss_rs_reconstruct_data  replaces rs.reconstruct_data(..)       (rscoding.rs:515)
+ * ss_rs_verify            replaces rs.verify(&slices)            (rscoding.rs:575)
+ * present[j] != 0 <=> shards[j] is Some(..); missing entries must still point at a
+ * shard_len-byte buffer to fill (the crate allocates it; here the caller does).  On success
+ * present[] is updated for the regenerated shards.  Fewer than d present ->
+ * SS_ERR_TOO_FEW_SHARDS_PRESENT and no output is written (never partial). */
+int ss_rs_encode(ss_rs_coder *coder, uint8_t *const *shards, size_t n_shards, size_t shard_len);
+int ss_rs_reconstruct(ss_rs_coder *coder, uint8_t *const *shards, uint8_t *present,
+                      size_t n_shards, size_t shard_len);
+int ss_rs_reconstruct_data(ss_rs_coder *coder, uint8_t *const *shards, uint8_t *present,
+                           size_t n_shards, size_t shard_len);
+int ss_rs_verify(ss_rs_coder *coder, const uint8_t *const *shards, size_t n_shards,
+                 size_t shard_len, int *ok);
+
+/* -- batched, device-resident log of codewords ------------------------------------------------
+ * Codeword g: payload bytes data[data_off[g] .. +data_len[g]) = the bincode-serialised request
+ * batch RSCodeword::from_data produces (rscoding.rs:223-243).  Geometry is the reference's
+ * (rscoding.rs:177-199): L_g = ceil(data_len/d); data shard i = payload bytes [i*L, (i+1)*L),
+ * zero-padded past data_len; a contiguous split, so data shards are VIEWS of the payload.
+ * Parity shard j of codeword g is written to parity[j*plane_stride + par_off[g] .. +L_g).
+ * One launch = RSCodeword::from_data's split + compute_parity (rspaxos/request.rs:72-77,
+ * crossword/request.rs:82-87) for n codewords; plane j is at the same time the packed
+ * per-destination send buffer subset_copy builds one codeword at a time (rscoding.rs:255-293,
+ * rspaxos/request.rs:127-142).  data_len[g] == 0 (null codeword) is skipped.
+ *
+ * flags:
+ *   SS_RS_OUT_PADDED16  every parity slot starts 16-byte aligned and has capacity
+ *                       round_up(L_g,16); bytes [L_g, round_up) are written as zeros.  This is
+ *                       the fast path (128-bit stores).  Without it stores are byte-exact.
+ * The payload arena must be a CUDA allocation (the kernel issues aligned 16-byte loads that may
+ * cover up to 15 bytes either side of a payload, inside the allocation's 256-byte granule).
+ *   SS_RS_EMIT_DATA     `parity` is plane d of a (d+p)-plane shard store with the same plane_stride:
+ *                       the kernel ALSO copies data shard i into plane i (parity - (d-i)*plane_stride),
+ *                       so all d+p planes are packed per-destination send buffers after one pass. */
+#define SS_RS_OUT_PADDED16 1u
+#define SS_RS_EMIT_DATA 2u
+int ss_rs_encode_batch_dev(ss_rs_coder *coder, const uint8_t *data, const uint64_t *data_off,
+                           const uint32_t *data_len, uint64_t n, uint8_t *parity,
+                           uint64_t plane_stride, const uint64_t *par_off, uint32_t flags);
+/* uniform geometry: data_off[g] = g*data_stride, data_len[g] = data_len, par_off[g] = g*shard_stride */
+int ss_rs_encode_uniform_dev(ss_rs_coder *coder, const uint8_t *data, uint64_t data_stride,
+                             uint32_t data_len, uint64_t n, uint8_t *parity,
+                             uint64_t plane_stride, uint64_t shard_stride, uint32_t flags);
+
+/* Batched reconstruct (rscoding.rs:490-537 over n codewords; callers rspaxos/durability.rs:146-159,
+ * crossword/durability.rs:163-179).  Shard j of codeword g lives at
+ * shards[j*plane_stride + off[g] .. +L_g), L_g = ceil(data_len[g]/d).  present[g] bit j =
+ * shard j available.  Missing DATA shards are regenerated in place (and missing parity too when
+ * data_only == 0).  status[g] = 0, SS_ERR_TOO_FEW_SHARDS_PRESENT (nothing written for g), or
+ * SS_ERR_INVALID_ARG for a null codeword (data_len == 0; rscoding.rs:495-497). */
+int ss_rs_reconstruct_batch_dev(ss_rs_coder *coder, uint8_t *shards, uint64_t plane_stride,
+                                const uint64_t *off, const uint32_t *data_len,
+                                const uint32_t *present, uint64_t n, int data_only,
+                                int32_t *status, uint32_t flags);
+
+/* host-buffer forms of the two batch calls (H2D, kernel, D2H inside; chunked + overlapped) */
+int ss_rs_encode_uniform(ss_rs_coder *coder, const uint8_t *data, uint64_t data_stride,
+                         uint32_t data_len, uint64_t n, uint8_t *parity, uint64_t plane_stride,
+                         uint64_t shard_stride);
+
+/* ---- quorum tallies ------------------------------------------------------------------------
+ * Bit-plane form.  planes[r*G + g] bit s = a VALID AcceptReply from replica r for slot s of
+ * group g (the leader's own WAL ack is one of the planes, multipaxos/durability.rs:99-103).
+ * committed[g] bit s = (count of set planes >= threshold) -- the end state of
+ * handle_msg_accept_reply on that ack set (multipaxos/messages.rs:404-413 with
+ * threshold = quorum_cnt; rspaxos/messages.rs:438-440 with majority + fault_tolerance).
+ * commit_bar[g] (may be NULL) = length of the committed prefix of the 64-slot window
+ * (multipaxos/durability.rs:161-170).  R <= 16. */
+int ss_tally_planes_dev(ss_ctx *ctx, const uint64_t *planes, uint32_t n_replicas, uint64_t n_groups,
+                        uint32_t threshold, uint64_t *committed, uint32_t *commit_bar);
+int ss_tally_planes(ss_ctx *ctx, const uint64_t *planes, uint32_t n_replicas, uint64_t n_groups,
+                    uint32_t threshold, uint64_t *committed, uint32_t *commit_bar);
+
+/* Per-instance vote-mask form: masks[i] = the instance's accept_acks Bitmap (bit r = replica r,
+ * src/utils/bitmap.rs:17; LeaderBookkeeping.accept_acks, multipaxos/mod.rs:181-197), one
+ * mask_bytes-wide (1 or 2) little-endian integer per instance.  commit_bits word i/64 bit i%64 =
+ * Bitmap::count() >= threshold (bitmap.rs:111-113). */
+int ss_tally_masks_dev(ss_ctx *ctx, const void *masks, uint32_t mask_bytes, uint64_t n_instances,
+                       uint32_t threshold, uint64_t *commit_bits);
+
+/* Ack ingest: applies the filters of handle_msg_accept_reply to a record stream and ORs the
+ * surviving acks into the planes (multipaxos/messages.rs:388 ballot == bal_prepared;
+ * :394-399 status == Accepting && ballot >= inst.bal; :404-406 duplicates are idempotent).
+ * accepting[g] bit s = instance (g,s) is in Status::Accepting; inst_bal[g*64+s] its ballot.
+ * Records with peer >= n_replicas or slot >= 64 are dropped (Bitmap::get -> Err, bitmap.rs:89-97). */
+int ss_ack_ingest_dev(ss_ctx *ctx, const uint32_t *rec_group, const uint8_t *rec_slot,
+                      const uint8_t *rec_peer, const uint64_t *rec_ballot, uint64_t n_records,
+                      const uint64_t *bal_prepared, const uint64_t *inst_bal,
+                      const uint64_t *accepting, uint32_t n_replicas, uint64_t n_groups,
+                      uint64_t *planes);
+
+/* Crossword commit predicate (crossword/messages.rs:15-62 coverage_under_faults, :535-542).
+ * policies[k*n_replicas + r] = shard bitmask (over T = total_shards ids) replica r holds under
+ * assignment policy k (Instance.assignment, crossword/mod.rs:260; balanced round-robin policies
+ * crossword/mod.rs:866-888, or the single init_assignment when unbalanced, adaptive.rs:129-131).
+ * policy_idx[i] selects instance i's policy; masks[i] = which replicas acked.
+ * balanced != 0 uses the reference's closed form (:28-33), else the subset enumeration (:35-61).
+ * commit iff #acks >= majority && coverage >= data_shards.  n_replicas <= 12, n_policies <= 16. */
+int ss_tally_crossword_dev(ss_ctx *ctx, const void *masks, uint32_t mask_bytes,
+                           const uint8_t *policy_idx, uint64_t n_instances,
+                           const uint32_t *policies_host, uint32_t n_policies, uint32_t n_replicas,
+                           uint32_t total_shards, uint32_t data_shards, uint32_t majority,
+                           uint32_t fault_tolerance, int balanced, uint64_t *commit_bits);
+
+/* Raft / CRaft match-index commit scan (raft/messages.rs:256-275; craft/messages.rs:288-314).
+ * match[p*G + g] for the n_peers = population-1 peers (self excluded, raft/mod.rs:560-562);
+ * entries last_commit+1 .. log_end-1 of group g have terms terms[g*window + (slot-last_commit-1)]
+ * (log_end - last_commit - 1 <= window).  new_commit[g] = the LAST slot in that range with
+ * term == curr_term and 1 + #{p: match[p] >= slot} >= threshold, else last_commit[g].
+ * threshold = quorum_cnt (Raft), majority+f or majority (CRaft full-copy). */
+int ss_raft_commit_scan_dev(ss_ctx *ctx, const uint32_t *match, uint32_t n_peers, uint64_t n_groups,
+                            const uint32_t *last_commit, const uint32_t *log_end,
+                            const uint32_t *curr_term, const uint32_t *terms, uint32_t window,
+                            uint32_t threshold, uint32_t *new_commit);
+
+/* ---- fused accept step (BASELINE config 3: RSPaxos encode + quorum) -------------------------
+ * ONE kernel launch that, for n_groups groups: RS-encodes each group's new request batch
+ * (as ss_rs_encode_uniform_dev) and tallies the group's 64-slot ack window
+ * (as ss_tally_planes_dev). */
+int ss_accept_step_fused_dev(ss_rs_coder *coder, const uint8_t *data, uint64_t data_stride,
+                             uint32_t data_len, uint64_t n_groups, uint8_t *parity,
+                             uint64_t plane_stride, uint64_t shard_stride, uint32_t flags,
+                             const uint64_t *planes, uint32_t n_replicas, uint32_t threshold,
+                             uint64_t *committed, uint32_t *commit_bar);
+
+/* ---- tuning / introspection (bench + tests) ------------------------------------------------ */
+/* selects the encode kernel variant: 0 = auto, 1 = direct-LDG, 2 = bulk-copy (TMA) ring */
+int ss_rs_set_variant(ss_rs_coder *coder, int variant);
+/* name of the kernel the last batch call on this coder launched (static string) */
+const char *ss_rs_last_kernel(const ss_rs_coder *coder);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SUMMERSET_B200_H */

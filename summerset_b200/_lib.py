@@ -1,0 +1,116 @@
+"""ctypes binding of libsummerset_b200.so (the C ABI in include/summerset_b200.h).
+
+Fails loudly when the shared library is missing: there is no Python / CPU fallback for any
+compute entry point.  Build it with `python -m summerset_b200.build` (or __graft_entry__.build()).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from pathlib import Path
+
+_PKG = Path(__file__).resolve().parent
+LIB_PATH = _PKG / "libsummerset_b200.so"
+
+# error codes (include/summerset_b200.h)
+SS_OK = 0
+SS_ERR_TOO_FEW_SHARDS = -1
+SS_ERR_TOO_MANY_SHARDS = -2
+SS_ERR_TOO_FEW_DATA_SHARDS = -3
+SS_ERR_TOO_MANY_DATA_SHARDS = -4
+SS_ERR_TOO_FEW_PARITY_SHARDS = -5
+SS_ERR_TOO_MANY_PARITY_SHARDS = -6
+SS_ERR_INCORRECT_SHARD_SIZE = -9
+SS_ERR_TOO_FEW_SHARDS_PRESENT = -10
+SS_ERR_EMPTY_SHARD = -11
+SS_ERR_INVALID_SHARD_FLAGS = -12
+SS_ERR_INVALID_INDEX = -13
+SS_ERR_INVALID_ARG = -20
+SS_ERR_UNSUPPORTED = -21
+SS_ERR_OUT_OF_MEMORY = -22
+SS_ERR_NO_DEVICE = -30
+SS_ERR_CUDA = -31
+SS_RS_OUT_PADDED16 = 1
+
+_vp, _u8p, _u32, _u64, _i = C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint64, C.c_int
+_sz = C.c_size_t
+
+# name -> (restype, argtypes); every symbol the header declares
+SIGNATURES = {
+    "ss_version": (_i, []),
+    "ss_last_error": (C.c_char_p, []),
+    "ss_strerror": (C.c_char_p, [_i]),
+    "ss_ctx_create": (_i, [_i, C.POINTER(_vp)]),
+    "ss_ctx_create_on_stream": (_i, [_i, _vp, C.POINTER(_vp)]),
+    "ss_ctx_destroy": (_i, [_vp]),
+    "ss_ctx_sync": (_i, [_vp]),
+    "ss_ctx_stream": (_vp, [_vp]),
+    "ss_ctx_sm_count": (_i, [_vp]),
+    "ss_ctx_launch_count": (_u64, [_vp]),
+    "ss_dev_alloc": (_i, [_vp, _sz, C.POINTER(_vp)]),
+    "ss_dev_free": (_i, [_vp, _vp]),
+    "ss_dev_memset": (_i, [_vp, _vp, _i, _sz]),
+    "ss_host_alloc": (_i, [_vp, _sz, C.POINTER(_vp)]),
+    "ss_host_free": (_i, [_vp, _vp]),
+    "ss_copy_h2d": (_i, [_vp, _vp, _vp, _sz]),
+    "ss_copy_d2h": (_i, [_vp, _vp, _vp, _sz]),
+    "ss_rs_coder_create": (_i, [_vp, _i, _i, C.POINTER(_vp)]),
+    "ss_rs_coder_destroy": (_i, [_vp]),
+    "ss_rs_data_shard_count": (_i, [_vp]),
+    "ss_rs_parity_shard_count": (_i, [_vp]),
+    "ss_rs_total_shard_count": (_i, [_vp]),
+    "ss_rs_coder_matrix": (_i, [_vp, _u8p]),
+    "ss_rs_encode": (_i, [_vp, C.POINTER(_vp), _sz, _sz]),
+    "ss_rs_reconstruct": (_i, [_vp, C.POINTER(_vp), _u8p, _sz, _sz]),
+    "ss_rs_reconstruct_data": (_i, [_vp, C.POINTER(_vp), _u8p, _sz, _sz]),
+    "ss_rs_verify": (_i, [_vp, C.POINTER(_vp), _sz, _sz, C.POINTER(_i)]),
+    "ss_rs_encode_batch_dev": (_i, [_vp, _vp, _vp, _vp, _u64, _vp, _u64, _vp, _u32]),
+    "ss_rs_encode_uniform_dev": (_i, [_vp, _vp, _u64, _u32, _u64, _vp, _u64, _u64, _u32]),
+    "ss_rs_reconstruct_batch_dev": (_i, [_vp, _vp, _u64, _vp, _vp, _vp, _u64, _i, _vp, _u32]),
+    "ss_rs_encode_uniform": (_i, [_vp, _vp, _u64, _u32, _u64, _vp, _u64, _u64]),
+    "ss_tally_planes_dev": (_i, [_vp, _vp, _u32, _u64, _u32, _vp, _vp]),
+    "ss_tally_planes": (_i, [_vp, _vp, _u32, _u64, _u32, _vp, _vp]),
+    "ss_tally_masks_dev": (_i, [_vp, _vp, _u32, _u64, _u32, _vp]),
+    "ss_ack_ingest_dev": (_i, [_vp, _vp, _vp, _vp, _vp, _u64, _vp, _vp, _vp, _u32, _u64, _vp]),
+    "ss_tally_crossword_dev": (_i, [_vp, _vp, _u32, _vp, _u64, _vp, _u32, _u32, _u32, _u32, _u32, _u32, _i, _vp]),
+    "ss_raft_commit_scan_dev": (_i, [_vp, _vp, _u32, _u64, _vp, _vp, _vp, _vp, _u32, _u32, _vp]),
+    "ss_accept_step_fused_dev": (_i, [_vp, _vp, _u64, _u32, _u64, _vp, _u64, _u64, _u32, _vp, _u32, _u32, _vp, _vp]),
+    "ss_rs_set_variant": (_i, [_vp, _i]),
+    "ss_rs_last_kernel": (C.c_char_p, [_vp]),
+}
+
+
+class SummersetError(RuntimeError):
+    """Mirror of `SummersetError(String)` (src/utils/error.rs:6-14): message + the C error code."""
+
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"[{code}] {msg}")
+        self.code = code
+        self.msg = msg
+
+
+_lib = None
+
+
+def load() -> C.CDLL:
+    """Loads the shared library and binds every declared symbol. Raises if anything is missing."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not LIB_PATH.exists():
+        raise ImportError(
+            f"{LIB_PATH} is missing: build the CUDA extension first "
+            "(`python -m summerset_b200.build`); there is no CPU fallback")
+    lib = C.CDLL(str(LIB_PATH))
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError if the symbol is not exported
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def check(rc: int) -> None:
+    if rc != SS_OK:
+        lib = load()
+        msg = lib.ss_last_error().decode("utf-8", "replace")
+        raise SummersetError(rc, msg or lib.ss_strerror(rc).decode())

@@ -1,0 +1,657 @@
+// capi.cu -- the extern "C" boundary declared in include/summerset_b200.h.
+//
+// Host-side logic only: handle management, argument checks that mirror the crate's error
+// behaviour, coefficient-program construction, H2D/D2H plumbing for the host-buffer entry points.
+// All arithmetic on shard bytes and vote masks happens in the kernels (rs_kernels.cu,
+// tally_kernels.cu).  There is no CPU fallback anywhere in this file.
+#include <cstdarg>
+#include <cstring>
+#include <mutex>
+#include <new>
+
+#include "gf256.hpp"
+#include "ss_internal.hpp"
+
+namespace ssb {
+
+// ---- errors -----------------------------------------------------------------------------------
+static std::mutex g_err_mu;
+static char g_err[512] = "";
+
+int set_error(int code, const char *fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    std::lock_guard<std::mutex> lk(g_err_mu);
+    snprintf(g_err, sizeof(g_err), "%s", buf);
+    return code;
+}
+
+int cuda_error(cudaError_t e, const char *what, const char *file, int line) {
+    const char *base = strrchr(file, '/');
+    const int code = (e == cudaErrorNoDevice || e == cudaErrorInsufficientDriver || e == cudaErrorNoKernelImageForDevice)
+                         ? SS_ERR_NO_DEVICE
+                         : (e == cudaErrorMemoryAllocation ? SS_ERR_OUT_OF_MEMORY : SS_ERR_CUDA);
+    return set_error(code, "CUDA error %d (%s) in %s at %s:%d", static_cast<int>(e), cudaGetErrorString(e), what,
+                     base ? base + 1 : file, line);
+}
+
+int ctx_bind(ss_ctx *ctx) {
+    if (ctx == nullptr) return set_error(SS_ERR_INVALID_ARG, "null context");
+    SS_CUDA(cudaSetDevice(ctx->device));
+    return SS_OK;
+}
+
+int ctx_scratch(ss_ctx *ctx, size_t bytes, void **out) {
+    if (bytes > ctx->scratch_bytes) {
+        // the old block may still be in use by queued kernels: drain before freeing
+        SS_CUDA(cudaStreamSynchronize(ctx->stream));
+        if (ctx->scratch) SS_CUDA(cudaFree(ctx->scratch));
+        ctx->scratch = nullptr;
+        ctx->scratch_bytes = 0;
+        size_t want = bytes < (1u << 20) ? (1u << 20) : bytes;
+        SS_CUDA(cudaMalloc(&ctx->scratch, want));
+        ctx->scratch_bytes = want;
+    }
+    *out = ctx->scratch;
+    return SS_OK;
+}
+
+static int pipeline_init(ss_ctx *ctx) {
+    if (ctx->pipeline_ready) return SS_OK;
+    SS_CUDA(cudaStreamCreateWithFlags(&ctx->h2d_stream, cudaStreamNonBlocking));
+    SS_CUDA(cudaStreamCreateWithFlags(&ctx->d2h_stream, cudaStreamNonBlocking));
+    for (int i = 0; i < ss_ctx::kStages; ++i) {
+        SS_CUDA(cudaEventCreateWithFlags(&ctx->ev_h2d[i], cudaEventDisableTiming));
+        SS_CUDA(cudaEventCreateWithFlags(&ctx->ev_kernel[i], cudaEventDisableTiming));
+        SS_CUDA(cudaEventCreateWithFlags(&ctx->ev_done[i], cudaEventDisableTiming));
+    }
+    ctx->pipeline_ready = true;
+    return SS_OK;
+}
+
+static int pipeline_staging(ss_ctx *ctx, size_t in_bytes, size_t out_bytes) {
+    SS_TRY(pipeline_init(ctx));
+    if (in_bytes > ctx->stage_in_bytes) {
+        for (int i = 0; i < ss_ctx::kStages; ++i) {
+            if (ctx->stage_in[i]) SS_CUDA(cudaFree(ctx->stage_in[i]));
+            ctx->stage_in[i] = nullptr;
+            SS_CUDA(cudaMalloc(&ctx->stage_in[i], in_bytes));
+        }
+        ctx->stage_in_bytes = in_bytes;
+    }
+    if (out_bytes > ctx->stage_out_bytes) {
+        for (int i = 0; i < ss_ctx::kStages; ++i) {
+            if (ctx->stage_out[i]) SS_CUDA(cudaFree(ctx->stage_out[i]));
+            ctx->stage_out[i] = nullptr;
+            SS_CUDA(cudaMalloc(&ctx->stage_out[i], out_bytes));
+        }
+        ctx->stage_out_bytes = out_bytes;
+    }
+    return SS_OK;
+}
+
+// ---- coefficient programs -----------------------------------------------------------------------
+static size_t prog_bytes(int d, int p) { return sizeof(ProgHeader) + size_t(p) * size_t(d) * 8 * 4; }
+
+static void fill_splats(uint32_t *splat, int d, int j, int i, uint8_t c) {
+    for (int k = 0; k < 8; ++k) {
+        const uint32_t b = gf::mul(c, static_cast<uint8_t>(1u << k));
+        splat[(size_t(j) * d + i) * 8 + k] = b * 0x01010101u;
+    }
+}
+
+// program for `present` pattern: outputs = missing data shards (then missing parity unless data_only)
+static void build_decode_program(const gf::Matrix &M, int d, int p, uint32_t present, bool data_only,
+                                 uint8_t *out) {
+    const int t = d + p;
+    memset(out, 0, prog_bytes(d, p));
+    ProgHeader *h = reinterpret_cast<ProgHeader *>(out);
+    uint32_t *splat = reinterpret_cast<uint32_t *>(out + sizeof(ProgHeader));
+    int src[kMaxD], ns = 0;
+    for (int i = 0; i < t && ns < d; ++i)
+        if ((present >> i) & 1u) src[ns++] = i;
+    if (ns < d) { h->valid = 0; return; }        // crate: Error::TooFewShardsPresent
+    h->valid = 1;
+    for (int i = 0; i < d; ++i) h->src[i] = static_cast<uint8_t>(src[i]);
+    gf::Matrix sub(d, d), dec;
+    for (int r = 0; r < d; ++r)
+        for (int c = 0; c < d; ++c) sub.at(r, c) = M.at(src[r], c);
+    if (!sub.inverse(dec)) { h->valid = 0; return; }   // cannot happen for an MDS matrix
+    int n_out = 0;
+    for (int r = 0; r < d; ++r) {
+        if ((present >> r) & 1u) continue;
+        h->dst[n_out] = static_cast<uint8_t>(r);
+        for (int i = 0; i < d; ++i) fill_splats(splat, d, n_out, i, dec.at(r, i));
+        ++n_out;
+    }
+    h->n_missing_data = static_cast<uint8_t>(n_out);
+    if (!data_only) {
+        for (int q = d; q < t; ++q) {
+            if ((present >> q) & 1u) continue;
+            h->dst[n_out] = static_cast<uint8_t>(q);
+            // parity row q over the d sources = M[q] * dec
+            for (int i = 0; i < d; ++i) {
+                uint8_t c = 0;
+                for (int k = 0; k < d; ++k) c ^= gf::mul(M.at(q, k), dec.at(k, i));
+                fill_splats(splat, d, n_out, i, c);
+            }
+            ++n_out;
+        }
+    }
+    h->n_out = static_cast<uint8_t>(n_out);
+}
+
+static void build_encode_program(const gf::Matrix &M, int d, int p, uint8_t *out) {
+    memset(out, 0, prog_bytes(d, p));
+    ProgHeader *h = reinterpret_cast<ProgHeader *>(out);
+    uint32_t *splat = reinterpret_cast<uint32_t *>(out + sizeof(ProgHeader));
+    h->valid = 1;
+    h->n_out = static_cast<uint8_t>(p);
+    for (int i = 0; i < d; ++i) h->src[i] = static_cast<uint8_t>(i);
+    for (int j = 0; j < p; ++j) {
+        h->dst[j] = static_cast<uint8_t>(j);      // relative to the parity base
+        for (int i = 0; i < d; ++i) fill_splats(splat, d, j, i, M.at(d + j, i));
+    }
+}
+
+static int check_shard_args(const ss_rs_coder *c, const void *shards, size_t n_shards, size_t shard_len) {
+    if (c == nullptr || shards == nullptr) return set_error(SS_ERR_INVALID_ARG, "null coder or shard array");
+    const size_t t = size_t(c->d + c->p);
+    if (n_shards < t) return set_error(SS_ERR_TOO_FEW_SHARDS, "too few shards: %zu < %zu", n_shards, t);
+    if (n_shards > t) return set_error(SS_ERR_TOO_MANY_SHARDS, "too many shards: %zu > %zu", n_shards, t);
+    if (shard_len == 0) return set_error(SS_ERR_EMPTY_SHARD, "empty shard");
+    if (shard_len >= 0x7fffffffull / size_t(c->d))
+        return set_error(SS_ERR_INVALID_ARG, "shard too large for one call: %zu bytes", shard_len);
+    return SS_OK;
+}
+
+}  // namespace ssb
+
+using namespace ssb;
+
+// =================================================================================================
+extern "C" {
+
+int ss_version(void) { return SS_VERSION; }
+
+const char *ss_last_error(void) { return g_err; }
+
+const char *ss_strerror(int code) {
+    switch (code) {
+        case SS_OK: return "ok";
+        case SS_ERR_TOO_FEW_SHARDS: return "too few shards";
+        case SS_ERR_TOO_MANY_SHARDS: return "too many shards";
+        case SS_ERR_TOO_FEW_DATA_SHARDS: return "too few data shards";
+        case SS_ERR_TOO_MANY_DATA_SHARDS: return "too many data shards";
+        case SS_ERR_TOO_FEW_PARITY_SHARDS: return "too few parity shards";
+        case SS_ERR_TOO_MANY_PARITY_SHARDS: return "too many parity shards";
+        case SS_ERR_TOO_FEW_BUFFER_SHARDS: return "too few buffer shards";
+        case SS_ERR_TOO_MANY_BUFFER_SHARDS: return "too many buffer shards";
+        case SS_ERR_INCORRECT_SHARD_SIZE: return "incorrect shard size";
+        case SS_ERR_TOO_FEW_SHARDS_PRESENT: return "too few shards present";
+        case SS_ERR_EMPTY_SHARD: return "empty shard";
+        case SS_ERR_INVALID_SHARD_FLAGS: return "invalid shard flags";
+        case SS_ERR_INVALID_INDEX: return "invalid index";
+        case SS_ERR_INVALID_ARG: return "invalid argument";
+        case SS_ERR_UNSUPPORTED: return "unsupported configuration";
+        case SS_ERR_OUT_OF_MEMORY: return "out of device memory";
+        case SS_ERR_NO_DEVICE: return "no usable sm_100 CUDA device (no CPU fallback)";
+        case SS_ERR_CUDA: return "CUDA error";
+        default: return "unknown error";
+    }
+}
+
+// ---- context ------------------------------------------------------------------------------------
+static int ctx_create_common(int device, void *stream, bool borrow, ss_ctx **out) {
+    if (out == nullptr) return set_error(SS_ERR_INVALID_ARG, "null out pointer");
+    *out = nullptr;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0) {
+        cudaGetLastError();
+        return set_error(SS_ERR_NO_DEVICE, "no CUDA device available (%s); this library has no CPU fallback",
+                         e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
+    }
+    if (device < 0 || device >= count) return set_error(SS_ERR_INVALID_ARG, "device %d out of range [0,%d)", device, count);
+    cudaDeviceProp prop;
+    SS_CUDA(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10)
+        return set_error(SS_ERR_NO_DEVICE, "device %d is sm_%d%d; kernels are built for sm_100a only", device, prop.major,
+                         prop.minor);
+    SS_CUDA(cudaSetDevice(device));
+    ss_ctx *ctx = new (std::nothrow) ss_ctx();
+    if (!ctx) return set_error(SS_ERR_OUT_OF_MEMORY, "host allocation failed");
+    ctx->device = device;
+    ctx->sm_count = prop.multiProcessorCount;
+    if (borrow) {
+        ctx->stream = static_cast<cudaStream_t>(stream);
+        ctx->owns_stream = false;
+    } else {
+        e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
+        if (e != cudaSuccess) { delete ctx; return cuda_error(e, "cudaStreamCreateWithFlags", __FILE__, __LINE__); }
+        ctx->owns_stream = true;
+    }
+    *out = ctx;
+    return SS_OK;
+}
+
+int ss_ctx_create(int device, ss_ctx **out) { return ctx_create_common(device, nullptr, false, out); }
+int ss_ctx_create_on_stream(int device, void *cuda_stream, ss_ctx **out) {
+    return ctx_create_common(device, cuda_stream, true, out);
+}
+
+int ss_ctx_destroy(ss_ctx *ctx) {
+    if (ctx == nullptr) return SS_OK;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    if (ctx->pipeline_ready) {
+        cudaStreamSynchronize(ctx->h2d_stream);
+        cudaStreamSynchronize(ctx->d2h_stream);
+        for (int i = 0; i < ss_ctx::kStages; ++i) {
+            cudaEventDestroy(ctx->ev_h2d[i]);
+            cudaEventDestroy(ctx->ev_kernel[i]);
+            cudaEventDestroy(ctx->ev_done[i]);
+        }
+        cudaStreamDestroy(ctx->h2d_stream);
+        cudaStreamDestroy(ctx->d2h_stream);
+    }
+    for (int i = 0; i < ss_ctx::kStages; ++i) {
+        if (ctx->stage_in[i]) cudaFree(ctx->stage_in[i]);
+        if (ctx->stage_out[i]) cudaFree(ctx->stage_out[i]);
+    }
+    if (ctx->scratch) cudaFree(ctx->scratch);
+    if (ctx->owns_stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+    return SS_OK;
+}
+
+int ss_ctx_sync(ss_ctx *ctx) {
+    SS_TRY(ctx_bind(ctx));
+    SS_CUDA(cudaStreamSynchronize(ctx->stream));
+    return SS_OK;
+}
+
+void *ss_ctx_stream(ss_ctx *ctx) { return ctx ? static_cast<void *>(ctx->stream) : nullptr; }
+int ss_ctx_sm_count(ss_ctx *ctx) { return ctx ? ctx->sm_count : 0; }
+uint64_t ss_ctx_launch_count(ss_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+int ss_dev_alloc(ss_ctx *ctx, size_t bytes, void **dptr) {
+    SS_TRY(ctx_bind(ctx));
+    if (dptr == nullptr) return set_error(SS_ERR_INVALID_ARG, "null out pointer");
+    SS_CUDA(cudaMalloc(dptr, bytes ? bytes : 1));
+    return SS_OK;
+}
+int ss_dev_free(ss_ctx *ctx, void *dptr) {
+    SS_TRY(ctx_bind(ctx));
+    SS_CUDA(cudaFree(dptr));
+    return SS_OK;
+}
+int ss_dev_memset(ss_ctx *ctx, void *dptr, int value, size_t bytes) {
+    SS_TRY(ctx_bind(ctx));
+    SS_CUDA(cudaMemsetAsync(dptr, value, bytes, ctx->stream));
+    return SS_OK;
+}
+int ss_host_alloc(ss_ctx *ctx, size_t bytes, void **hptr) {
+    SS_TRY(ctx_bind(ctx));
+    if (hptr == nullptr) return set_error(SS_ERR_INVALID_ARG, "null out pointer");
+    SS_CUDA(cudaHostAlloc(hptr, bytes ? bytes : 1, cudaHostAllocDefault));
+    return SS_OK;
+}
+int ss_host_free(ss_ctx *ctx, void *hptr) {
+    SS_TRY(ctx_bind(ctx));
+    SS_CUDA(cudaFreeHost(hptr));
+    return SS_OK;
+}
+int ss_copy_h2d(ss_ctx *ctx, void *dst_dev, const void *src_host, size_t bytes) {
+    SS_TRY(ctx_bind(ctx));
+    SS_CUDA(cudaMemcpyAsync(dst_dev, src_host, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    return SS_OK;
+}
+int ss_copy_d2h(ss_ctx *ctx, void *dst_host, const void *src_dev, size_t bytes) {
+    SS_TRY(ctx_bind(ctx));
+    SS_CUDA(cudaMemcpyAsync(dst_host, src_dev, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    return SS_OK;
+}
+
+// ---- coder --------------------------------------------------------------------------------------
+int ss_rs_coder_create(ss_ctx *ctx, int d, int p, ss_rs_coder **out) {
+    if (out == nullptr) return set_error(SS_ERR_INVALID_ARG, "null out pointer");
+    *out = nullptr;
+    SS_TRY(ctx_bind(ctx));
+    // crate ReedSolomon::new error order
+    if (d <= 0) return set_error(SS_ERR_TOO_FEW_DATA_SHARDS, "too few data shards: %d", d);
+    if (p <= 0) return set_error(SS_ERR_TOO_FEW_PARITY_SHARDS, "too few parity shards: %d", p);
+    if (d + p > 256) return set_error(SS_ERR_TOO_MANY_SHARDS, "too many shards: %d + %d > 256", d, p);
+    ss_rs_coder *c = new (std::nothrow) ss_rs_coder();
+    if (!c) return set_error(SS_ERR_OUT_OF_MEMORY, "host allocation failed");
+    c->ctx = ctx; c->d = d; c->p = p;
+    gf::Matrix M;
+    try {
+        M = gf::coding_matrix(d, p);
+    } catch (const std::exception &ex) {
+        delete c;
+        return set_error(SS_ERR_INVALID_ARG, "matrix construction failed: %s", ex.what());
+    }
+    c->matrix = M.v;
+    c->is_rs32 = (d == 3 && p == 2 && M.at(3, 0) == 1 && M.at(3, 1) == 1 && M.at(3, 2) == 1 && M.at(4, 0) == 0x0f &&
+                  M.at(4, 1) == 0x08 && M.at(4, 2) == 0x06);
+    c->batch_ok = (d <= kMaxD && p <= kMaxP);
+    c->dec_ok = c->batch_ok && (d + p <= 12);
+    c->prog_stride = prog_bytes(d, p);
+    if (c->batch_ok) {
+        std::vector<uint8_t> buf(c->prog_stride);
+        build_encode_program(M, d, p, buf.data());
+        cudaError_t e = cudaMalloc(&c->enc_prog, buf.size());
+        if (e == cudaSuccess) e = cudaMemcpy(c->enc_prog, buf.data(), buf.size(), cudaMemcpyHostToDevice);
+        if (e != cudaSuccess) { ss_rs_coder_destroy(c); return cuda_error(e, "upload encode program", __FILE__, __LINE__); }
+    }
+    if (c->dec_ok) {
+        const size_t npat = size_t(1) << (d + p);
+        std::vector<uint8_t> all(npat * c->prog_stride), dat(npat * c->prog_stride);
+        for (size_t pat = 0; pat < npat; ++pat) {
+            build_decode_program(M, d, p, static_cast<uint32_t>(pat), false, all.data() + pat * c->prog_stride);
+            build_decode_program(M, d, p, static_cast<uint32_t>(pat), true, dat.data() + pat * c->prog_stride);
+        }
+        cudaError_t e = cudaMalloc(&c->dec_progs, all.size());
+        if (e == cudaSuccess) e = cudaMalloc(&c->dec_progs_data, dat.size());
+        if (e == cudaSuccess) e = cudaMemcpy(c->dec_progs, all.data(), all.size(), cudaMemcpyHostToDevice);
+        if (e == cudaSuccess) e = cudaMemcpy(c->dec_progs_data, dat.data(), dat.size(), cudaMemcpyHostToDevice);
+        if (e != cudaSuccess) { ss_rs_coder_destroy(c); return cuda_error(e, "upload decode programs", __FILE__, __LINE__); }
+    }
+    *out = c;
+    return SS_OK;
+}
+
+int ss_rs_coder_destroy(ss_rs_coder *c) {
+    if (c == nullptr) return SS_OK;
+    if (c->ctx) {
+        cudaSetDevice(c->ctx->device);
+        cudaStreamSynchronize(c->ctx->stream);
+    }
+    if (c->enc_prog) cudaFree(c->enc_prog);
+    if (c->dec_progs) cudaFree(c->dec_progs);
+    if (c->dec_progs_data) cudaFree(c->dec_progs_data);
+    delete c;
+    return SS_OK;
+}
+
+int ss_rs_data_shard_count(const ss_rs_coder *c) { return c ? c->d : 0; }
+int ss_rs_parity_shard_count(const ss_rs_coder *c) { return c ? c->p : 0; }
+int ss_rs_total_shard_count(const ss_rs_coder *c) { return c ? c->d + c->p : 0; }
+int ss_rs_coder_matrix(const ss_rs_coder *c, uint8_t *out) {
+    if (c == nullptr || out == nullptr) return set_error(SS_ERR_INVALID_ARG, "null argument");
+    memcpy(out, c->matrix.data(), c->matrix.size());
+    return SS_OK;
+}
+int ss_rs_set_variant(ss_rs_coder *c, int variant) {
+    if (c == nullptr) return set_error(SS_ERR_INVALID_ARG, "null coder");
+    c->variant = variant;
+    return SS_OK;
+}
+const char *ss_rs_last_kernel(const ss_rs_coder *c) { return c ? c->last_kernel : "none"; }
+
+// ---- one codeword, host slices --------------------------------------------------------------------
+// Device layout used for single-codeword calls: shard j at scratch + j*ds, ds = round_up(L,16).
+int ss_rs_encode(ss_rs_coder *c, uint8_t *const *shards, size_t n_shards, size_t shard_len) {
+    SS_TRY(check_shard_args(c, shards, n_shards, shard_len));
+    ss_ctx *ctx = c->ctx;
+    SS_TRY(ctx_bind(ctx));
+    const int d = c->d, p = c->p;
+    const size_t L = shard_len, ds = (L + 15) & ~size_t(15);
+    const size_t par_at = (size_t(d) * L + 255) & ~size_t(255);
+    void *scr = nullptr;
+    SS_TRY(ctx_scratch(ctx, par_at + size_t(p) * ds, &scr));
+    uint8_t *d_data = static_cast<uint8_t *>(scr);
+    uint8_t *d_par = d_data + par_at;
+    for (int i = 0; i < d; ++i)
+        SS_CUDA(cudaMemcpyAsync(d_data + size_t(i) * L, shards[i], L, cudaMemcpyHostToDevice, ctx->stream));
+    EncGeom g{};
+    g.data = d_data; g.data_off = nullptr; g.data_len = nullptr; g.data_stride = size_t(d) * L;
+    g.uni_len = static_cast<uint32_t>(size_t(d) * L);
+    g.parity = d_par; g.plane_stride = ds; g.par_off = nullptr; g.shard_stride = ds; g.n = 1;
+    g.flags = SS_RS_OUT_PADDED16;
+    SS_TRY(launch_rs_encode(c, g, nullptr));
+    for (int j = 0; j < p; ++j)
+        SS_CUDA(cudaMemcpyAsync(shards[d + j], d_par + size_t(j) * ds, L, cudaMemcpyDeviceToHost, ctx->stream));
+    SS_CUDA(cudaStreamSynchronize(ctx->stream));
+    return SS_OK;
+}
+
+static int reconstruct_one(ss_rs_coder *c, uint8_t *const *shards, uint8_t *present, size_t n_shards,
+                           size_t shard_len, int data_only) {
+    SS_TRY(check_shard_args(c, shards, n_shards, shard_len));
+    if (present == nullptr) return set_error(SS_ERR_INVALID_ARG, "null present array");
+    ss_ctx *ctx = c->ctx;
+    SS_TRY(ctx_bind(ctx));
+    const int d = c->d, p = c->p, t = d + p;
+    int np = 0;
+    for (int i = 0; i < t; ++i) np += present[i] ? 1 : 0;
+    if (np == t) return SS_OK;                       // crate: nothing to do
+    if (np < d) return set_error(SS_ERR_TOO_FEW_SHARDS_PRESENT, "too few shards present: %d < %d", np, d);
+    if (!c->dec_ok)
+        return set_error(SS_ERR_UNSUPPORTED, "reconstruct needs d+p <= 12 on this build (coder is %d,%d)", d, p);
+    const size_t L = shard_len, ds = (L + 15) & ~size_t(15);
+    const size_t meta = 256;
+    void *scr = nullptr;
+    SS_TRY(ctx_scratch(ctx, meta + size_t(t) * ds, &scr));
+    uint8_t *d_meta = static_cast<uint8_t *>(scr);
+    uint8_t *d_sh = d_meta + meta;
+    uint32_t pat = 0;
+    for (int i = 0; i < t; ++i)
+        if (present[i]) pat |= 1u << i;
+    struct { uint64_t off; uint32_t len; uint32_t pat; int32_t status; } h = {0, static_cast<uint32_t>(size_t(d) * L), pat, 0};
+    SS_CUDA(cudaMemcpyAsync(d_meta, &h, sizeof(h), cudaMemcpyHostToDevice, ctx->stream));
+    for (int i = 0; i < t; ++i)
+        if (present[i])
+            SS_CUDA(cudaMemcpyAsync(d_sh + size_t(i) * ds, shards[i], L, cudaMemcpyHostToDevice, ctx->stream));
+    SS_TRY(launch_rs_reconstruct(c, d_sh, ds, reinterpret_cast<const uint64_t *>(d_meta),
+                                 reinterpret_cast<const uint32_t *>(d_meta + 8),
+                                 reinterpret_cast<const uint32_t *>(d_meta + 12), 1, data_only,
+                                 reinterpret_cast<int32_t *>(d_meta + 16), SS_RS_OUT_PADDED16));
+    const int upto = data_only ? d : t;
+    for (int i = 0; i < upto; ++i)
+        if (!present[i])
+            SS_CUDA(cudaMemcpyAsync(shards[i], d_sh + size_t(i) * ds, L, cudaMemcpyDeviceToHost, ctx->stream));
+    SS_CUDA(cudaStreamSynchronize(ctx->stream));
+    for (int i = 0; i < upto; ++i) present[i] = 1;
+    return SS_OK;
+}
+
+int ss_rs_reconstruct(ss_rs_coder *c, uint8_t *const *shards, uint8_t *present, size_t n_shards, size_t shard_len) {
+    return reconstruct_one(c, shards, present, n_shards, shard_len, 0);
+}
+int ss_rs_reconstruct_data(ss_rs_coder *c, uint8_t *const *shards, uint8_t *present, size_t n_shards,
+                           size_t shard_len) {
+    return reconstruct_one(c, shards, present, n_shards, shard_len, 1);
+}
+
+int ss_rs_verify(ss_rs_coder *c, const uint8_t *const *shards, size_t n_shards, size_t shard_len, int *ok) {
+    SS_TRY(check_shard_args(c, shards, n_shards, shard_len));
+    if (ok == nullptr) return set_error(SS_ERR_INVALID_ARG, "null ok pointer");
+    const int d = c->d, p = c->p;
+    std::vector<std::vector<uint8_t>> par(p, std::vector<uint8_t>(shard_len));
+    std::vector<uint8_t *> tmp(d + p);
+    for (int i = 0; i < d; ++i) tmp[i] = const_cast<uint8_t *>(shards[i]);
+    for (int j = 0; j < p; ++j) tmp[d + j] = par[j].data();
+    SS_TRY(ss_rs_encode(c, tmp.data(), n_shards, shard_len));    // parity recomputed on the GPU
+    *ok = 1;
+    for (int j = 0; j < p; ++j)
+        if (memcmp(par[j].data(), shards[d + j], shard_len) != 0) { *ok = 0; break; }
+    return SS_OK;
+}
+
+// ---- batched, device-resident ---------------------------------------------------------------------
+int ss_rs_encode_batch_dev(ss_rs_coder *c, const uint8_t *data, const uint64_t *data_off, const uint32_t *data_len,
+                           uint64_t n, uint8_t *parity, uint64_t plane_stride, const uint64_t *par_off, uint32_t flags) {
+    if (c == nullptr) return set_error(SS_ERR_INVALID_ARG, "null coder");
+    if (n == 0) return SS_OK;
+    if (!data || !data_off || !data_len || !parity || !par_off) return set_error(SS_ERR_INVALID_ARG, "null buffer");
+    EncGeom g{};
+    g.data = data; g.data_off = data_off; g.data_len = data_len; g.parity = parity; g.plane_stride = plane_stride;
+    g.par_off = par_off; g.n = n; g.flags = flags;
+    return launch_rs_encode(c, g, nullptr);
+}
+
+int ss_rs_encode_uniform_dev(ss_rs_coder *c, const uint8_t *data, uint64_t data_stride, uint32_t data_len, uint64_t n,
+                             uint8_t *parity, uint64_t plane_stride, uint64_t shard_stride, uint32_t flags) {
+    if (c == nullptr) return set_error(SS_ERR_INVALID_ARG, "null coder");
+    if (n == 0 || data_len == 0) return SS_OK;
+    if (!data || !parity) return set_error(SS_ERR_INVALID_ARG, "null buffer");
+    EncGeom g{};
+    g.data = data; g.data_off = nullptr; g.data_stride = data_stride; g.uni_len = data_len; g.parity = parity;
+    g.plane_stride = plane_stride; g.shard_stride = shard_stride; g.n = n; g.flags = flags;
+    return launch_rs_encode(c, g, nullptr);
+}
+
+int ss_rs_reconstruct_batch_dev(ss_rs_coder *c, uint8_t *shards, uint64_t plane_stride, const uint64_t *off,
+                                const uint32_t *data_len, const uint32_t *present, uint64_t n, int data_only,
+                                int32_t *status, uint32_t flags) {
+    if (c == nullptr) return set_error(SS_ERR_INVALID_ARG, "null coder");
+    if (n == 0) return SS_OK;
+    if (!shards || !off || !data_len || !present || !status) return set_error(SS_ERR_INVALID_ARG, "null buffer");
+    return launch_rs_reconstruct(c, shards, plane_stride, off, data_len, present, n, data_only, status, flags);
+}
+
+int ss_accept_step_fused_dev(ss_rs_coder *c, const uint8_t *data, uint64_t data_stride, uint32_t data_len,
+                             uint64_t n_groups, uint8_t *parity, uint64_t plane_stride, uint64_t shard_stride,
+                             uint32_t flags, const uint64_t *planes, uint32_t n_replicas, uint32_t threshold,
+                             uint64_t *committed, uint32_t *commit_bar) {
+    if (c == nullptr) return set_error(SS_ERR_INVALID_ARG, "null coder");
+    if (n_groups == 0) return SS_OK;
+    if (!data || !parity || !planes || !committed) return set_error(SS_ERR_INVALID_ARG, "null buffer");
+    if (n_replicas == 0 || n_replicas > 16) return set_error(SS_ERR_INVALID_ARG, "n_replicas must be 1..16");
+    EncGeom g{};
+    g.data = data; g.data_off = nullptr; g.data_stride = data_stride; g.uni_len = data_len; g.parity = parity;
+    g.plane_stride = plane_stride; g.shard_stride = shard_stride; g.n = n_groups; g.flags = flags;
+    TallyArgs t;
+    t.planes = planes; t.R = n_replicas; t.threshold = threshold; t.G = n_groups; t.committed = committed;
+    t.commit_bar = commit_bar;
+    return launch_rs_encode(c, g, &t);
+}
+
+// ---- host-buffer batch encode: chunked, copy/compute overlapped -----------------------------------
+int ss_rs_encode_uniform(ss_rs_coder *c, const uint8_t *data, uint64_t data_stride, uint32_t data_len, uint64_t n,
+                         uint8_t *parity, uint64_t plane_stride, uint64_t shard_stride) {
+    if (c == nullptr) return set_error(SS_ERR_INVALID_ARG, "null coder");
+    if (n == 0 || data_len == 0) return SS_OK;
+    if (!data || !parity) return set_error(SS_ERR_INVALID_ARG, "null buffer");
+    ss_ctx *ctx = c->ctx;
+    SS_TRY(ctx_bind(ctx));
+    const int d = c->d, p = c->p;
+    const uint64_t L = (uint64_t(data_len) + d - 1) / d, ds = (L + 15) & ~uint64_t(15);
+    if (data_stride < data_len || shard_stride < L) return set_error(SS_ERR_INVALID_ARG, "stride shorter than element");
+    // chunk: ~64 MiB of payload
+    uint64_t C = (64ull << 20) / data_stride;
+    if (C < 1) C = 1;
+    if (C > n) C = n;
+    const uint64_t in_stride_dev = (data_stride + 15) & ~uint64_t(15);
+    const bool in_contig = (in_stride_dev == data_stride);
+    SS_TRY(pipeline_staging(ctx, C * in_stride_dev + 256, uint64_t(p) * C * ds));
+    const uint64_t nchunks = (n + C - 1) / C;
+    for (uint64_t k = 0; k < nchunks; ++k) {
+        const int b = static_cast<int>(k % ss_ctx::kStages);
+        const uint64_t g0 = k * C, nc = (n - g0) < C ? (n - g0) : C;
+        uint8_t *din = static_cast<uint8_t *>(ctx->stage_in[b]);
+        uint8_t *dout = static_cast<uint8_t *>(ctx->stage_out[b]);
+        if (k >= ss_ctx::kStages) SS_CUDA(cudaStreamWaitEvent(ctx->h2d_stream, ctx->ev_done[b], 0));
+        if (in_contig)
+            SS_CUDA(cudaMemcpyAsync(din, data + g0 * data_stride, nc * data_stride, cudaMemcpyHostToDevice, ctx->h2d_stream));
+        else
+            SS_CUDA(cudaMemcpy2DAsync(din, in_stride_dev, data + g0 * data_stride, data_stride, data_len, nc,
+                                      cudaMemcpyHostToDevice, ctx->h2d_stream));
+        SS_CUDA(cudaEventRecord(ctx->ev_h2d[b], ctx->h2d_stream));
+        SS_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_h2d[b], 0));
+        EncGeom g{};
+        g.data = din; g.data_off = nullptr; g.data_stride = in_stride_dev; g.uni_len = data_len; g.parity = dout;
+        g.plane_stride = C * ds; g.shard_stride = ds; g.n = nc; g.flags = SS_RS_OUT_PADDED16;
+        SS_TRY(launch_rs_encode(c, g, nullptr));
+        SS_CUDA(cudaEventRecord(ctx->ev_kernel[b], ctx->stream));
+        SS_CUDA(cudaStreamWaitEvent(ctx->d2h_stream, ctx->ev_kernel[b], 0));
+        for (int j = 0; j < p; ++j) {
+            uint8_t *hdst = parity + uint64_t(j) * plane_stride + g0 * shard_stride;
+            const uint8_t *dsrc = dout + uint64_t(j) * C * ds;
+            if (shard_stride == ds)
+                SS_CUDA(cudaMemcpyAsync(hdst, dsrc, nc * ds, cudaMemcpyDeviceToHost, ctx->d2h_stream));
+            else
+                SS_CUDA(cudaMemcpy2DAsync(hdst, shard_stride, dsrc, ds, L, nc, cudaMemcpyDeviceToHost, ctx->d2h_stream));
+        }
+        SS_CUDA(cudaEventRecord(ctx->ev_done[b], ctx->d2h_stream));
+    }
+    SS_CUDA(cudaStreamSynchronize(ctx->d2h_stream));
+    SS_CUDA(cudaStreamSynchronize(ctx->stream));
+    return SS_OK;
+}
+
+// ---- tallies ----------------------------------------------------------------------------------------
+int ss_tally_planes_dev(ss_ctx *ctx, const uint64_t *planes, uint32_t R, uint64_t G, uint32_t thr, uint64_t *committed,
+                        uint32_t *commit_bar) {
+    if (ctx == nullptr) return set_error(SS_ERR_INVALID_ARG, "null context");
+    if (G == 0) return SS_OK;
+    if (!planes || !committed) return set_error(SS_ERR_INVALID_ARG, "null buffer");
+    return launch_tally_planes(ctx, planes, R, G, thr, committed, commit_bar);
+}
+
+int ss_tally_planes(ss_ctx *ctx, const uint64_t *planes, uint32_t R, uint64_t G, uint32_t thr, uint64_t *committed,
+                    uint32_t *commit_bar) {
+    if (ctx == nullptr) return set_error(SS_ERR_INVALID_ARG, "null context");
+    if (G == 0) return SS_OK;
+    if (!planes || !committed) return set_error(SS_ERR_INVALID_ARG, "null buffer");
+    SS_TRY(ctx_bind(ctx));
+    const size_t in_b = size_t(R) * G * 8, out_b = G * 8, bar_b = commit_bar ? G * 4 : 0;
+    void *scr = nullptr;
+    SS_TRY(ctx_scratch(ctx, in_b + out_b + bar_b, &scr));
+    uint64_t *d_pl = static_cast<uint64_t *>(scr);
+    uint64_t *d_cm = d_pl + size_t(R) * G;
+    uint32_t *d_bar = commit_bar ? reinterpret_cast<uint32_t *>(d_cm + G) : nullptr;
+    SS_CUDA(cudaMemcpyAsync(d_pl, planes, in_b, cudaMemcpyHostToDevice, ctx->stream));
+    SS_TRY(launch_tally_planes(ctx, d_pl, R, G, thr, d_cm, d_bar));
+    SS_CUDA(cudaMemcpyAsync(committed, d_cm, out_b, cudaMemcpyDeviceToHost, ctx->stream));
+    if (commit_bar) SS_CUDA(cudaMemcpyAsync(commit_bar, d_bar, bar_b, cudaMemcpyDeviceToHost, ctx->stream));
+    SS_CUDA(cudaStreamSynchronize(ctx->stream));
+    return SS_OK;
+}
+
+int ss_tally_masks_dev(ss_ctx *ctx, const void *masks, uint32_t mask_bytes, uint64_t n, uint32_t thr,
+                       uint64_t *commit_bits) {
+    if (ctx == nullptr) return set_error(SS_ERR_INVALID_ARG, "null context");
+    if (n == 0) return SS_OK;
+    if (!masks || !commit_bits) return set_error(SS_ERR_INVALID_ARG, "null buffer");
+    return launch_tally_masks(ctx, masks, mask_bytes, n, thr, commit_bits);
+}
+
+int ss_ack_ingest_dev(ss_ctx *ctx, const uint32_t *rec_group, const uint8_t *rec_slot, const uint8_t *rec_peer,
+                      const uint64_t *rec_ballot, uint64_t n_records, const uint64_t *bal_prepared,
+                      const uint64_t *inst_bal, const uint64_t *accepting, uint32_t R, uint64_t G, uint64_t *planes) {
+    if (ctx == nullptr) return set_error(SS_ERR_INVALID_ARG, "null context");
+    if (n_records == 0) return SS_OK;
+    if (!rec_group || !rec_slot || !rec_peer || !rec_ballot || !bal_prepared || !inst_bal || !accepting || !planes)
+        return set_error(SS_ERR_INVALID_ARG, "null buffer");
+    return launch_ack_ingest(ctx, rec_group, rec_slot, rec_peer, rec_ballot, n_records, bal_prepared, inst_bal,
+                             accepting, R, G, planes);
+}
+
+int ss_tally_crossword_dev(ss_ctx *ctx, const void *masks, uint32_t mask_bytes, const uint8_t *policy_idx, uint64_t n,
+                           const uint32_t *policies_host, uint32_t n_policies, uint32_t n_replicas, uint32_t T,
+                           uint32_t d, uint32_t majority, uint32_t f, int balanced, uint64_t *commit_bits) {
+    if (ctx == nullptr) return set_error(SS_ERR_INVALID_ARG, "null context");
+    if (n == 0) return SS_OK;
+    if (!masks || !policy_idx || !policies_host || !commit_bits) return set_error(SS_ERR_INVALID_ARG, "null buffer");
+    return launch_tally_crossword(ctx, masks, mask_bytes, policy_idx, n, policies_host, n_policies, n_replicas, T, d,
+                                  majority, f, balanced, commit_bits);
+}
+
+int ss_raft_commit_scan_dev(ss_ctx *ctx, const uint32_t *match, uint32_t n_peers, uint64_t G,
+                            const uint32_t *last_commit, const uint32_t *log_end, const uint32_t *curr_term,
+                            const uint32_t *terms, uint32_t window, uint32_t threshold, uint32_t *new_commit) {
+    if (ctx == nullptr) return set_error(SS_ERR_INVALID_ARG, "null context");
+    if (G == 0) return SS_OK;
+    if ((!match && n_peers) || !last_commit || !log_end || !curr_term || !terms || !new_commit)
+        return set_error(SS_ERR_INVALID_ARG, "null buffer");
+    return launch_raft_scan(ctx, match, n_peers, G, last_commit, log_end, curr_term, terms, window, threshold,
+                            new_commit);
+}
+
+}  // extern "C"

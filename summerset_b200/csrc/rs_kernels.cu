@@ -1,0 +1,446 @@
+// rs_kernels.cu -- Reed-Solomon GF(2^8) shard encode / reconstruct kernels for sm_100a.
+//
+// What they replace (reference, josehu07/summerset @ 1daf80aa):
+//   RSCodeword::from_data split + compute_parity  src/utils/rscoding.rs:165-243,447-486
+//     -> crate ReedSolomon::encode (rscoding.rs:484): parity_j = sum_i M[d+j][i] * data_i
+//   RSCodeword::reconstruct_data / reconstruct_all src/utils/rscoding.rs:490-537
+//     -> crate ReedSolomon::reconstruct{,_data} (rscoding.rs:515,517)
+// executed for millions of codewords per launch instead of one per event-loop turn
+// (rspaxos/request.rs:72-77, crossword/request.rs:82-87, rspaxos/durability.rs:146-159).
+//
+// This is HBM-bound byte work: no tensor cores.  Design points:
+//   * a thread owns one 16-byte "column" of a codeword: it reads the 16 bytes at the same offset
+//     of each of the d source shards (128-bit loads; shards of a contiguous split are generally
+//     misaligned w.r.t. 16 bytes, handled with two aligned loads + a byte funnel shift whose
+//     second load is an L1 hit on the neighbour lane's data) and writes 16 bytes of each output
+//     shard with one 128-bit streaming store;
+//   * GF multiplication is done on four packed field elements per 32-bit register with
+//     prmt/lop3/shift only -- no table, no shared-memory gathers:
+//       - RS(3,2), the code of every 5-replica RSPaxos/Crossword/CRaft deployment, is specialised:
+//         parity0 = a^b^c, parity1 = 0f*a ^ 08*b ^ 06*c evaluated by Horner's rule in x
+//         ( ((a^b)*x ^ (a^c))*x ^ (a^c))*x ^ a ): three packed xtime steps per word;
+//       - every other (d,p) and every reconstruction runs the generic kernel: each source word is
+//         expanded into its 8 bit-planes (byte masks via prmt sign replication) and accumulated
+//         into each output as mask_k & splat(c*2^k); the splats come from a small per-program
+//         coefficient table (one program per erasure pattern, built on the host at coder creation);
+//   * uniform geometry (all codewords the same length) maps threads to columns with a flat index,
+//     so no lane idles on codeword tails; ragged geometry gives each warp whole codewords.
+#include <cstring>
+
+#include "device_common.cuh"
+#include "ss_internal.hpp"
+
+namespace ssb {
+
+using dev::keep_bytes;
+using dev::load16;
+using dev::msb_mask;
+using dev::store16;
+using dev::xtime4;
+
+constexpr int kThreads = 256;
+
+// ------------------------------------------------------------------------------------------------
+// compute cores
+// ------------------------------------------------------------------------------------------------
+
+// RS(3,2): parity rows {01 01 01}, {0f 08 06} (checked on the host against the coder's matrix).
+__device__ __forceinline__ void rs32_word(uint32_t a, uint32_t b, uint32_t c, uint32_t &p0,
+                                          uint32_t &p1) {
+    const uint32_t t = a ^ b;
+    const uint32_t u = a ^ c;
+    p0 = t ^ c;
+    uint32_t r = xtime4(t) ^ u;
+    r = xtime4(r) ^ u;
+    p1 = xtime4(r) ^ a;
+}
+
+__device__ __forceinline__ void rs32_column(const uint8_t *src, uint32_t len, uint32_t L, uint32_t k,
+                                            uint8_t *out, uint64_t plane_stride, bool padded, bool emit_data) {
+    const int64_t rem = static_cast<int64_t>(len) - static_cast<int64_t>(k);
+    auto nv = [](int64_t r) { return r > 16 ? 16 : (r < 0 ? 0 : static_cast<int>(r)); };
+    const uint4 a = load16(src + k, nv(rem));
+    const uint4 b = load16(src + static_cast<uint64_t>(L) + k, nv(rem - L));
+    const uint4 c = load16(src + 2ull * L + k, nv(rem - 2ll * L));
+    uint4 p0, p1;
+    rs32_word(a.x, b.x, c.x, p0.x, p1.x);
+    rs32_word(a.y, b.y, c.y, p0.y, p1.y);
+    rs32_word(a.z, b.z, c.z, p0.z, p1.z);
+    rs32_word(a.w, b.w, c.w, p0.w, p1.w);
+    const int onv = static_cast<int>(L - k) > 16 ? 16 : static_cast<int>(L - k);
+    store16(out + k, p0, onv, padded);
+    store16(out + plane_stride + k, p1, onv, padded);
+    if (emit_data) {   // data shards copied into planes 0..2 of the shard store (pack-for-send, rscoding.rs:255-293)
+        store16(out - 3 * plane_stride + k, a, onv, padded);
+        store16(out - 2 * plane_stride + k, b, onv, padded);
+        store16(out - 1 * plane_stride + k, c, onv, padded);
+    }
+}
+
+// Generic bit-plane core: acc[j] ^= sum over bits k of (mask_k(x_i) & splat(c_ji * 2^k)).
+template <int P>
+__device__ __forceinline__ void bitplane_accumulate(const uint4 &x, const uint32_t *__restrict__ splat_i,
+                                                    int d, int n_out, uint4 (&acc)[P]) {
+    // splat_i points at splat[(0*d + i)*8]; output j is at + j*d*8
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        const int sh = 7 - k;
+        const uint4 m = make_uint4(msb_mask(x.x << sh), msb_mask(x.y << sh), msb_mask(x.z << sh),
+                                   msb_mask(x.w << sh));
+#pragma unroll
+        for (int j = 0; j < P; ++j) {
+            if (j < n_out) {
+                const uint32_t c = __ldg(splat_i + j * d * 8 + k);
+                acc[j].x ^= m.x & c;
+                acc[j].y ^= m.y & c;
+                acc[j].z ^= m.z & c;
+                acc[j].w ^= m.w & c;
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// encode kernels
+// ------------------------------------------------------------------------------------------------
+struct EncUniform {
+    const uint8_t *data;
+    uint64_t data_stride;
+    uint32_t len, L, vpc;
+    uint8_t *parity;
+    uint64_t plane_stride, shard_stride;
+    uint64_t n;
+    uint32_t total;   // n * vpc (host guarantees it fits 32 bits per launch)
+    uint32_t padded;  // bit0: SS_RS_OUT_PADDED16, bit1: SS_RS_EMIT_DATA
+    // fused tally (planes == nullptr: none)
+    const uint64_t *planes;
+    uint32_t R, threshold;
+    uint64_t G;
+    uint64_t *committed;
+    uint32_t *commit_bar;
+};
+
+__global__ void __launch_bounds__(kThreads) rs32_encode_uniform_kernel(const __grid_constant__ EncUniform P) {
+    const uint32_t t = blockIdx.x * kThreads + threadIdx.x;
+    if (P.planes != nullptr && t < P.G) {
+        const uint64_t w = dev::tally_word(P.planes, P.R, P.G, t, P.threshold);
+        P.committed[t] = w;
+        if (P.commit_bar != nullptr) P.commit_bar[t] = dev::commit_prefix(w);
+    }
+    if (t >= P.total) return;
+    const uint32_t g = t / P.vpc;
+    const uint32_t k = (t - g * P.vpc) * 16u;
+    rs32_column(P.data + static_cast<uint64_t>(g) * P.data_stride, P.len, P.L, k,
+                P.parity + static_cast<uint64_t>(g) * P.shard_stride, P.plane_stride, (P.padded & 1u) != 0u,
+                (P.padded & 2u) != 0u);
+}
+
+struct EncRagged {
+    const uint8_t *data;
+    const uint64_t *data_off;
+    const uint32_t *data_len;
+    uint8_t *parity;
+    uint64_t plane_stride;
+    const uint64_t *par_off;
+    uint64_t n;
+    uint32_t padded;
+};
+
+__global__ void __launch_bounds__(kThreads) rs32_encode_ragged_kernel(const __grid_constant__ EncRagged P) {
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint64_t warp = (static_cast<uint64_t>(blockIdx.x) * kThreads + threadIdx.x) >> 5;
+    const uint64_t nwarps = (static_cast<uint64_t>(gridDim.x) * kThreads) >> 5;
+    for (uint64_t g = warp; g < P.n; g += nwarps) {
+        const uint32_t len = __ldg(P.data_len + g);
+        if (len == 0u) continue;                      // null codeword (rscoding.rs:451-453)
+        const uint32_t L = (len + 2u) / 3u;           // rscoding.rs:177-181 with d = 3
+        const uint32_t vpc = (L + 15u) >> 4;
+        const uint8_t *src = P.data + __ldg(P.data_off + g);
+        uint8_t *out = P.parity + __ldg(P.par_off + g);
+        for (uint32_t v = lane; v < vpc; v += 32u)
+            rs32_column(src, len, L, v * 16u, out, P.plane_stride, (P.padded & 1u) != 0u, (P.padded & 2u) != 0u);
+    }
+}
+
+// generic encode from the payload arena (any d <= 32, p <= P)
+struct GenArgs {
+    const uint32_t *prog;     // ProgHeader + splats (encode: single program)
+    int d;
+};
+
+template <int P>
+__device__ __forceinline__ void generic_payload_column(const uint8_t *src, uint32_t len, uint32_t L,
+                                                       uint32_t k, uint8_t *out, uint64_t plane_stride,
+                                                       uint32_t oflags, const uint32_t *prog, int d, int p) {
+    const bool padded = (oflags & 1u) != 0u, emit_data = (oflags & 2u) != 0u;
+    const int onv = static_cast<int>(L - k) > 16 ? 16 : static_cast<int>(L - k);
+    const uint32_t *splat = prog + sizeof(ProgHeader) / 4;
+    uint4 acc[P];
+#pragma unroll
+    for (int j = 0; j < P; ++j) acc[j] = make_uint4(0u, 0u, 0u, 0u);
+    for (int i = 0; i < d; ++i) {
+        const int64_t pos = static_cast<int64_t>(i) * L + k;
+        const int64_t rem = static_cast<int64_t>(len) - pos;
+        const int nv = rem > 16 ? 16 : (rem < 0 ? 0 : static_cast<int>(rem));
+        const uint4 x = load16(src + pos, nv);        // nv == 0: zeros, no memory access
+        if (emit_data)
+            store16(out - static_cast<uint64_t>(d - i) * plane_stride + k, x, onv, padded);
+        if (nv == 0) continue;                        // all-zero padding contributes nothing
+        bitplane_accumulate<P>(x, splat + i * 8, d, p, acc);
+    }
+#pragma unroll
+    for (int j = 0; j < P; ++j)
+        if (j < p) store16(out + static_cast<uint64_t>(j) * plane_stride + k, acc[j], onv, padded);
+}
+
+template <int P>
+__global__ void __launch_bounds__(kThreads)
+generic_encode_uniform_kernel(const __grid_constant__ EncUniform E, const uint32_t *__restrict__ prog, int d, int p) {
+    const uint32_t t = blockIdx.x * kThreads + threadIdx.x;
+    if (E.planes != nullptr && t < E.G) {
+        const uint64_t w = dev::tally_word(E.planes, E.R, E.G, t, E.threshold);
+        E.committed[t] = w;
+        if (E.commit_bar != nullptr) E.commit_bar[t] = dev::commit_prefix(w);
+    }
+    if (t >= E.total) return;
+    const uint32_t g = t / E.vpc;
+    const uint32_t k = (t - g * E.vpc) * 16u;
+    generic_payload_column<P>(E.data + static_cast<uint64_t>(g) * E.data_stride, E.len, E.L, k,
+                              E.parity + static_cast<uint64_t>(g) * E.shard_stride, E.plane_stride,
+                              E.padded, prog, d, p);
+}
+
+template <int P>
+__global__ void __launch_bounds__(kThreads)
+generic_encode_ragged_kernel(const __grid_constant__ EncRagged E, const uint32_t *__restrict__ prog, int d, int p) {
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint64_t warp = (static_cast<uint64_t>(blockIdx.x) * kThreads + threadIdx.x) >> 5;
+    const uint64_t nwarps = (static_cast<uint64_t>(gridDim.x) * kThreads) >> 5;
+    for (uint64_t g = warp; g < E.n; g += nwarps) {
+        const uint32_t len = __ldg(E.data_len + g);
+        if (len == 0u) continue;
+        const uint32_t L = (len + static_cast<uint32_t>(d) - 1u) / static_cast<uint32_t>(d);
+        const uint32_t vpc = (L + 15u) >> 4;
+        const uint8_t *src = E.data + __ldg(E.data_off + g);
+        uint8_t *out = E.parity + __ldg(E.par_off + g);
+        for (uint32_t v = lane; v < vpc; v += 32u)
+            generic_payload_column<P>(src, len, L, v * 16u, out, E.plane_stride, E.padded, prog, d, p);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// reconstruct kernel: shards in planes, one coefficient program per erasure pattern
+// ------------------------------------------------------------------------------------------------
+struct DecArgs {
+    uint8_t *shards;
+    uint64_t plane_stride;
+    const uint64_t *off;
+    const uint32_t *data_len;
+    const uint32_t *present;
+    uint64_t n;
+    int32_t *status;
+    const uint8_t *progs;     // 2^(d+p) programs of prog_stride bytes
+    uint32_t prog_stride;
+    uint32_t pattern_mask;
+    int d;
+    uint32_t padded;
+};
+
+template <int P>
+__global__ void __launch_bounds__(kThreads) generic_reconstruct_kernel(const __grid_constant__ DecArgs A) {
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint64_t warp = (static_cast<uint64_t>(blockIdx.x) * kThreads + threadIdx.x) >> 5;
+    const uint64_t nwarps = (static_cast<uint64_t>(gridDim.x) * kThreads) >> 5;
+    const int d = A.d;
+    for (uint64_t g = warp; g < A.n; g += nwarps) {
+        const uint32_t len = __ldg(A.data_len + g);
+        if (len == 0u) {                              // null codeword: rscoding.rs:495-497
+            if (lane == 0u) A.status[g] = SS_ERR_INVALID_ARG;
+            continue;
+        }
+        const uint32_t pat = __ldg(A.present + g) & A.pattern_mask;
+        const uint8_t *prog = A.progs + static_cast<uint64_t>(pat) * A.prog_stride;
+        const ProgHeader *hdr = reinterpret_cast<const ProgHeader *>(prog);
+        const int valid = hdr->valid;
+        const int n_out = hdr->n_out;
+        if (lane == 0u) A.status[g] = valid ? SS_OK : SS_ERR_TOO_FEW_SHARDS_PRESENT;
+        if (!valid || n_out == 0) continue;           // never partial output
+        const uint32_t *splat = reinterpret_cast<const uint32_t *>(prog + sizeof(ProgHeader));
+        const uint32_t L = (len + static_cast<uint32_t>(d) - 1u) / static_cast<uint32_t>(d);
+        const uint32_t vpc = (L + 15u) >> 4;
+        uint8_t *base = A.shards + __ldg(A.off + g);
+        for (uint32_t v = lane; v < vpc; v += 32u) {
+            const uint32_t k = v * 16u;
+            const int nv = static_cast<int>(L - k) > 16 ? 16 : static_cast<int>(L - k);
+            uint4 acc[P];
+#pragma unroll
+            for (int j = 0; j < P; ++j) acc[j] = make_uint4(0u, 0u, 0u, 0u);
+            for (int i = 0; i < d; ++i) {
+                const uint4 x = load16(base + static_cast<uint64_t>(hdr->src[i]) * A.plane_stride + k, nv);
+                bitplane_accumulate<P>(x, splat + i * 8, d, n_out, acc);
+            }
+#pragma unroll
+            for (int j = 0; j < P; ++j)
+                if (j < n_out)
+                    store16(base + static_cast<uint64_t>(hdr->dst[j]) * A.plane_stride + k, acc[j], nv,
+                            A.padded != 0u);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host launchers
+// ------------------------------------------------------------------------------------------------
+static inline uint32_t ragged_grid(ss_ctx *ctx, uint64_t n) {
+    // persistent-ish grid: enough warps to fill the machine several times over, capped by n
+    const uint64_t warps_per_cta = kThreads / 32;
+    uint64_t ctas = (n + warps_per_cta - 1) / warps_per_cta;
+    const uint64_t cap = static_cast<uint64_t>(ctx->sm_count) * 8ull * 4ull;  // 8 CTAs/SM resident x 4 waves
+    if (ctas > cap) ctas = cap;
+    if (ctas == 0) ctas = 1;
+    return static_cast<uint32_t>(ctas);
+}
+
+template <typename F>
+static int dispatch_p(int p, F &&f) {
+    switch (p) {
+        case 1: return f(std::integral_constant<int, 1>{});
+        case 2: return f(std::integral_constant<int, 2>{});
+        case 3: return f(std::integral_constant<int, 3>{});
+        case 4: return f(std::integral_constant<int, 4>{});
+        case 5: case 6: return f(std::integral_constant<int, 6>{});
+        case 7: case 8: return f(std::integral_constant<int, 8>{});
+        default: return set_error(SS_ERR_UNSUPPORTED, "batched kernels support at most %d outputs, got %d", kMaxP, p);
+    }
+}
+
+int launch_rs_encode(ss_rs_coder *coder, const EncGeom &g, const TallyArgs *tally) {
+    ss_ctx *ctx = coder->ctx;
+    SS_TRY(ctx_bind(ctx));
+    if (!coder->batch_ok)
+        return set_error(SS_ERR_UNSUPPORTED, "batched encode needs d <= %d, p <= %d (coder is %d,%d)", kMaxD,
+                         kMaxP, coder->d, coder->p);
+    const int d = coder->d, p = coder->p;
+    const bool padded = (g.flags & SS_RS_OUT_PADDED16) != 0u;
+    if (padded && ((reinterpret_cast<uintptr_t>(g.parity) | g.plane_stride) & 15u))
+        return set_error(SS_ERR_INVALID_ARG, "SS_RS_OUT_PADDED16 needs 16-byte aligned parity base and plane_stride");
+    const bool use_rs32 = coder->is_rs32;
+    cudaStream_t st = ctx->stream;
+
+    if (g.data_off == nullptr) {
+        // ---- uniform geometry: flat column index ----
+        const uint32_t len = g.uni_len;
+        if (len == 0u || g.n == 0u) {
+            if (tally == nullptr || tally->planes == nullptr) return SS_OK;
+        }
+        if (len >= 0x7fffffffu) return set_error(SS_ERR_INVALID_ARG, "data_len too large");
+        const uint32_t L = len == 0u ? 0u : (len + static_cast<uint32_t>(d) - 1u) / static_cast<uint32_t>(d);
+        const uint32_t vpc = (L + 15u) >> 4;
+        if (padded && (g.shard_stride & 15u))
+            return set_error(SS_ERR_INVALID_ARG, "SS_RS_OUT_PADDED16 needs shard_stride %% 16 == 0");
+        if (padded && g.shard_stride < static_cast<uint64_t>(vpc) * 16u)
+            return set_error(SS_ERR_INVALID_ARG, "shard_stride %llu < padded shard length %u",
+                             (unsigned long long)g.shard_stride, vpc * 16u);
+        // chunk so that n_chunk * vpc fits in 32 bits
+        const uint64_t max_cw = vpc ? (0xffffff00ull / vpc) : g.n;
+        uint64_t done = 0;
+        bool tally_pending = tally != nullptr && tally->planes != nullptr;
+        do {
+            const uint64_t nc = (g.n - done) < max_cw ? (g.n - done) : max_cw;
+            EncUniform E;
+            E.data = g.data + done * g.data_stride;
+            E.data_stride = g.data_stride;
+            E.len = len; E.L = L; E.vpc = vpc;
+            E.parity = g.parity + done * g.shard_stride;
+            E.plane_stride = g.plane_stride; E.shard_stride = g.shard_stride;
+            E.n = nc;
+            E.total = static_cast<uint32_t>(nc * vpc);
+            E.padded = (padded ? 1u : 0u) | ((g.flags & SS_RS_EMIT_DATA) ? 2u : 0u);
+            E.planes = nullptr; E.R = 0; E.threshold = 0; E.G = 0; E.committed = nullptr; E.commit_bar = nullptr;
+            uint64_t threads = E.total;
+            if (tally_pending) {
+                if (tally->G > 0xffffff00ull) return set_error(SS_ERR_INVALID_ARG, "too many groups for one fused launch");
+                E.planes = tally->planes; E.R = tally->R; E.threshold = tally->threshold; E.G = tally->G;
+                E.committed = tally->committed; E.commit_bar = tally->commit_bar;
+                if (threads < tally->G) threads = tally->G;
+                tally_pending = false;
+            }
+            if (threads == 0) break;
+            const uint32_t grid = static_cast<uint32_t>((threads + kThreads - 1) / kThreads);
+            if (use_rs32) {
+                rs32_encode_uniform_kernel<<<grid, kThreads, 0, st>>>(E);
+                coder->last_kernel = E.planes ? "rs32_encode_uniform_kernel+tally" : "rs32_encode_uniform_kernel";
+            } else {
+                const uint32_t *prog = static_cast<const uint32_t *>(coder->enc_prog);
+                SS_TRY(dispatch_p(p, [&](auto PC) {
+                    generic_encode_uniform_kernel<decltype(PC)::value><<<grid, kThreads, 0, st>>>(E, prog, d, p);
+                    return SS_OK;
+                }));
+                coder->last_kernel = "generic_encode_uniform_kernel";
+            }
+            SS_CUDA(cudaGetLastError());
+            ctx->launches++;
+            done += nc;
+        } while (done < g.n);
+        return SS_OK;
+    }
+
+    // ---- ragged geometry: a warp per codeword ----
+    if (g.n == 0) return SS_OK;
+    if (g.data_len == nullptr || g.par_off == nullptr)
+        return set_error(SS_ERR_INVALID_ARG, "ragged encode needs data_off, data_len and par_off");
+    EncRagged E;
+    E.data = g.data; E.data_off = g.data_off; E.data_len = g.data_len;
+    E.parity = g.parity; E.plane_stride = g.plane_stride; E.par_off = g.par_off;
+    E.n = g.n; E.padded = (padded ? 1u : 0u) | ((g.flags & SS_RS_EMIT_DATA) ? 2u : 0u);
+    const uint32_t grid = ragged_grid(ctx, g.n);
+    if (use_rs32) {
+        rs32_encode_ragged_kernel<<<grid, kThreads, 0, st>>>(E);
+        coder->last_kernel = "rs32_encode_ragged_kernel";
+    } else {
+        const uint32_t *prog = static_cast<const uint32_t *>(coder->enc_prog);
+        SS_TRY(dispatch_p(p, [&](auto PC) {
+            generic_encode_ragged_kernel<decltype(PC)::value><<<grid, kThreads, 0, st>>>(E, prog, d, p);
+            return SS_OK;
+        }));
+        coder->last_kernel = "generic_encode_ragged_kernel";
+    }
+    SS_CUDA(cudaGetLastError());
+    ctx->launches++;
+    if (tally != nullptr && tally->planes != nullptr)
+        return launch_tally_planes(ctx, tally->planes, tally->R, tally->G, tally->threshold, tally->committed,
+                                   tally->commit_bar);
+    return SS_OK;
+}
+
+int launch_rs_reconstruct(ss_rs_coder *coder, uint8_t *shards, uint64_t plane_stride, const uint64_t *off,
+                          const uint32_t *data_len, const uint32_t *present, uint64_t n, int data_only,
+                          int32_t *status, uint32_t flags) {
+    ss_ctx *ctx = coder->ctx;
+    SS_TRY(ctx_bind(ctx));
+    if (!coder->batch_ok || !coder->dec_ok)
+        return set_error(SS_ERR_UNSUPPORTED, "batched reconstruct needs d+p <= 12 (coder is %d,%d)", coder->d, coder->p);
+    if (n == 0) return SS_OK;
+    const bool padded = (flags & SS_RS_OUT_PADDED16) != 0u;
+    if (padded && ((reinterpret_cast<uintptr_t>(shards) | plane_stride) & 15u))
+        return set_error(SS_ERR_INVALID_ARG, "SS_RS_OUT_PADDED16 needs 16-byte aligned shard base and plane_stride");
+    DecArgs A;
+    A.shards = shards; A.plane_stride = plane_stride; A.off = off; A.data_len = data_len; A.present = present;
+    A.n = n; A.status = status;
+    A.progs = static_cast<const uint8_t *>(data_only ? coder->dec_progs_data : coder->dec_progs);
+    A.prog_stride = static_cast<uint32_t>(coder->prog_stride);
+    A.pattern_mask = (1u << (coder->d + coder->p)) - 1u;
+    A.d = coder->d;
+    A.padded = padded ? 1u : 0u;
+    const uint32_t grid = ragged_grid(ctx, n);
+    SS_TRY(dispatch_p(coder->p, [&](auto PC) {
+        generic_reconstruct_kernel<decltype(PC)::value><<<grid, kThreads, 0, ctx->stream>>>(A);
+        return SS_OK;
+    }));
+    coder->last_kernel = "generic_reconstruct_kernel";
+    SS_CUDA(cudaGetLastError());
+    ctx->launches++;
+    return SS_OK;
+}
+
+}  // namespace ssb

@@ -1,0 +1,134 @@
+// ss_internal.hpp -- shared declarations between the C-ABI layer (capi.cu) and the kernel files.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <cstdio>
+#include <string>
+#include <vector>
+
+#include "../../include/summerset_b200.h"
+
+namespace ssb {
+
+// ---- error plumbing -------------------------------------------------------------------------
+int set_error(int code, const char *fmt, ...);
+int cuda_error(cudaError_t e, const char *what, const char *file, int line);
+
+#define SS_CUDA(call)                                                        \
+    do {                                                                     \
+        cudaError_t _e = (call);                                             \
+        if (_e != cudaSuccess) return ::ssb::cuda_error(_e, #call, __FILE__, __LINE__); \
+    } while (0)
+
+#define SS_TRY(call)                \
+    do {                            \
+        int _rc = (call);           \
+        if (_rc != SS_OK) return _rc; \
+    } while (0)
+
+// ---- coefficient programs consumed by the generic (bit-plane) coding kernel --------------------
+// One "program" says: read d source shards, produce n_out output shards, out_j = sum_i c[j][i]*src_i.
+// splat[(j*d + i)*8 + k] = the byte gfmul(c[j][i], 1<<k) replicated into all four bytes of a word.
+constexpr int kMaxD = 32;
+constexpr int kMaxP = 8;
+struct ProgHeader {           // 64 bytes, followed by p*d*8 uint32 splats
+    uint8_t n_out;
+    uint8_t n_missing_data;   // how many of dst[] are data shards (they come first)
+    uint8_t valid;            // 0: fewer than d shards present (nothing can be computed)
+    uint8_t pad0;
+    uint8_t src[kMaxD];       // source shard index per input
+    uint8_t dst[kMaxP];       // destination shard index per output
+    uint8_t pad1[20];
+};
+static_assert(sizeof(ProgHeader) == 64, "ProgHeader must be 64 bytes");
+
+}  // namespace ssb
+
+// ---- opaque handles -------------------------------------------------------------------------
+struct ss_ctx {
+    int device = -1;
+    cudaStream_t stream = nullptr;
+    bool owns_stream = false;
+    int sm_count = 0;
+    uint64_t launches = 0;
+    // grow-only device scratch (scan temporaries, LUTs)
+    void *scratch = nullptr;
+    size_t scratch_bytes = 0;
+    // host-buffer pipeline (lazily created): H2D stream, D2H stream, triple-buffered staging
+    static constexpr int kStages = 3;
+    cudaStream_t h2d_stream = nullptr, d2h_stream = nullptr;
+    cudaEvent_t ev_h2d[kStages] = {}, ev_kernel[kStages] = {}, ev_done[kStages] = {};
+    bool pipeline_ready = false;
+    void *stage_in[kStages] = {};
+    void *stage_out[kStages] = {};
+    size_t stage_in_bytes = 0, stage_out_bytes = 0;
+};
+
+struct ss_rs_coder {
+    ss_ctx *ctx = nullptr;
+    int d = 0, p = 0;
+    std::vector<uint8_t> matrix;      // (d+p) x d
+    bool is_rs32 = false;             // matrix parity rows == {01 01 01},{0f 08 06}: hand-specialised kernel
+    int variant = 0;
+    const char *last_kernel = "none";
+    // device tables
+    void *enc_prog = nullptr;         // ProgHeader + splats for encode
+    void *dec_progs = nullptr;        // one program per present-pattern (2^(d+p) of them), or null
+    void *dec_progs_data = nullptr;   // same, data_only flavour
+    size_t prog_stride = 0;           // bytes per program
+    bool batch_ok = false;            // d,p within the batched kernels' limits
+    bool dec_ok = false;              // d+p small enough for the per-pattern decode table
+};
+
+namespace ssb {
+
+int ctx_bind(ss_ctx *ctx);                              // cudaSetDevice(ctx->device)
+int ctx_scratch(ss_ctx *ctx, size_t bytes, void **out); // grow-only scratch
+
+// ---- kernel launchers (defined in the .cu files) ---------------------------------------------
+struct EncGeom {
+    // sources: payload arena
+    const uint8_t *data;
+    const uint64_t *data_off;   // ragged (null => uniform)
+    const uint32_t *data_len;   // ragged
+    uint64_t data_stride;       // uniform
+    uint32_t uni_len;           // uniform
+    // outputs: parity planes
+    uint8_t *parity;
+    uint64_t plane_stride;
+    const uint64_t *par_off;    // ragged
+    uint64_t shard_stride;      // uniform
+    uint64_t n;
+    uint32_t flags;
+};
+
+struct TallyArgs {              // optional fused tally
+    const uint64_t *planes = nullptr;
+    uint32_t R = 0, threshold = 0;
+    uint64_t G = 0;
+    uint64_t *committed = nullptr;
+    uint32_t *commit_bar = nullptr;
+};
+
+int launch_rs_encode(ss_rs_coder *coder, const EncGeom &g, const TallyArgs *tally);
+int launch_rs_reconstruct(ss_rs_coder *coder, uint8_t *shards, uint64_t plane_stride,
+                          const uint64_t *off, const uint32_t *data_len, const uint32_t *present,
+                          uint64_t n, int data_only, int32_t *status, uint32_t flags);
+int launch_tally_planes(ss_ctx *ctx, const uint64_t *planes, uint32_t R, uint64_t G, uint32_t thr,
+                        uint64_t *committed, uint32_t *commit_bar);
+int launch_tally_masks(ss_ctx *ctx, const void *masks, uint32_t mask_bytes, uint64_t n, uint32_t thr,
+                       uint64_t *commit_bits);
+int launch_ack_ingest(ss_ctx *ctx, const uint32_t *rec_group, const uint8_t *rec_slot,
+                      const uint8_t *rec_peer, const uint64_t *rec_ballot, uint64_t n_records,
+                      const uint64_t *bal_prepared, const uint64_t *inst_bal, const uint64_t *accepting,
+                      uint32_t R, uint64_t G, uint64_t *planes);
+int launch_tally_crossword(ss_ctx *ctx, const void *masks, uint32_t mask_bytes, const uint8_t *policy_idx,
+                           uint64_t n, const uint32_t *policies_host, uint32_t n_policies,
+                           uint32_t n_replicas, uint32_t T, uint32_t d, uint32_t majority, uint32_t f,
+                           int balanced, uint64_t *commit_bits);
+int launch_raft_scan(ss_ctx *ctx, const uint32_t *match, uint32_t n_peers, uint64_t G,
+                     const uint32_t *last_commit, const uint32_t *log_end, const uint32_t *curr_term,
+                     const uint32_t *terms, uint32_t window, uint32_t threshold, uint32_t *new_commit);
+
+}  // namespace ssb

@@ -1,0 +1,386 @@
+// tally_kernels.cu -- quorum vote tallies, ack ingest, Crossword coverage predicate and the Raft
+// match-index commit scan, batched over millions of independent (group, slot) instances (sm_100a).
+//
+// What they replace (reference, josehu07/summerset @ 1daf80aa) -- work the reference does one
+// message at a time inside the replica's event loop:
+//   handle_msg_accept_reply    multipaxos/messages.rs:370-443, rspaxos/messages.rs:395-465,
+//                              crossword/messages.rs:481-574 (+ coverage_under_faults :15-62)
+//   commit_bar advance         multipaxos/durability.rs:161-170
+//   AppendEntriesReply scan    raft/messages.rs:256-275, craft/messages.rs:288-314
+// All of it is HBM-bound integer/bit work: coalesced 64/128-bit loads, no shared-memory staging
+// needed except for the Crossword look-up table.
+#include "device_common.cuh"
+#include "ss_internal.hpp"
+
+namespace ssb {
+
+constexpr int kTallyThreads = 256;
+
+// ------------------------------------------------------------------------------------------------
+// bit-plane tally: one thread per group (64 slots per thread)
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kTallyThreads)
+tally_planes_kernel(const uint64_t *__restrict__ planes, uint32_t R, uint64_t G, uint32_t threshold,
+                    uint64_t *__restrict__ committed, uint32_t *__restrict__ commit_bar) {
+    const uint64_t stride = static_cast<uint64_t>(gridDim.x) * kTallyThreads;
+    for (uint64_t g = static_cast<uint64_t>(blockIdx.x) * kTallyThreads + threadIdx.x; g < G; g += stride) {
+        const uint64_t w = dev::tally_word(planes, R, G, g, threshold);
+        committed[g] = w;
+        if (commit_bar != nullptr) commit_bar[g] = dev::commit_prefix(w);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// per-instance vote masks: SWAR popcount of 16 one-byte Bitmaps per 128-bit load
+// ------------------------------------------------------------------------------------------------
+// per-byte population count of four packed bytes
+__device__ __forceinline__ uint32_t popc_bytes(uint32_t x) {
+    x = x - ((x >> 1) & 0x55555555u);
+    x = (x & 0x33333333u) + ((x >> 2) & 0x33333333u);
+    return (x + (x >> 4)) & 0x0f0f0f0fu;
+}
+// 4-bit result: bit b = (byte b of cnt >= thr), cnt bytes <= 8, 1 <= thr <= 127
+__device__ __forceinline__ uint32_t ge_nibble(uint32_t cnt, uint32_t thr) {
+    const uint32_t v = (cnt + (0x80u - thr) * 0x01010101u) & 0x80808080u;   // msb set where cnt >= thr
+    return (((v >> 7) * 0x01020408u) >> 24) & 0xfu;
+}
+
+__global__ void __launch_bounds__(kTallyThreads)
+tally_masks8_kernel(const uint8_t *__restrict__ masks, uint64_t n, uint32_t threshold,
+                    uint16_t *__restrict__ commit16) {
+    // thread i handles instances [16i, 16i+16) -> 16 commit bits
+    const uint64_t nvec = ((n + 63) / 64) * 4;     // whole 64-bit output words
+    const uint64_t stride = static_cast<uint64_t>(gridDim.x) * kTallyThreads;
+    for (uint64_t i = static_cast<uint64_t>(blockIdx.x) * kTallyThreads + threadIdx.x; i < nvec; i += stride) {
+        const uint64_t first = i * 16;
+        const int nv = first >= n ? 0 : ((n - first) >= 16 ? 16 : static_cast<int>(n - first));
+        const uint4 v = dev::load16(masks + first, nv);    // masks is 16-byte aligned in practice
+        uint32_t bits;
+        if (threshold == 0u) bits = 0xffffu;
+        else if (threshold > 8u) bits = 0u;
+        else
+            bits = ge_nibble(popc_bytes(v.x), threshold) | (ge_nibble(popc_bytes(v.y), threshold) << 4) |
+                   (ge_nibble(popc_bytes(v.z), threshold) << 8) | (ge_nibble(popc_bytes(v.w), threshold) << 12);
+        if (nv < 16) bits &= (1u << nv) - 1u;   // nv == 0 -> 0
+        commit16[i] = static_cast<uint16_t>(bits);
+    }
+}
+
+__global__ void __launch_bounds__(kTallyThreads)
+tally_masks16_kernel(const uint16_t *__restrict__ masks, uint64_t n, uint32_t threshold,
+                     uint8_t *__restrict__ commit8) {
+    // thread i handles instances [8i, 8i+8) -> 8 commit bits
+    const uint64_t nvec = ((n + 63) / 64) * 8;     // whole 64-bit output words
+    const uint64_t stride = static_cast<uint64_t>(gridDim.x) * kTallyThreads;
+    for (uint64_t i = static_cast<uint64_t>(blockIdx.x) * kTallyThreads + threadIdx.x; i < nvec; i += stride) {
+        const uint64_t first = i * 8;
+        const int nv = first >= n ? 0 : ((n - first) >= 8 ? 8 : static_cast<int>(n - first));
+        const uint4 v = dev::load16(reinterpret_cast<const uint8_t *>(masks + first), nv * 2);
+        const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+        uint32_t bits = 0;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            bits |= (static_cast<uint32_t>(__popc(w[j] & 0xffffu)) >= threshold ? 1u : 0u) << (2 * j);
+            bits |= (static_cast<uint32_t>(__popc(w[j] >> 16)) >= threshold ? 1u : 0u) << (2 * j + 1);
+        }
+        if (nv < 8) bits &= (1u << nv) - 1u;
+        commit8[i] = static_cast<uint8_t>(bits);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// ack ingest: record stream -> planes, with the handler's filters
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kTallyThreads)
+ack_ingest_kernel(const uint32_t *__restrict__ rec_group, const uint8_t *__restrict__ rec_slot,
+                  const uint8_t *__restrict__ rec_peer, const uint64_t *__restrict__ rec_ballot, uint64_t n_records,
+                  const uint64_t *__restrict__ bal_prepared, const uint64_t *__restrict__ inst_bal,
+                  const uint64_t *__restrict__ accepting, uint32_t R, uint64_t G, uint64_t *planes) {
+    const uint64_t stride = static_cast<uint64_t>(gridDim.x) * kTallyThreads;
+    for (uint64_t i = static_cast<uint64_t>(blockIdx.x) * kTallyThreads + threadIdx.x; i < n_records; i += stride) {
+        const uint64_t g = rec_group[i];
+        const uint32_t s = rec_slot[i], peer = rec_peer[i];
+        if (g >= G || s >= 64u || peer >= R) continue;            // Bitmap::get -> Err (bitmap.rs:89-97)
+        const uint64_t ballot = rec_ballot[i];
+        if (ballot != __ldg(bal_prepared + g)) continue;          // multipaxos/messages.rs:388
+        if (((__ldg(accepting + g) >> s) & 1ull) == 0ull) continue; // :394-399 status != Accepting
+        if (ballot < __ldg(inst_bal + g * 64 + s)) continue;      // :394-399 ballot < inst.bal
+        // :404-409 -- duplicates are idempotent, so an atomic OR is an exact model
+        atomicOr(reinterpret_cast<unsigned long long *>(planes + static_cast<uint64_t>(peer) * G + g), 1ull << s);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Crossword: look-up table over (policy, ack mask), then a streaming look-up kernel
+// ------------------------------------------------------------------------------------------------
+// one thread per (policy, ack_mask): evaluates the reference predicate verbatim
+__global__ void crossword_lut_kernel(const uint32_t *__restrict__ policies, uint32_t n_policies, uint32_t n,
+                                     uint32_t T, uint32_t d, uint32_t majority, uint32_t f, int balanced,
+                                     uint32_t *__restrict__ lut_bits /* n_policies * 2^n bits, zeroed */) {
+    const uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t nmask = 1u << n;
+    if (idx >= n_policies * nmask) return;
+    const uint32_t k = idx / nmask, ack = idx % nmask;
+    const uint32_t *asg = policies + k * n;
+    const uint32_t nacks = __popc(ack);
+    uint32_t coverage;
+    if (nacks <= f) {
+        coverage = 0;                                             // crossword/messages.rs:22-24
+    } else if (balanced) {
+        // :28-33 -- spr read from "an" entry; balanced => all equal, take the lowest acked replica
+        const uint32_t first = __ffs(ack) - 1;
+        coverage = (nacks - f - 1u) * (T / n) + __popc(asg[first]);
+    } else {
+        // :35-61 -- min over all (nacks - f)-subsets of the union of their shards
+        const uint32_t cnt = nacks - f;
+        coverage = T;
+        for (uint32_t sub = ack; ; sub = (sub - 1u) & ack) {      // all sub-masks of ack
+            if (static_cast<uint32_t>(__popc(sub)) == cnt) {
+                uint32_t cov = 0;
+                for (uint32_t r = 0; r < n; ++r)
+                    if ((sub >> r) & 1u) cov |= asg[r];
+                const uint32_t c = __popc(cov);
+                if (c < coverage) coverage = c;
+            }
+            if (sub == 0u) break;
+        }
+    }
+    if (nacks >= majority && coverage >= d)                       // :535-542
+        atomicOr(lut_bits + (idx >> 5), 1u << (idx & 31u));
+}
+
+template <typename MaskT>
+__global__ void __launch_bounds__(kTallyThreads)
+tally_crossword_kernel(const MaskT *__restrict__ masks, const uint8_t *__restrict__ policy_idx, uint64_t n_inst,
+                       const uint32_t *__restrict__ lut_bits, uint32_t lut_words, uint32_t n_policies, uint32_t n,
+                       uint8_t *__restrict__ commit8) {
+    extern __shared__ uint32_t lut[];
+    for (uint32_t i = threadIdx.x; i < lut_words; i += kTallyThreads) lut[i] = lut_bits[i];
+    __syncthreads();
+    const uint32_t nmask = 1u << n;
+    const uint64_t nvec = ((n_inst + 63) / 64) * 8;   // whole 64-bit output words
+    const uint64_t stride = static_cast<uint64_t>(gridDim.x) * kTallyThreads;
+    for (uint64_t i = static_cast<uint64_t>(blockIdx.x) * kTallyThreads + threadIdx.x; i < nvec; i += stride) {
+        const uint64_t first = i * 8;
+        const int nv = first >= n_inst ? 0 : ((n_inst - first) >= 8 ? 8 : static_cast<int>(n_inst - first));
+        uint32_t bits = 0;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            if (j < nv) {
+                const uint32_t ack = static_cast<uint32_t>(masks[first + j]) & (nmask - 1u);
+                uint32_t k = policy_idx[first + j];
+                if (k < n_policies) {
+                    const uint32_t e = k * nmask + ack;
+                    bits |= ((lut[e >> 5] >> (e & 31u)) & 1u) << j;
+                }
+            }
+        }
+        commit8[i] = static_cast<uint8_t>(bits);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Raft / CRaft commit scan: a warp walks 32 groups; lanes own groups for the scalar part and
+// cooperate on each group's term window (coalesced 128-byte rows + ballot).
+// ------------------------------------------------------------------------------------------------
+constexpr int kRaftMaxPeers = 16;
+
+template <int NP>   // NP >= n_peers: compile-time bound so the match values stay in registers
+__global__ void __launch_bounds__(kTallyThreads)
+raft_scan_kernel(const uint32_t *__restrict__ match, uint32_t n_peers, uint64_t G,
+                 const uint32_t *__restrict__ last_commit, const uint32_t *__restrict__ log_end,
+                 const uint32_t *__restrict__ curr_term, const uint32_t *__restrict__ terms, uint32_t W,
+                 uint32_t threshold, uint32_t *__restrict__ new_commit) {
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint64_t warp = (static_cast<uint64_t>(blockIdx.x) * kTallyThreads + threadIdx.x) >> 5;
+    const uint64_t nwarps = (static_cast<uint64_t>(gridDim.x) * kTallyThreads) >> 5;
+    const uint64_t nbatches = (G + 31) / 32;
+    for (uint64_t b = warp; b < nbatches; b += nwarps) {
+        const uint64_t g = b * 32 + lane;
+        const bool live = g < G;
+        // ---- per-lane scalar part: highest slot the peers' match indices allow ----
+        uint32_t lc = 0, le = 0, ct = 0, upper = 0;
+        bool any = false;
+        if (live) {
+            lc = __ldg(last_commit + g);
+            le = __ldg(log_end + g);
+            ct = __ldg(curr_term + g);
+            // match_cnt(slot) = 1 + #{p: match[p] >= slot} >= threshold  <=>  slot <= m, where m is
+            // the (threshold-1)-th largest peer match (raft/messages.rs:266-271).
+            const uint32_t need = threshold > 0u ? threshold - 1u : 0u;   // peers required
+            if (need == 0u) {
+                upper = 0xffffffffu; any = true;
+            } else if (need <= n_peers) {
+                uint32_t mv[NP];
+#pragma unroll
+                for (int q = 0; q < NP; ++q)
+                    mv[q] = (static_cast<uint32_t>(q) < n_peers) ? __ldg(match + static_cast<uint64_t>(q) * G + g) : 0u;
+                // need-th largest: the value with exactly (need-1) elements ranked above it
+                uint32_t kth = 0;
+#pragma unroll
+                for (int q = 0; q < NP; ++q) {
+                    if (static_cast<uint32_t>(q) < n_peers) {
+                        uint32_t rank = 0;
+#pragma unroll
+                        for (int r = 0; r < NP; ++r)
+                            if (static_cast<uint32_t>(r) < n_peers)
+                                rank += (mv[r] > mv[q] || (mv[r] == mv[q] && r < q)) ? 1u : 0u;
+                        if (rank == need - 1u) kth = mv[q];
+                    }
+                }
+                upper = kth; any = true;
+            }
+            // slots scanned: last_commit+1 .. log_end-1 (raft/messages.rs:256-258)
+            if (any && le > 0u) { if (upper > le - 1u) upper = le - 1u; }
+            else any = false;
+            if (any && upper <= lc) any = false;
+        }
+        uint32_t result = lc;
+        // ---- cooperative part: for each group of the batch, find the last slot in (lc, upper]
+        //      whose term equals curr_term (raft/messages.rs:261-263,271-274: last one wins) ----
+        const uint32_t todo = __ballot_sync(0xffffffffu, live && any);
+        uint32_t rem = todo;
+        while (rem) {
+            const int src = __ffs(rem) - 1;
+            rem &= rem - 1u;
+            const uint32_t s_lc = __shfl_sync(0xffffffffu, lc, src);
+            const uint32_t s_up = __shfl_sync(0xffffffffu, upper, src);
+            const uint32_t s_ct = __shfl_sync(0xffffffffu, ct, src);
+            const uint64_t sg = b * 32 + static_cast<uint64_t>(src);
+            const uint32_t span = s_up - s_lc;                    // window offsets 0 .. span-1 are candidates
+            const uint32_t *row = terms + sg * W;
+            uint32_t found = 0xffffffffu;
+            // walk the window from the top in 32-entry chunks
+            const uint32_t limit = span < W ? span : W;
+            for (int base = static_cast<int>((limit - 1u) & ~31u); base >= 0; base -= 32) {
+                const uint32_t o = static_cast<uint32_t>(base) + lane;
+                const bool hit = o < limit && __ldg(row + o) == s_ct;
+                const uint32_t m = __ballot_sync(0xffffffffu, hit);
+                if (m) { found = static_cast<uint32_t>(base) + (31u - __clz(m)); break; }
+            }
+            if (lane == static_cast<uint32_t>(src) && found != 0xffffffffu) result = s_lc + 1u + found;
+        }
+        if (live) new_commit[g] = result;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host launchers
+// ------------------------------------------------------------------------------------------------
+static inline uint32_t stream_grid(ss_ctx *ctx, uint64_t items) {
+    uint64_t ctas = (items + kTallyThreads - 1) / kTallyThreads;
+    const uint64_t cap = static_cast<uint64_t>(ctx->sm_count) * 8ull * 4ull;
+    if (ctas > cap) ctas = cap;
+    if (ctas == 0) ctas = 1;
+    return static_cast<uint32_t>(ctas);
+}
+
+int launch_tally_planes(ss_ctx *ctx, const uint64_t *planes, uint32_t R, uint64_t G, uint32_t thr,
+                        uint64_t *committed, uint32_t *commit_bar) {
+    SS_TRY(ctx_bind(ctx));
+    if (R == 0 || R > 16) return set_error(SS_ERR_INVALID_ARG, "n_replicas must be 1..16, got %u", R);
+    if (G == 0) return SS_OK;
+    tally_planes_kernel<<<stream_grid(ctx, G), kTallyThreads, 0, ctx->stream>>>(planes, R, G, thr, committed, commit_bar);
+    SS_CUDA(cudaGetLastError());
+    ctx->launches++;
+    return SS_OK;
+}
+
+int launch_tally_masks(ss_ctx *ctx, const void *masks, uint32_t mask_bytes, uint64_t n, uint32_t thr,
+                       uint64_t *commit_bits) {
+    SS_TRY(ctx_bind(ctx));
+    if (n == 0) return SS_OK;
+    if (mask_bytes == 1) {
+        tally_masks8_kernel<<<stream_grid(ctx, ((n + 63) / 64) * 4), kTallyThreads, 0, ctx->stream>>>(
+            static_cast<const uint8_t *>(masks), n, thr, reinterpret_cast<uint16_t *>(commit_bits));
+    } else if (mask_bytes == 2) {
+        tally_masks16_kernel<<<stream_grid(ctx, ((n + 63) / 64) * 8), kTallyThreads, 0, ctx->stream>>>(
+            static_cast<const uint16_t *>(masks), n, thr, reinterpret_cast<uint8_t *>(commit_bits));
+    } else {
+        return set_error(SS_ERR_INVALID_ARG, "mask_bytes must be 1 or 2, got %u", mask_bytes);
+    }
+    SS_CUDA(cudaGetLastError());
+    ctx->launches++;
+    return SS_OK;
+}
+
+int launch_ack_ingest(ss_ctx *ctx, const uint32_t *rec_group, const uint8_t *rec_slot, const uint8_t *rec_peer,
+                      const uint64_t *rec_ballot, uint64_t n_records, const uint64_t *bal_prepared,
+                      const uint64_t *inst_bal, const uint64_t *accepting, uint32_t R, uint64_t G, uint64_t *planes) {
+    SS_TRY(ctx_bind(ctx));
+    if (R == 0 || R > 16) return set_error(SS_ERR_INVALID_ARG, "n_replicas must be 1..16, got %u", R);
+    if (n_records == 0) return SS_OK;
+    ack_ingest_kernel<<<stream_grid(ctx, n_records), kTallyThreads, 0, ctx->stream>>>(
+        rec_group, rec_slot, rec_peer, rec_ballot, n_records, bal_prepared, inst_bal, accepting, R, G, planes);
+    SS_CUDA(cudaGetLastError());
+    ctx->launches++;
+    return SS_OK;
+}
+
+int launch_tally_crossword(ss_ctx *ctx, const void *masks, uint32_t mask_bytes, const uint8_t *policy_idx,
+                           uint64_t n, const uint32_t *policies_host, uint32_t n_policies, uint32_t n_replicas,
+                           uint32_t T, uint32_t d, uint32_t majority, uint32_t f, int balanced,
+                           uint64_t *commit_bits) {
+    SS_TRY(ctx_bind(ctx));
+    if (n_replicas == 0 || n_replicas > 12) return set_error(SS_ERR_INVALID_ARG, "n_replicas must be 1..12, got %u", n_replicas);
+    if (n_policies == 0 || n_policies > 16) return set_error(SS_ERR_INVALID_ARG, "n_policies must be 1..16, got %u", n_policies);
+    if (T == 0 || T > 32) return set_error(SS_ERR_INVALID_ARG, "total_shards must be 1..32, got %u", T);
+    if (mask_bytes != 1 && mask_bytes != 2) return set_error(SS_ERR_INVALID_ARG, "mask_bytes must be 1 or 2");
+    if (mask_bytes == 1 && n_replicas > 8) return set_error(SS_ERR_INVALID_ARG, "n_replicas > 8 needs 2-byte masks");
+    if (n == 0) return SS_OK;
+    const uint32_t entries = n_policies << n_replicas;
+    const uint32_t lut_words = (entries + 31) / 32;
+    const size_t pol_bytes = sizeof(uint32_t) * n_policies * n_replicas;
+    const size_t pol_slot = (pol_bytes + 255) & ~size_t(255);
+    void *scratch = nullptr;
+    SS_TRY(ctx_scratch(ctx, pol_slot + lut_words * 4, &scratch));
+    uint32_t *d_pol = static_cast<uint32_t *>(scratch);
+    uint32_t *d_lut = reinterpret_cast<uint32_t *>(static_cast<uint8_t *>(scratch) + pol_slot);
+    SS_CUDA(cudaMemcpyAsync(d_pol, policies_host, pol_bytes, cudaMemcpyHostToDevice, ctx->stream));
+    // policies_host may be pageable and reused by the caller right after we return
+    SS_CUDA(cudaStreamSynchronize(ctx->stream));
+    SS_CUDA(cudaMemsetAsync(d_lut, 0, lut_words * 4, ctx->stream));
+    crossword_lut_kernel<<<(entries + 127) / 128, 128, 0, ctx->stream>>>(d_pol, n_policies, n_replicas, T, d, majority,
+                                                                         f, balanced, d_lut);
+    SS_CUDA(cudaGetLastError());
+    ctx->launches++;
+    const uint32_t grid = stream_grid(ctx, ((n + 63) / 64) * 8);
+    const size_t smem = lut_words * 4;
+    if (mask_bytes == 1)
+        tally_crossword_kernel<uint8_t><<<grid, kTallyThreads, smem, ctx->stream>>>(
+            static_cast<const uint8_t *>(masks), policy_idx, n, d_lut, lut_words, n_policies, n_replicas,
+            reinterpret_cast<uint8_t *>(commit_bits));
+    else
+        tally_crossword_kernel<uint16_t><<<grid, kTallyThreads, smem, ctx->stream>>>(
+            static_cast<const uint16_t *>(masks), policy_idx, n, d_lut, lut_words, n_policies, n_replicas,
+            reinterpret_cast<uint8_t *>(commit_bits));
+    SS_CUDA(cudaGetLastError());
+    ctx->launches++;
+    return SS_OK;
+}
+
+int launch_raft_scan(ss_ctx *ctx, const uint32_t *match, uint32_t n_peers, uint64_t G, const uint32_t *last_commit,
+                     const uint32_t *log_end, const uint32_t *curr_term, const uint32_t *terms, uint32_t window,
+                     uint32_t threshold, uint32_t *new_commit) {
+    SS_TRY(ctx_bind(ctx));
+    if (n_peers > kRaftMaxPeers) return set_error(SS_ERR_INVALID_ARG, "n_peers must be <= %d, got %u", kRaftMaxPeers, n_peers);
+    if (G == 0) return SS_OK;
+    const uint64_t warps = (G + 31) / 32;
+    uint64_t ctas = (warps + (kTallyThreads / 32) - 1) / (kTallyThreads / 32);
+    const uint64_t cap = static_cast<uint64_t>(ctx->sm_count) * 8ull * 4ull;
+    if (ctas > cap) ctas = cap;
+    const uint32_t grid = static_cast<uint32_t>(ctas);
+#define SS_RAFT_LAUNCH(NP) raft_scan_kernel<NP><<<grid, kTallyThreads, 0, ctx->stream>>>( \
+        match, n_peers, G, last_commit, log_end, curr_term, terms, window, threshold, new_commit)
+    if (n_peers <= 2) SS_RAFT_LAUNCH(2);
+    else if (n_peers <= 4) SS_RAFT_LAUNCH(4);
+    else if (n_peers <= 6) SS_RAFT_LAUNCH(6);
+    else if (n_peers <= 8) SS_RAFT_LAUNCH(8);
+    else SS_RAFT_LAUNCH(16);
+#undef SS_RAFT_LAUNCH
+    SS_CUDA(cudaGetLastError());
+    ctx->launches++;
+    return SS_OK;
+}
+
+}  // namespace ssb
