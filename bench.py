@@ -42,8 +42,9 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="cfg3", choices=["cfg3", "cfg2", "cfg5"])
+    ap.add_argument("--workload", default="cfg3", choices=["cfg3", "cfg2", "cfg5", "cfg3b", "cfg4"])
     ap.add_argument("--groups", type=int, default=G_PER_GPU, help="groups per GPU")
+    ap.add_argument("--variant", type=int, default=0, help="encode kernel variant (tuning)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     return ap.parse_args()
@@ -199,9 +200,14 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=dev)
     ctx = Context(local)
     rs = ReedSolomon(ctx, D, P)
+    rs.set_variant(args.variant)
     n = args.groups
     L, ds, ps = rs.parity_layout(DATA_LEN, n)
     peak, peak_src = measured_peaks()
+    if args.workload == "cfg3b":
+        return run_cfg3b(args, ctx, rs, dev, world, rank, peak, peak_src)
+    if args.workload == "cfg4":
+        return run_cfg4(args, ctx, rs, dev, world, rank, peak, peak_src)
 
     # ---- synthetic inputs, generated on the device (seeded) ----
     gen = torch.Generator(device=dev); gen.manual_seed(wl.SEED_BASE + 3 + 1000 * rank)
@@ -247,7 +253,7 @@ def run_ours(args):
     if world > 1:
         ack_recv.copy_(planes)
 
-    # ---- cfg5 (Raft) is a separate small harness ----
+    # ---- cfg5 (Raft), cfg3b (reconstruct) and cfg4 (Crossword ragged) are separate small harnesses ----
     if args.workload == "cfg5":
         return run_cfg5(args, ctx, dev, world, rank, peak, peak_src)
 
@@ -477,6 +483,118 @@ def run_cfg5(args, ctx, dev, world, rank, peak, peak_src):
                           "gpu_launches": int(ctx.launches - l0), "e2e": None, "cpu_baseline": None}))
     if world > 1:
         dist.barrier(); dist.destroy_process_group()
+
+
+def _time_steps(torch, fn, steps, warmup):
+    for _ in range(max(3, warmup)):
+        fn()
+    torch.cuda.synchronize()
+    a = torch.cuda.Event(enable_timing=True); b = torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(steps):
+        fn()
+    b.record()
+    torch.cuda.synchronize()
+    return a.elapsed_time(b) / steps
+
+
+def run_cfg3b(args, ctx, rs, dev, world, rank, peak, peak_src):
+    """cfg 3b: batched reconstruct_data of 2^20 RS(3,2) codewords x 4 KB under the seeded erasure mix."""
+    import torch
+    from summerset_b200 import workloads as wl
+    n = args.groups
+    L, ds, ps = rs.parity_layout(DATA_LEN, n)
+    gen = torch.Generator(device=dev); gen.manual_seed(wl.SEED_BASE + 3 + rank)
+    data = torch.randint(0, 256, (n, DATA_LEN), dtype=torch.uint8, device=dev, generator=gen)
+    sh = torch.zeros((D + P, n, ds), dtype=torch.uint8, device=dev)
+    padded = torch.zeros((n, D * L), dtype=torch.uint8, device=dev)
+    padded[:, :DATA_LEN] = data
+    for i in range(D):
+        sh[i, :, :L] = padded[:, i * L:(i + 1) * L]
+    del padded
+    rs.encode_uniform(data, DATA_LEN, parity=sh[D:])
+    keep = sh.clone()
+    present = wl.erasure_patterns(n, D, P, seed_extra=rank)
+    pm = torch.from_numpy(present.astype(np.int32)).to(dev)
+    for j in range(D + P):
+        sh[j][((pm >> j) & 1) == 0] = 0x5A
+    off = torch.arange(n, dtype=torch.int64, device=dev) * ds
+    lens = torch.full((n,), DATA_LEN, dtype=torch.int32, device=dev)
+    l0 = ctx.launches
+    ms = _time_steps(torch, lambda: rs.reconstruct_batch(sh, n * ds, off, lens, pm, True), args.steps, args.warmup)
+    launches = (ctx.launches - l0)
+    ok = all(torch.equal(sh[i], keep[i]) for i in range(D))
+    miss_data = sum(((present >> i) & 1) == 0 for i in range(D)).astype(np.int64)
+    alg = int(((miss_data > 0) * D * L + miss_data * L).sum()) + n * 20
+    if rank == 0:
+        print(json.dumps({"metric": "RS reconstruct GB/s (reconstruct_data, RS(3,2), 4 KB payloads, cfg-3b erasure mix)",
+                          "value": alg / (ms * 1e-3) / 1e9, "unit": "GB/s", "n_gpus": world, "steps": args.steps,
+                          "warmup": max(3, args.warmup), "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+                          "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+                          "config": {"workload": "cfg3b: reconstruct_data, 2^20 codewords, 50% intact / 25% one data shard / 25% two shards missing"},
+                          "codewords_per_s": n / (ms * 1e-3), "roundtrip_bit_exact": bool(ok), "kernel": rs.last_kernel(),
+                          "roofline": {"bound": "hbm", "achieved": alg / (ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                                       "frac": alg / (ms * 1e-3) / 1e9 / peak, "traffic": None,
+                                       "algorithmic_bytes_per_launch": alg, "peak_source": peak_src},
+                          "gpu_launches": int(launches * args.steps // max(1, args.steps + max(3, args.warmup))), "e2e": None, "cpu_baseline": None}))
+
+
+def run_cfg4(args, ctx, rs, dev, world, rank, peak, peak_src):
+    """cfg 4: Crossword n=5,d=3,T=5,f=2: ragged RS(3,2) encode of mixed 256 B..64 KB payloads + coverage tally."""
+    import torch
+    from oracle import pyoracle as oracle
+    from summerset_b200 import workloads as wl
+    n = args.groups
+    lens, spr = wl.cfg4_lengths(n, seed_extra=rank)
+    lay = wl.ragged_layout(lens, D)
+    gen = torch.Generator(device=dev); gen.manual_seed(wl.SEED_BASE + 4 + rank)
+    arena = torch.randint(0, 256, (lay["data_bytes"] + 256,), dtype=torch.uint8, device=dev, generator=gen)
+    parity = torch.empty((P, lay["plane_bytes"]), dtype=torch.uint8, device=dev)
+    doff = torch.from_numpy(lay["data_off"].astype(np.int64)).to(dev)
+    poff = torch.from_numpy(lay["par_off"].astype(np.int64)).to(dev)
+    dlen = torch.from_numpy(lens.astype(np.int32)).to(dev)
+    masks = torch.randint(0, 32, (n,), dtype=torch.uint8, device=dev, generator=gen) | 1     # leader always acks
+    pidx = torch.from_numpy((spr - 1).astype(np.uint8)).to(dev)
+    policies = [list(map(int, oracle.cw_brr_assignment(5, 5, s))) for s in (1, 2, 3)]
+
+    def step():
+        rs.encode_batch(arena, doff, dlen, parity, lay["plane_bytes"], poff)
+        return ctx.tally_crossword(masks, pidx, policies, 5, 3, 3, 2, True)
+
+    l0 = ctx.launches
+    ms = _time_steps(torch, step, args.steps, args.warmup)
+    launches = ctx.launches - l0
+    ms_enc = _time_steps(torch, lambda: rs.encode_batch(arena, doff, dlen, parity, lay["plane_bytes"], poff), args.steps, 1)
+    # spot check vs oracle
+    idx = np.arange(0, n, max(1, n // 64))
+    a = arena.cpu().numpy() if lay["data_bytes"] < (1 << 31) else None
+    note = None
+    if a is not None:
+        sub_len = lens[idx]; sub_lay = wl.ragged_layout(sub_len, D)
+        sub = np.zeros(sub_lay["data_bytes"] + 64, dtype=np.uint8)
+        for j, g in enumerate(idx):
+            o = int(lay["data_off"][g]); so = int(sub_lay["data_off"][j])
+            sub[so:so + int(lens[g])] = a[o:o + int(lens[g])]
+        want = np.zeros((P, sub_lay["plane_bytes"]), dtype=np.uint8)
+        oracle.rs_encode_batch(D, P, sub, sub_lay["data_off"], sub_len, want.reshape(-1), sub_lay["plane_bytes"], sub_lay["par_off"])
+        got = parity.cpu().numpy()
+        for j, g in enumerate(idx):
+            Lg = int(lay["L"][g]); o = int(lay["par_off"][g]); so = int(sub_lay["par_off"][j])
+            assert (got[:, o:o + Lg] == want[:, so:so + Lg]).all(), "cfg4 parity check failed"
+        note = f"{len(idx)} sampled codewords bit-exact vs oracle"
+    alg = int((lay["L"].astype(np.int64) * (D + P)).sum()) + n * 22
+    if rank == 0:
+        print(json.dumps({"metric": "RS shard GB/s, Crossword ragged encode + coverage tally", "value": alg / (ms * 1e-3) / 1e9,
+                          "unit": "GB/s", "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": ms,
+                          "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+                          "config": {"workload": "cfg4: Crossword n=5 d=3 T=5 f=2, 2^20 codewords, data_len uniform over {256..65536}, spr uniform {1,2,3}",
+                                     "payload_bytes": int(lens.astype(np.int64).sum())},
+                          "slots_committed_per_s": n / (ms * 1e-3), "encode_only_ms": ms_enc, "parity_check": note,
+                          "kernel": rs.last_kernel(),
+                          "roofline": {"bound": "hbm", "achieved": alg / (ms_enc * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                                       "frac": alg / (ms_enc * 1e-3) / 1e9 / peak, "traffic": None,
+                                       "algorithmic_bytes_per_launch": alg, "peak_source": peak_src},
+                          "gpu_launches": int(launches), "e2e": None, "cpu_baseline": None}))
 
 
 def main():

@@ -94,12 +94,19 @@ static int pipeline_staging(ss_ctx *ctx, size_t in_bytes, size_t out_bytes) {
 }
 
 // ---- coefficient programs -----------------------------------------------------------------------
-static size_t prog_bytes(int d, int p) { return sizeof(ProgHeader) + size_t(p) * size_t(d) * 8 * 4; }
+static size_t prog_bytes(int d, int p) { return sizeof(ProgHeader) + 2 * size_t(p) * size_t(d) * 8 * 4; }
 
-static void fill_splats(uint32_t *splat, int d, int j, int i, uint8_t c) {
+// fills, for coefficient c = c[j][i] of a (p x d) program: the bit-plane splats, the Horner bit masks
+// (stored p*d*8 words after the splats) and the running top bit of row j
+static void fill_coef(uint8_t *prog, int d, int p, int j, int i, uint8_t c) {
+    ProgHeader *h = reinterpret_cast<ProgHeader *>(prog);
+    uint32_t *splat = reinterpret_cast<uint32_t *>(prog + sizeof(ProgHeader));
+    uint32_t *hmask = splat + size_t(p) * d * 8;
     for (int k = 0; k < 8; ++k) {
         const uint32_t b = gf::mul(c, static_cast<uint8_t>(1u << k));
         splat[(size_t(j) * d + i) * 8 + k] = b * 0x01010101u;
+        hmask[(size_t(j) * d + i) * 8 + k] = ((c >> k) & 1u) ? 0xffffffffu : 0u;
+        if (((c >> k) & 1u) && k > h->top[j]) h->top[j] = static_cast<uint8_t>(k);
     }
 }
 
@@ -109,7 +116,6 @@ static void build_decode_program(const gf::Matrix &M, int d, int p, uint32_t pre
     const int t = d + p;
     memset(out, 0, prog_bytes(d, p));
     ProgHeader *h = reinterpret_cast<ProgHeader *>(out);
-    uint32_t *splat = reinterpret_cast<uint32_t *>(out + sizeof(ProgHeader));
     int src[kMaxD], ns = 0;
     for (int i = 0; i < t && ns < d; ++i)
         if ((present >> i) & 1u) src[ns++] = i;
@@ -124,7 +130,7 @@ static void build_decode_program(const gf::Matrix &M, int d, int p, uint32_t pre
     for (int r = 0; r < d; ++r) {
         if ((present >> r) & 1u) continue;
         h->dst[n_out] = static_cast<uint8_t>(r);
-        for (int i = 0; i < d; ++i) fill_splats(splat, d, n_out, i, dec.at(r, i));
+        for (int i = 0; i < d; ++i) fill_coef(out, d, p, n_out, i, dec.at(r, i));
         ++n_out;
     }
     h->n_missing_data = static_cast<uint8_t>(n_out);
@@ -136,7 +142,7 @@ static void build_decode_program(const gf::Matrix &M, int d, int p, uint32_t pre
             for (int i = 0; i < d; ++i) {
                 uint8_t c = 0;
                 for (int k = 0; k < d; ++k) c ^= gf::mul(M.at(q, k), dec.at(k, i));
-                fill_splats(splat, d, n_out, i, c);
+                fill_coef(out, d, p, n_out, i, c);
             }
             ++n_out;
         }
@@ -147,13 +153,12 @@ static void build_decode_program(const gf::Matrix &M, int d, int p, uint32_t pre
 static void build_encode_program(const gf::Matrix &M, int d, int p, uint8_t *out) {
     memset(out, 0, prog_bytes(d, p));
     ProgHeader *h = reinterpret_cast<ProgHeader *>(out);
-    uint32_t *splat = reinterpret_cast<uint32_t *>(out + sizeof(ProgHeader));
     h->valid = 1;
     h->n_out = static_cast<uint8_t>(p);
     for (int i = 0; i < d; ++i) h->src[i] = static_cast<uint8_t>(i);
     for (int j = 0; j < p; ++j) {
         h->dst[j] = static_cast<uint8_t>(j);      // relative to the parity base
-        for (int i = 0; i < d; ++i) fill_splats(splat, d, j, i, M.at(d + j, i));
+        for (int i = 0; i < d; ++i) fill_coef(out, d, p, j, i, M.at(d + j, i));
     }
 }
 

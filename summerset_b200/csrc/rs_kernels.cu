@@ -135,6 +135,114 @@ __global__ void __launch_bounds__(kThreads) rs32_encode_uniform_kernel(const __g
                 (P.padded & 2u) != 0u);
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// RS(3,2) "row" kernel for uniform geometry (the BASELINE config-3 hot kernel)
+// ------------------------------------------------------------------------------------------------
+// A CTA of round_up(vpc,32) threads walks codewords g = blockIdx.x, + gridDim.x, ...; thread v owns
+// column v of every codeword it visits, so there is no per-thread index division and all address
+// arithmetic is a per-iteration pointer bump.  With a 16-byte-aligned payload stride the misalignment of
+// shard 1 and shard 2 w.r.t. 16 bytes is the same for every codeword: the byte funnel (prmt selector and
+// word offset) is kernel-uniform, hoisted out of the loop, and its branches are uniform.  Only the last
+// column(s) of a codeword (partial output vector / zero-padded payload tail) take the masked general path.
+// Lanes beyond vpc in the last warp would idle; lane vpc tallies the group's 64-slot ack window instead.
+struct Enc32Row {
+    const uint8_t *data;
+    uint64_t data_stride;
+    uint8_t *parity;
+    uint64_t plane_stride, shard_stride;
+    uint32_t n, len, L, vpc;
+    uint32_t fast_cols;       // columns [0, fast_cols) need no masking
+    uint32_t s1, s2;          // (L & 15), (2L & 15): misalignment of shards 1 and 2
+    uint32_t emit_data;
+    const uint64_t *planes;   // fused tally (nullptr: none); G == n
+    uint32_t R, threshold;
+    uint64_t *committed;
+    uint32_t *commit_bar;
+};
+
+// bytes [s, s+16) of the 32-byte window {lo, hi}; s is kernel-uniform
+__device__ __forceinline__ uint4 funnel16(const uint4 &lo, const uint4 &hi, uint32_t s) {
+    const uint32_t sel = 0x3210u + 0x1111u * (s & 3u);
+    switch (s >> 2) {
+        case 0:
+            return make_uint4(dev::prmt(lo.x, lo.y, sel), dev::prmt(lo.y, lo.z, sel), dev::prmt(lo.z, lo.w, sel),
+                              dev::prmt(lo.w, hi.x, sel));
+        case 1:
+            return make_uint4(dev::prmt(lo.y, lo.z, sel), dev::prmt(lo.z, lo.w, sel), dev::prmt(lo.w, hi.x, sel),
+                              dev::prmt(hi.x, hi.y, sel));
+        case 2:
+            return make_uint4(dev::prmt(lo.z, lo.w, sel), dev::prmt(lo.w, hi.x, sel), dev::prmt(hi.x, hi.y, sel),
+                              dev::prmt(hi.y, hi.z, sel));
+        default:
+            return make_uint4(dev::prmt(lo.w, hi.x, sel), dev::prmt(hi.x, hi.y, sel), dev::prmt(hi.y, hi.z, sel),
+                              dev::prmt(hi.z, hi.w, sel));
+    }
+}
+
+// one Horner step r*x ^ u on four packed field elements: shift on the FMA pipe (imad), then
+// prmt (sign mask) + two lop3 on the ALU pipe.
+__device__ __forceinline__ uint32_t horner_step(uint32_t r, uint32_t u) {
+    const uint32_t m = msb_mask(r);
+    const uint32_t r2 = r * 2u;
+    const uint32_t t = (r2 & 0xfefefefeu) ^ u;
+    return t ^ (m & 0x1d1d1d1du);
+}
+__device__ __forceinline__ void rs32_word_fast(uint32_t a, uint32_t b, uint32_t c, uint32_t &p0, uint32_t &p1) {
+    const uint32_t t = a ^ b;
+    const uint32_t u = a ^ c;
+    p0 = a ^ b ^ c;
+    uint32_t r = horner_step(t, u);
+    r = horner_step(r, u);
+    p1 = horner_step(r, a);
+}
+
+template <bool EMIT, int MAXT, int MINB>
+__global__ void __launch_bounds__(MAXT, MINB) rs32_encode_row_kernel(const __grid_constant__ Enc32Row P) {
+    const uint32_t v = threadIdx.x;
+    const uint32_t k = v * 16u;
+    const uint32_t s1 = P.s1, s2 = P.s2;
+    // aligned in-codeword offsets of the vectors that cover shard 1 / shard 2 at column v
+    const uint32_t o1 = P.L + k - s1, o2 = 2u * P.L + k - s2;
+    const bool is_fast = v < P.fast_cols;
+    const bool is_col = v < P.vpc;
+    const bool is_tally = (P.planes != nullptr) && (v == (P.vpc < blockDim.x ? P.vpc : 0u));
+    for (uint32_t g = blockIdx.x; g < P.n; g += gridDim.x) {
+        const uint8_t *src = P.data + static_cast<uint64_t>(g) * P.data_stride;
+        uint8_t *out = P.parity + static_cast<uint64_t>(g) * P.shard_stride;
+        if (is_fast) {
+            // all loads first (memory-level parallelism), then the byte funnels
+            const uint4 a = dev::ldg128(src + k);
+            const uint4 b0 = dev::ldg128(src + o1);
+            const uint4 c0 = dev::ldg128(src + o2);
+            uint4 b1 = b0, c1 = c0;
+            if (s1 != 0u) b1 = dev::ldg128(src + o1 + 16u);
+            if (s2 != 0u) c1 = dev::ldg128(src + o2 + 16u);
+            const uint4 b = s1 != 0u ? funnel16(b0, b1, s1) : b0;
+            const uint4 c = s2 != 0u ? funnel16(c0, c1, s2) : c0;
+            uint4 p0, p1;
+            rs32_word_fast(a.x, b.x, c.x, p0.x, p1.x);
+            rs32_word_fast(a.y, b.y, c.y, p0.y, p1.y);
+            rs32_word_fast(a.z, b.z, c.z, p0.z, p1.z);
+            rs32_word_fast(a.w, b.w, c.w, p0.w, p1.w);
+            dev::stg128_cs(out + k, p0);
+            dev::stg128_cs(out + P.plane_stride + k, p1);
+            if (EMIT) {
+                dev::stg128_cs(out - 3 * P.plane_stride + k, a);
+                dev::stg128_cs(out - 2 * P.plane_stride + k, b);
+                dev::stg128_cs(out - 1 * P.plane_stride + k, c);
+            }
+        } else if (is_col) {
+            rs32_column(src, P.len, P.L, k, out, P.plane_stride, true, EMIT);
+        }
+        if (is_tally) {
+            const uint64_t w = dev::tally_word(P.planes, P.R, P.n, g, P.threshold);
+            P.committed[g] = w;
+            if (P.commit_bar != nullptr) P.commit_bar[g] = dev::commit_prefix(w);
+        }
+    }
+}
+
 struct EncRagged {
     const uint8_t *data;
     const uint64_t *data_off;
@@ -244,6 +352,7 @@ struct DecArgs {
     uint32_t pattern_mask;
     int d;
     uint32_t padded;
+    uint32_t hmask_off;       // words from the splat table to the Horner mask table (p*d*8)
 };
 
 template <int P>
@@ -286,6 +395,148 @@ __global__ void __launch_bounds__(kThreads) generic_reconstruct_kernel(const __g
                             A.padded != 0u);
         }
     }
+}
+
+
+// ------------------------------------------------------------------------------------------------
+// Horner core for arbitrary (run-time) coefficients, d <= D sources held in registers.
+//   out_j = sum_i c_ji * x_i = sum_k x^k * ( XOR of the x_i whose c_ji has bit k set )
+// evaluated from the top bit down: acc = acc*x ^ (XOR_i x_i & hmask[j][i][k]).  Per output word that is
+// (top+1) * d lop3 + top packed-xtime steps -- 2-3x fewer ALU ops than the bit-plane form, which matters
+// because reconstruction is otherwise ALU-bound rather than HBM-bound.
+// ------------------------------------------------------------------------------------------------
+template <int D>
+__device__ __forceinline__ uint4 horner_row(const uint4 (&x)[D], int d, const uint32_t *__restrict__ hm_j, int top) {
+    uint4 acc = make_uint4(0u, 0u, 0u, 0u);
+    for (int k = top; k >= 0; --k) {
+        if (k != top) {
+            const uint4 m = make_uint4(msb_mask(acc.x), msb_mask(acc.y), msb_mask(acc.z), msb_mask(acc.w));
+            acc.x = ((acc.x * 2u) & 0xfefefefeu) ^ (m.x & 0x1d1d1d1du);
+            acc.y = ((acc.y * 2u) & 0xfefefefeu) ^ (m.y & 0x1d1d1d1du);
+            acc.z = ((acc.z * 2u) & 0xfefefefeu) ^ (m.z & 0x1d1d1d1du);
+            acc.w = ((acc.w * 2u) & 0xfefefefeu) ^ (m.w & 0x1d1d1d1du);
+        }
+#pragma unroll
+        for (int i = 0; i < D; ++i) {
+            if (i < d) {
+                const uint32_t hm = __ldg(hm_j + i * 8 + k);
+                acc.x ^= x[i].x & hm;
+                acc.y ^= x[i].y & hm;
+                acc.z ^= x[i].z & hm;
+                acc.w ^= x[i].w & hm;
+            }
+        }
+    }
+    return acc;
+}
+
+template <int D>
+__global__ void __launch_bounds__(kThreads) horner_reconstruct_kernel(const __grid_constant__ DecArgs A) {
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint64_t warp = (static_cast<uint64_t>(blockIdx.x) * kThreads + threadIdx.x) >> 5;
+    const uint64_t nwarps = (static_cast<uint64_t>(gridDim.x) * kThreads) >> 5;
+    const int d = A.d;
+    for (uint64_t g = warp; g < A.n; g += nwarps) {
+        const uint32_t len = __ldg(A.data_len + g);
+        if (len == 0u) {                              // null codeword: rscoding.rs:495-497
+            if (lane == 0u) A.status[g] = SS_ERR_INVALID_ARG;
+            continue;
+        }
+        const uint32_t pat = __ldg(A.present + g) & A.pattern_mask;
+        const uint8_t *prog = A.progs + static_cast<uint64_t>(pat) * A.prog_stride;
+        const ProgHeader *hdr = reinterpret_cast<const ProgHeader *>(prog);
+        const int valid = hdr->valid;
+        const int n_out = hdr->n_out;
+        if (lane == 0u) A.status[g] = valid ? SS_OK : SS_ERR_TOO_FEW_SHARDS_PRESENT;
+        if (!valid || n_out == 0) continue;           // never partial output
+        const uint32_t *hmask = reinterpret_cast<const uint32_t *>(prog + sizeof(ProgHeader)) + A.hmask_off;
+        const uint32_t L = (len + static_cast<uint32_t>(d) - 1u) / static_cast<uint32_t>(d);
+        const uint32_t vpc = (L + 15u) >> 4;
+        uint8_t *base = A.shards + __ldg(A.off + g);
+        for (uint32_t v = lane; v < vpc; v += 32u) {
+            const uint32_t k = v * 16u;
+            const int nv = static_cast<int>(L - k) > 16 ? 16 : static_cast<int>(L - k);
+            uint4 x[D];
+#pragma unroll
+            for (int i = 0; i < D; ++i)
+                x[i] = (i < d) ? load16(base + static_cast<uint64_t>(hdr->src[i]) * A.plane_stride + k, nv)
+                               : make_uint4(0u, 0u, 0u, 0u);
+            for (int j = 0; j < n_out; ++j) {
+                const uint4 acc = horner_row<D>(x, d, hmask + j * d * 8, hdr->top[j]);
+                store16(base + static_cast<uint64_t>(hdr->dst[j]) * A.plane_stride + k, acc, nv, A.padded != 0u);
+            }
+        }
+    }
+}
+
+template <int D>
+__device__ __forceinline__ void horner_payload_column(const uint8_t *src, uint32_t len, uint32_t L, uint32_t k,
+                                                      uint8_t *out, uint64_t plane_stride, uint32_t oflags,
+                                                      const uint32_t *prog, int d, int p) {
+    const bool padded = (oflags & 1u) != 0u, emit_data = (oflags & 2u) != 0u;
+    const int onv = static_cast<int>(L - k) > 16 ? 16 : static_cast<int>(L - k);
+    const ProgHeader *hdr = reinterpret_cast<const ProgHeader *>(prog);
+    const uint32_t *hmask = prog + sizeof(ProgHeader) / 4 + p * d * 8;
+    uint4 x[D];
+#pragma unroll
+    for (int i = 0; i < D; ++i) {
+        if (i < d) {
+            const int64_t pos = static_cast<int64_t>(i) * L + k;
+            const int64_t rem = static_cast<int64_t>(len) - pos;
+            x[i] = load16(src + pos, rem > 16 ? 16 : (rem < 0 ? 0 : static_cast<int>(rem)));
+            if (emit_data) store16(out - static_cast<uint64_t>(d - i) * plane_stride + k, x[i], onv, padded);
+        } else {
+            x[i] = make_uint4(0u, 0u, 0u, 0u);
+        }
+    }
+    for (int j = 0; j < p; ++j) {
+        const uint4 acc = horner_row<D>(x, d, hmask + j * d * 8, hdr->top[j]);
+        store16(out + static_cast<uint64_t>(j) * plane_stride + k, acc, onv, padded);
+    }
+}
+
+template <int D>
+__global__ void __launch_bounds__(kThreads)
+horner_encode_uniform_kernel(const __grid_constant__ EncUniform E, const uint32_t *__restrict__ prog, int d, int p) {
+    const uint32_t t = blockIdx.x * kThreads + threadIdx.x;
+    if (E.planes != nullptr && t < E.G) {
+        const uint64_t w = dev::tally_word(E.planes, E.R, E.G, t, E.threshold);
+        E.committed[t] = w;
+        if (E.commit_bar != nullptr) E.commit_bar[t] = dev::commit_prefix(w);
+    }
+    if (t >= E.total) return;
+    const uint32_t g = t / E.vpc;
+    const uint32_t k = (t - g * E.vpc) * 16u;
+    horner_payload_column<D>(E.data + static_cast<uint64_t>(g) * E.data_stride, E.len, E.L, k,
+                             E.parity + static_cast<uint64_t>(g) * E.shard_stride, E.plane_stride, E.padded, prog, d, p);
+}
+
+template <int D>
+__global__ void __launch_bounds__(kThreads)
+horner_encode_ragged_kernel(const __grid_constant__ EncRagged E, const uint32_t *__restrict__ prog, int d, int p) {
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint64_t warp = (static_cast<uint64_t>(blockIdx.x) * kThreads + threadIdx.x) >> 5;
+    const uint64_t nwarps = (static_cast<uint64_t>(gridDim.x) * kThreads) >> 5;
+    for (uint64_t g = warp; g < E.n; g += nwarps) {
+        const uint32_t len = __ldg(E.data_len + g);
+        if (len == 0u) continue;
+        const uint32_t L = (len + static_cast<uint32_t>(d) - 1u) / static_cast<uint32_t>(d);
+        const uint32_t vpc = (L + 15u) >> 4;
+        const uint8_t *src = E.data + __ldg(E.data_off + g);
+        uint8_t *out = E.parity + __ldg(E.par_off + g);
+        for (uint32_t v = lane; v < vpc; v += 32u)
+            horner_payload_column<D>(src, len, L, v * 16u, out, E.plane_stride, E.padded, prog, d, p);
+    }
+}
+
+// smallest instantiated register capacity >= d (0: use the bit-plane kernels)
+template <typename F>
+static int dispatch_d(int d, F &&f) {
+    if (d <= 2) return f(std::integral_constant<int, 2>{});
+    if (d == 3) return f(std::integral_constant<int, 3>{});
+    if (d == 4) return f(std::integral_constant<int, 4>{});
+    if (d <= 6) return f(std::integral_constant<int, 6>{});
+    return f(std::integral_constant<int, 8>{});
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -341,6 +592,40 @@ int launch_rs_encode(ss_rs_coder *coder, const EncGeom &g, const TallyArgs *tall
         if (padded && g.shard_stride < static_cast<uint64_t>(vpc) * 16u)
             return set_error(SS_ERR_INVALID_ARG, "shard_stride %llu < padded shard length %u",
                              (unsigned long long)g.shard_stride, vpc * 16u);
+
+        // ---- RS(3,2) row kernel: aligned uniform geometry, codewords up to 256 columns ----
+        if (use_rs32 && coder->variant != 1 && padded && vpc >= 1 && vpc <= 256 && g.n <= 0xffffffffull &&
+            ((reinterpret_cast<uintptr_t>(g.data) | g.data_stride) & 15u) == 0u &&
+            (tally == nullptr || tally->planes == nullptr || tally->G == g.n)) {
+            Enc32Row Rw;
+            Rw.data = g.data; Rw.data_stride = g.data_stride; Rw.parity = g.parity;
+            Rw.plane_stride = g.plane_stride; Rw.shard_stride = g.shard_stride;
+            Rw.n = static_cast<uint32_t>(g.n); Rw.len = len; Rw.L = L; Rw.vpc = vpc;
+            const uint32_t lim = (len - 2u * L) < L ? (len - 2u * L) : L;     // bytes of shard 2 inside the payload
+            Rw.fast_cols = len >= 2u * L ? lim / 16u : 0u;
+            Rw.s1 = L & 15u; Rw.s2 = (2u * L) & 15u;
+            Rw.emit_data = (g.flags & SS_RS_EMIT_DATA) ? 1u : 0u;
+            Rw.planes = nullptr; Rw.R = 0; Rw.threshold = 0; Rw.committed = nullptr; Rw.commit_bar = nullptr;
+            if (tally != nullptr && tally->planes != nullptr) {
+                Rw.planes = tally->planes; Rw.R = tally->R; Rw.threshold = tally->threshold;
+                Rw.committed = tally->committed; Rw.commit_bar = tally->commit_bar;
+            }
+            const uint32_t threads = (vpc + 31u) & ~31u;
+            // resident CTAs per SM (2048 threads, 32 CTAs) x a few waves; every CTA strides over codewords
+            uint32_t per_sm = 2048u / threads; if (per_sm > 32u) per_sm = 32u;
+            uint64_t ctas = static_cast<uint64_t>(ctx->sm_count) * per_sm * 4ull;
+            if (ctas > g.n) ctas = g.n;
+            const uint32_t grid = static_cast<uint32_t>(ctas);
+            // register budget variants (tuning knob ss_rs_set_variant): 0/2 = 40 regs, 3 = 32 regs, 4 = unconstrained
+            if (Rw.emit_data) rs32_encode_row_kernel<true, 256, 1><<<grid, threads, 0, st>>>(Rw);
+            else if (threads <= 128 && coder->variant == 3) rs32_encode_row_kernel<false, 128, 16><<<grid, threads, 0, st>>>(Rw);
+            else if (threads <= 128 && coder->variant != 4) rs32_encode_row_kernel<false, 128, 12><<<grid, threads, 0, st>>>(Rw);
+            else rs32_encode_row_kernel<false, 256, 1><<<grid, threads, 0, st>>>(Rw);
+            coder->last_kernel = Rw.planes ? "rs32_encode_row_kernel+tally" : "rs32_encode_row_kernel";
+            SS_CUDA(cudaGetLastError());
+            ctx->launches++;
+            return SS_OK;
+        }
         // chunk so that n_chunk * vpc fits in 32 bits
         const uint64_t max_cw = vpc ? (0xffffff00ull / vpc) : g.n;
         uint64_t done = 0;
@@ -370,6 +655,13 @@ int launch_rs_encode(ss_rs_coder *coder, const EncGeom &g, const TallyArgs *tall
             if (use_rs32) {
                 rs32_encode_uniform_kernel<<<grid, kThreads, 0, st>>>(E);
                 coder->last_kernel = E.planes ? "rs32_encode_uniform_kernel+tally" : "rs32_encode_uniform_kernel";
+            } else if (d <= 8 && coder->variant != 5) {
+                const uint32_t *prog = static_cast<const uint32_t *>(coder->enc_prog);
+                SS_TRY(dispatch_d(d, [&](auto DC) {
+                    horner_encode_uniform_kernel<decltype(DC)::value><<<grid, kThreads, 0, st>>>(E, prog, d, p);
+                    return SS_OK;
+                }));
+                coder->last_kernel = "horner_encode_uniform_kernel";
             } else {
                 const uint32_t *prog = static_cast<const uint32_t *>(coder->enc_prog);
                 SS_TRY(dispatch_p(p, [&](auto PC) {
@@ -397,6 +689,13 @@ int launch_rs_encode(ss_rs_coder *coder, const EncGeom &g, const TallyArgs *tall
     if (use_rs32) {
         rs32_encode_ragged_kernel<<<grid, kThreads, 0, st>>>(E);
         coder->last_kernel = "rs32_encode_ragged_kernel";
+    } else if (d <= 8 && coder->variant != 5) {
+        const uint32_t *prog = static_cast<const uint32_t *>(coder->enc_prog);
+        SS_TRY(dispatch_d(d, [&](auto DC) {
+            horner_encode_ragged_kernel<decltype(DC)::value><<<grid, kThreads, 0, st>>>(E, prog, d, p);
+            return SS_OK;
+        }));
+        coder->last_kernel = "horner_encode_ragged_kernel";
     } else {
         const uint32_t *prog = static_cast<const uint32_t *>(coder->enc_prog);
         SS_TRY(dispatch_p(p, [&](auto PC) {
@@ -432,12 +731,21 @@ int launch_rs_reconstruct(ss_rs_coder *coder, uint8_t *shards, uint64_t plane_st
     A.pattern_mask = (1u << (coder->d + coder->p)) - 1u;
     A.d = coder->d;
     A.padded = padded ? 1u : 0u;
+    A.hmask_off = static_cast<uint32_t>(coder->p * coder->d * 8);
     const uint32_t grid = ragged_grid(ctx, n);
-    SS_TRY(dispatch_p(coder->p, [&](auto PC) {
-        generic_reconstruct_kernel<decltype(PC)::value><<<grid, kThreads, 0, ctx->stream>>>(A);
-        return SS_OK;
-    }));
-    coder->last_kernel = "generic_reconstruct_kernel";
+    if (coder->d <= 8 && coder->variant != 5) {
+        SS_TRY(dispatch_d(coder->d, [&](auto DC) {
+            horner_reconstruct_kernel<decltype(DC)::value><<<grid, kThreads, 0, ctx->stream>>>(A);
+            return SS_OK;
+        }));
+        coder->last_kernel = "horner_reconstruct_kernel";
+    } else {
+        SS_TRY(dispatch_p(coder->p, [&](auto PC) {
+            generic_reconstruct_kernel<decltype(PC)::value><<<grid, kThreads, 0, ctx->stream>>>(A);
+            return SS_OK;
+        }));
+        coder->last_kernel = "generic_reconstruct_kernel";
+    }
     SS_CUDA(cudaGetLastError());
     ctx->launches++;
     return SS_OK;

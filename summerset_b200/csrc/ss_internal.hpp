@@ -32,15 +32,17 @@ int cuda_error(cudaError_t e, const char *what, const char *file, int line);
 // splat[(j*d + i)*8 + k] = the byte gfmul(c[j][i], 1<<k) replicated into all four bytes of a word.
 constexpr int kMaxD = 32;
 constexpr int kMaxP = 8;
-struct ProgHeader {           // 64 bytes, followed by p*d*8 uint32 splats
+struct ProgHeader {           // 64 bytes, followed by p*d*8 uint32 splats, then p*d*8 uint32 Horner bit masks
     uint8_t n_out;
     uint8_t n_missing_data;   // how many of dst[] are data shards (they come first)
     uint8_t valid;            // 0: fewer than d shards present (nothing can be computed)
     uint8_t pad0;
     uint8_t src[kMaxD];       // source shard index per input
     uint8_t dst[kMaxP];       // destination shard index per output
-    uint8_t pad1[20];
+    uint8_t top[kMaxP];       // highest set bit over the coefficients of output j (Horner start), 0 if all zero
+    uint8_t pad1[12];
 };
+// Horner masks: hmask[(j*d + i)*8 + k] = 0xffffffff if bit k of c[j][i] is set, else 0.
 static_assert(sizeof(ProgHeader) == 64, "ProgHeader must be 64 bytes");
 
 }  // namespace ssb

@@ -159,7 +159,50 @@ def test_encode_uniform_matches_oracle(ctx, oracle, d, p, data_len):
     want = oracle.rs_encode_uniform(d, p, data, data_len)
     assert got.shape == want.shape
     assert (got == want).all()
-    assert rs.last_kernel().startswith("rs32_" if (d, p) == (3, 2) else "generic_")
+    assert rs.last_kernel().startswith("rs32_" if (d, p) == (3, 2) else ("horner_" if d <= 8 else "generic_"))
+
+
+@pytest.mark.parametrize("variant", [1, 3, 4, 5])
+def test_encode_kernel_variants(ctx, oracle, variant):
+    """every selectable kernel variant (flat v1, register budgets of the row kernel, bit-plane generic) is bit-exact"""
+    for d, p, data_len, n in [(3, 2, 4096, 2500), (3, 2, 100, 700), (3, 2, 16 * 200, 33), (4, 3, 4096, 300), (5, 4, 1000, 300)]:
+        rs = ReedSolomon(ctx, d, p)
+        rs.set_variant(variant)
+        data = wl.payload_uniform(n, data_len, seed_extra=variant)
+        got = _gpu_encode_uniform(rs, data, data_len)
+        assert (got == oracle.rs_encode_uniform(d, p, data, data_len)).all(), (variant, d, p, data_len, rs.last_kernel())
+    # reconstruct with the bit-plane kernel too
+    if variant == 5:
+        d, p, data_len = 3, 2, 777
+        rs = ReedSolomon(ctx, d, p); rs.set_variant(5)
+        n = 32
+        data = wl.payload_uniform(n, data_len, seed_extra=1)
+        full, L, ds = _planes_from(oracle, d, p, data, data_len)
+        present = np.arange(n, dtype=np.uint32)
+        sh = torch.from_numpy(full.copy()).to(DEV)
+        off = torch.arange(n, dtype=torch.int64, device=DEV) * ds
+        st = rs.reconstruct_batch(sh, n * ds, off, torch.full((n,), data_len, dtype=torch.int32, device=DEV),
+                                  torch.from_numpy(present.astype(np.int32)).to(DEV), False)
+        torch.cuda.synchronize()
+        assert rs.last_kernel() == "generic_reconstruct_kernel"
+        assert (sh.cpu().numpy()[:, :, :L] == full[:, :, :L]).all()
+        assert [int(x) for x in st.cpu()] == [0 if bin(pt).count("1") >= d else -10 for pt in range(n)]
+
+
+def test_row_kernel_emit_data_and_wide_codewords(ctx, oracle):
+    """SS_RS_EMIT_DATA (all d+p planes in one pass) on the row kernel and the general kernels; codewords wider
+    than the row kernel's 256-column limit fall back to the flat kernel"""
+    from summerset_b200._lib import check
+    for d, p, data_len, n in [(3, 2, 4096, 1000), (3, 2, 20000, 64), (3, 2, 5, 40), (4, 3, 1000, 100)]:
+        rs = ReedSolomon(ctx, d, p)
+        data = wl.payload_uniform(n, data_len, seed_extra=3)
+        L, ds, ps = rs.parity_layout(data_len, n)
+        sh = torch.full((d + p, n, ds), 0x11, dtype=torch.uint8, device=DEV)
+        dt = torch.from_numpy(data).to(DEV)
+        check(ctx.lib.ss_rs_encode_uniform_dev(rs.h, dt.data_ptr(), data.shape[1], data_len, n, sh[d:].data_ptr(), ps, ds, 3))
+        torch.cuda.synchronize()
+        full, L2, ds2 = _planes_from(oracle, d, p, data, data_len)
+        assert (sh.cpu().numpy() == full).all(), (d, p, data_len, rs.last_kernel())
 
 
 def test_encode_unaligned_stride_and_exact_output(ctx, oracle):
