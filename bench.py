@@ -45,6 +45,7 @@ def parse_args():
     ap.add_argument("--workload", default="cfg3", choices=["cfg3", "cfg2", "cfg5", "cfg3b", "cfg4"])
     ap.add_argument("--groups", type=int, default=G_PER_GPU, help="groups per GPU")
     ap.add_argument("--variant", type=int, default=0, help="encode kernel variant (tuning)")
+    ap.add_argument("--no-tally", action="store_true", help="tuning: time the encode alone")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     return ap.parse_args()
@@ -244,6 +245,9 @@ def run_ours(args):
         if args.workload == "cfg2":
             ctx.tally_planes(planes, THRESH_MULTIPAXOS, True, committed, bar)
             return
+        if args.no_tally:
+            check(ctx.lib.ss_rs_encode_uniform_dev(rs.h, data.data_ptr(), DATA_LEN, DATA_LEN, n, parity.data_ptr(), ps, ds, flags))
+            return
         check(ctx.lib.ss_accept_step_fused_dev(rs.h, data.data_ptr(), DATA_LEN, DATA_LEN, n, parity.data_ptr(), ps, ds,
                                                flags, (ack_recv if world > 1 else planes).data_ptr(), R,
                                                THRESH_RSPAXOS, committed.data_ptr(), bar.data_ptr()))
@@ -284,12 +288,12 @@ def run_ours(args):
     for i in range(args.steps):
         a, b = k_evs[i]
         a.record()
-        if args.workload == "cfg2":
-            ctx.tally_planes(planes, THRESH_MULTIPAXOS, True, committed, bar)
+        if world == 1:
+            step()
         else:
             check(ctx.lib.ss_accept_step_fused_dev(rs.h, data.data_ptr(), DATA_LEN, DATA_LEN, n, parity.data_ptr(), ps, ds,
-                                                   flags, (ack_recv if world > 1 else planes).data_ptr(), R,
-                                                   THRESH_RSPAXOS, committed.data_ptr(), bar.data_ptr()))
+                                                   flags, ack_recv.data_ptr(), R, THRESH_RSPAXOS, committed.data_ptr(),
+                                                   bar.data_ptr()))
         b.record()
     torch.cuda.synchronize()
     kt = [a.elapsed_time(b) for a, b in k_evs]
@@ -310,6 +314,9 @@ def run_ours(args):
             got = parity[:, idx].cpu().numpy()
             assert (got == want).all(), "bench parity check failed"
         src = (ack_recv if world > 1 else planes)
+        if args.no_tally:
+            committed.zero_()
+            ctx.tally_planes(src, THRESH_RSPAXOS if args.workload != "cfg2" else THRESH_MULTIPAXOS, True, committed, bar)
         cw, bw = oracle.tally_planes(src[:, idx].cpu().numpy().view(np.uint64),
                                      THRESH_RSPAXOS if args.workload != "cfg2" else THRESH_MULTIPAXOS)
         assert (committed[idx].cpu().numpy().view(np.uint64) == cw).all(), "bench commit check failed"

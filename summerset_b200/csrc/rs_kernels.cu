@@ -155,6 +155,7 @@ struct Enc32Row {
     uint32_t fast_cols;       // columns [0, fast_cols) need no masking
     uint32_t s1, s2;          // (L & 15), (2L & 15): misalignment of shards 1 and 2
     uint32_t emit_data;
+    uint32_t chunk;           // 0: codewords g = blockIdx.x + i*gridDim.x ; else CTA b owns [b*chunk, (b+1)*chunk)
     const uint64_t *planes;   // fused tally (nullptr: none); G == n
     uint32_t R, threshold;
     uint64_t *committed;
@@ -197,6 +198,45 @@ __device__ __forceinline__ void rs32_word_fast(uint32_t a, uint32_t b, uint32_t 
     p1 = horner_step(r, a);
 }
 
+// one column of the row kernel.  MASKED: this warp owns the codeword's last column(s): inputs past data_len
+// are zeroed, outputs past L are zeroed, and a second aligned load is issued only when it holds a valid byte.
+template <bool EMIT, bool MASKED>
+__device__ __forceinline__ void rs32_row_column(const uint8_t *__restrict__ src, uint8_t *__restrict__ out,
+                                                uint64_t plane_stride, uint32_t k, uint32_t o1, uint32_t o2,
+                                                uint32_t s1, uint32_t s2, int nva, int nvb, int nvc, int onv) {
+    // loads first (pairs adjacent so the second one hits the sectors the first just brought into L1)
+    uint4 a = dev::ldg128(src + k);
+    const uint4 b0 = dev::ldg128(src + o1);
+    uint4 b1 = b0;
+    if (s1 != 0u && (!MASKED || static_cast<int>(s1) + nvb > 16)) b1 = dev::ldg128(src + o1 + 16u);
+    const uint4 c0 = dev::ldg128(src + o2);
+    uint4 c1 = c0;
+    if (s2 != 0u && (!MASKED || static_cast<int>(s2) + nvc > 16)) c1 = dev::ldg128(src + o2 + 16u);
+    uint4 b = s1 != 0u ? funnel16(b0, b1, s1) : b0;
+    uint4 c = s2 != 0u ? funnel16(c0, c1, s2) : c0;
+    if (MASKED) {
+        a = keep_bytes(a, nva);
+        b = keep_bytes(b, nvb);
+        c = keep_bytes(c, nvc);
+    }
+    uint4 p0, p1;
+    rs32_word_fast(a.x, b.x, c.x, p0.x, p1.x);
+    rs32_word_fast(a.y, b.y, c.y, p0.y, p1.y);
+    rs32_word_fast(a.z, b.z, c.z, p0.z, p1.z);
+    rs32_word_fast(a.w, b.w, c.w, p0.w, p1.w);
+    if (MASKED) {
+        p0 = keep_bytes(p0, onv);
+        p1 = keep_bytes(p1, onv);
+    }
+    dev::stg128_cs(out + k, p0);
+    dev::stg128_cs(out + plane_stride + k, p1);
+    if (EMIT) {
+        dev::stg128_cs(out - 3 * plane_stride + k, MASKED ? keep_bytes(a, onv) : a);
+        dev::stg128_cs(out - 2 * plane_stride + k, MASKED ? keep_bytes(b, onv) : b);
+        dev::stg128_cs(out - 1 * plane_stride + k, MASKED ? keep_bytes(c, onv) : c);
+    }
+}
+
 template <bool EMIT, int MAXT, int MINB>
 __global__ void __launch_bounds__(MAXT, MINB) rs32_encode_row_kernel(const __grid_constant__ Enc32Row P) {
     const uint32_t v = threadIdx.x;
@@ -204,42 +244,44 @@ __global__ void __launch_bounds__(MAXT, MINB) rs32_encode_row_kernel(const __gri
     const uint32_t s1 = P.s1, s2 = P.s2;
     // aligned in-codeword offsets of the vectors that cover shard 1 / shard 2 at column v
     const uint32_t o1 = P.L + k - s1, o2 = 2u * P.L + k - s2;
-    const bool is_fast = v < P.fast_cols;
     const bool is_col = v < P.vpc;
-    const bool is_tally = (P.planes != nullptr) && (v == (P.vpc < blockDim.x ? P.vpc : 0u));
-    for (uint32_t g = blockIdx.x; g < P.n; g += gridDim.x) {
-        const uint8_t *src = P.data + static_cast<uint64_t>(g) * P.data_stride;
-        uint8_t *out = P.parity + static_cast<uint64_t>(g) * P.shard_stride;
-        if (is_fast) {
-            // all loads first (memory-level parallelism), then the byte funnels
-            const uint4 a = dev::ldg128(src + k);
-            const uint4 b0 = dev::ldg128(src + o1);
-            const uint4 c0 = dev::ldg128(src + o2);
-            uint4 b1 = b0, c1 = c0;
-            if (s1 != 0u) b1 = dev::ldg128(src + o1 + 16u);
-            if (s2 != 0u) c1 = dev::ldg128(src + o2 + 16u);
-            const uint4 b = s1 != 0u ? funnel16(b0, b1, s1) : b0;
-            const uint4 c = s2 != 0u ? funnel16(c0, c1, s2) : c0;
-            uint4 p0, p1;
-            rs32_word_fast(a.x, b.x, c.x, p0.x, p1.x);
-            rs32_word_fast(a.y, b.y, c.y, p0.y, p1.y);
-            rs32_word_fast(a.z, b.z, c.z, p0.z, p1.z);
-            rs32_word_fast(a.w, b.w, c.w, p0.w, p1.w);
-            dev::stg128_cs(out + k, p0);
-            dev::stg128_cs(out + P.plane_stride + k, p1);
-            if (EMIT) {
-                dev::stg128_cs(out - 3 * P.plane_stride + k, a);
-                dev::stg128_cs(out - 2 * P.plane_stride + k, b);
-                dev::stg128_cs(out - 1 * P.plane_stride + k, c);
-            }
-        } else if (is_col) {
-            rs32_column(src, P.len, P.L, k, out, P.plane_stride, true, EMIT);
-        }
-        if (is_tally) {
+    // warp-uniform: does this warp contain a column that needs masking?
+    const uint32_t warp_first = v & ~31u;
+    const bool warp_masked = warp_first + 32u > P.fast_cols;
+    auto clamp16 = [](int64_t r) { return r > 16 ? 16 : (r < 0 ? 0 : static_cast<int>(r)); };
+    const int nva = clamp16(static_cast<int64_t>(P.len) - k);
+    const int nvb = clamp16(static_cast<int64_t>(P.len) - P.L - k);
+    const int nvc = clamp16(static_cast<int64_t>(P.len) - 2ll * P.L - k);
+    const int onv = clamp16(static_cast<int64_t>(P.L) - k);
+
+    // ---- fused tally: this CTA's contiguous slice of groups, coalesced (one pass, before the encode loop) ----
+    if (P.planes != nullptr) {
+        const uint32_t per = (P.n + gridDim.x - 1) / gridDim.x;
+        const uint32_t lo = blockIdx.x * per;
+        const uint32_t hi = lo + per < P.n ? lo + per : P.n;
+        for (uint32_t g = lo + v; g < hi; g += blockDim.x) {
             const uint64_t w = dev::tally_word(P.planes, P.R, P.n, g, P.threshold);
             P.committed[g] = w;
             if (P.commit_bar != nullptr) P.commit_bar[g] = dev::commit_prefix(w);
         }
+    }
+    if (!is_col) return;
+
+    const uint32_t g_begin = P.chunk ? blockIdx.x * P.chunk : blockIdx.x;
+    const uint32_t g_step = P.chunk ? 1u : gridDim.x;
+    const uint32_t g_end = P.chunk ? (g_begin + P.chunk < P.n ? g_begin + P.chunk : P.n) : P.n;
+    if (!warp_masked) {
+#pragma unroll 1
+        for (uint32_t g = g_begin; g < g_end; g += g_step)
+            rs32_row_column<EMIT, false>(P.data + static_cast<uint64_t>(g) * P.data_stride,
+                                         P.parity + static_cast<uint64_t>(g) * P.shard_stride, P.plane_stride, k, o1, o2,
+                                         s1, s2, 16, 16, 16, 16);
+    } else {
+#pragma unroll 1
+        for (uint32_t g = g_begin; g < g_end; g += g_step)
+            rs32_row_column<EMIT, true>(P.data + static_cast<uint64_t>(g) * P.data_stride,
+                                        P.parity + static_cast<uint64_t>(g) * P.shard_stride, P.plane_stride, k, o1, o2,
+                                        s1, s2, nva, nvb, nvc, onv);
     }
 }
 
@@ -594,7 +636,7 @@ int launch_rs_encode(ss_rs_coder *coder, const EncGeom &g, const TallyArgs *tall
                              (unsigned long long)g.shard_stride, vpc * 16u);
 
         // ---- RS(3,2) row kernel: aligned uniform geometry, codewords up to 256 columns ----
-        if (use_rs32 && coder->variant != 1 && padded && vpc >= 1 && vpc <= 256 && g.n <= 0xffffffffull &&
+        if (use_rs32 && (coder->variant & 15) != 1 && padded && vpc >= 1 && vpc <= 256 && g.n <= 0xffffffffull &&
             ((reinterpret_cast<uintptr_t>(g.data) | g.data_stride) & 15u) == 0u &&
             (tally == nullptr || tally->planes == nullptr || tally->G == g.n)) {
             Enc32Row Rw;
@@ -613,14 +655,26 @@ int launch_rs_encode(ss_rs_coder *coder, const EncGeom &g, const TallyArgs *tall
             const uint32_t threads = (vpc + 31u) & ~31u;
             // resident CTAs per SM (2048 threads, 32 CTAs) x a few waves; every CTA strides over codewords
             uint32_t per_sm = 2048u / threads; if (per_sm > 32u) per_sm = 32u;
-            uint64_t ctas = static_cast<uint64_t>(ctx->sm_count) * per_sm * 4ull;
+            const int vr = coder->variant & 15, vchunk = (coder->variant >> 4) & 1, vw = (coder->variant >> 5) & 7;
+            static const uint64_t kWaves[8] = {16, 1, 2, 4, 64, 256, 1u << 20, 8};   // [0] = default, rest: tuning
+            const uint64_t waves = kWaves[vw];
+            uint64_t ctas = static_cast<uint64_t>(ctx->sm_count) * per_sm * waves;
             if (ctas > g.n) ctas = g.n;
+            Rw.chunk = 0;
+            if (vchunk) { Rw.chunk = static_cast<uint32_t>((g.n + ctas - 1) / ctas); ctas = (g.n + Rw.chunk - 1) / Rw.chunk; }
             const uint32_t grid = static_cast<uint32_t>(ctas);
             // register budget variants (tuning knob ss_rs_set_variant): 0/2 = 40 regs, 3 = 32 regs, 4 = unconstrained
-            if (Rw.emit_data) rs32_encode_row_kernel<true, 256, 1><<<grid, threads, 0, st>>>(Rw);
-            else if (threads <= 128 && coder->variant == 3) rs32_encode_row_kernel<false, 128, 16><<<grid, threads, 0, st>>>(Rw);
-            else if (threads <= 128 && coder->variant != 4) rs32_encode_row_kernel<false, 128, 12><<<grid, threads, 0, st>>>(Rw);
-            else rs32_encode_row_kernel<false, 256, 1><<<grid, threads, 0, st>>>(Rw);
+            // Register budget: 56/thread (9 CTAs of <= 128 threads per SM) measured best on B200 -- more
+            // occupancy (40 or 32 registers) spills, fewer resident CTAs (64+) loses latency hiding
+            // (profiles/r01_row_kernel_sweep.txt).  The other budgets stay selectable for tuning.
+            if (threads > 128) {
+                if (Rw.emit_data) rs32_encode_row_kernel<true, 256, 4><<<grid, threads, 0, st>>>(Rw);
+                else rs32_encode_row_kernel<false, 256, 4><<<grid, threads, 0, st>>>(Rw);
+            } else if (Rw.emit_data) rs32_encode_row_kernel<true, 128, 8><<<grid, threads, 0, st>>>(Rw);
+            else if (vr == 3) rs32_encode_row_kernel<false, 128, 16><<<grid, threads, 0, st>>>(Rw);   // 32 regs
+            else if (vr == 2) rs32_encode_row_kernel<false, 128, 12><<<grid, threads, 0, st>>>(Rw);   // 40 regs
+            else if (vr == 6) rs32_encode_row_kernel<false, 128, 8><<<grid, threads, 0, st>>>(Rw);    // 64 regs
+            else rs32_encode_row_kernel<false, 128, 9><<<grid, threads, 0, st>>>(Rw);                 // 56 regs
             coder->last_kernel = Rw.planes ? "rs32_encode_row_kernel+tally" : "rs32_encode_row_kernel";
             SS_CUDA(cudaGetLastError());
             ctx->launches++;
@@ -655,7 +709,7 @@ int launch_rs_encode(ss_rs_coder *coder, const EncGeom &g, const TallyArgs *tall
             if (use_rs32) {
                 rs32_encode_uniform_kernel<<<grid, kThreads, 0, st>>>(E);
                 coder->last_kernel = E.planes ? "rs32_encode_uniform_kernel+tally" : "rs32_encode_uniform_kernel";
-            } else if (d <= 8 && coder->variant != 5) {
+            } else if (d <= 8 && (coder->variant & 15) != 5) {
                 const uint32_t *prog = static_cast<const uint32_t *>(coder->enc_prog);
                 SS_TRY(dispatch_d(d, [&](auto DC) {
                     horner_encode_uniform_kernel<decltype(DC)::value><<<grid, kThreads, 0, st>>>(E, prog, d, p);
@@ -689,7 +743,7 @@ int launch_rs_encode(ss_rs_coder *coder, const EncGeom &g, const TallyArgs *tall
     if (use_rs32) {
         rs32_encode_ragged_kernel<<<grid, kThreads, 0, st>>>(E);
         coder->last_kernel = "rs32_encode_ragged_kernel";
-    } else if (d <= 8 && coder->variant != 5) {
+    } else if (d <= 8 && (coder->variant & 15) != 5) {
         const uint32_t *prog = static_cast<const uint32_t *>(coder->enc_prog);
         SS_TRY(dispatch_d(d, [&](auto DC) {
             horner_encode_ragged_kernel<decltype(DC)::value><<<grid, kThreads, 0, st>>>(E, prog, d, p);
@@ -733,7 +787,7 @@ int launch_rs_reconstruct(ss_rs_coder *coder, uint8_t *shards, uint64_t plane_st
     A.padded = padded ? 1u : 0u;
     A.hmask_off = static_cast<uint32_t>(coder->p * coder->d * 8);
     const uint32_t grid = ragged_grid(ctx, n);
-    if (coder->d <= 8 && coder->variant != 5) {
+    if (coder->d <= 8 && (coder->variant & 15) != 5) {
         SS_TRY(dispatch_d(coder->d, [&](auto DC) {
             horner_reconstruct_kernel<decltype(DC)::value><<<grid, kThreads, 0, ctx->stream>>>(A);
             return SS_OK;
