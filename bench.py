@@ -574,21 +574,18 @@ def run_cfg4(args, ctx, rs, dev, world, rank, peak, peak_src):
     ms_enc = _time_steps(torch, lambda: rs.encode_batch(arena, doff, dlen, parity, lay["plane_bytes"], poff), args.steps, 1)
     # spot check vs oracle
     idx = np.arange(0, n, max(1, n // 64))
-    a = arena.cpu().numpy() if lay["data_bytes"] < (1 << 31) else None
-    note = None
-    if a is not None:
-        sub_len = lens[idx]; sub_lay = wl.ragged_layout(sub_len, D)
-        sub = np.zeros(sub_lay["data_bytes"] + 64, dtype=np.uint8)
-        for j, g in enumerate(idx):
-            o = int(lay["data_off"][g]); so = int(sub_lay["data_off"][j])
-            sub[so:so + int(lens[g])] = a[o:o + int(lens[g])]
-        want = np.zeros((P, sub_lay["plane_bytes"]), dtype=np.uint8)
-        oracle.rs_encode_batch(D, P, sub, sub_lay["data_off"], sub_len, want.reshape(-1), sub_lay["plane_bytes"], sub_lay["par_off"])
-        got = parity.cpu().numpy()
-        for j, g in enumerate(idx):
-            Lg = int(lay["L"][g]); o = int(lay["par_off"][g]); so = int(sub_lay["par_off"][j])
-            assert (got[:, o:o + Lg] == want[:, so:so + Lg]).all(), "cfg4 parity check failed"
-        note = f"{len(idx)} sampled codewords bit-exact vs oracle"
+    sub_len = lens[idx]; sub_lay = wl.ragged_layout(sub_len, D)
+    sub = np.zeros(sub_lay["data_bytes"] + 64, dtype=np.uint8)
+    for j, g in enumerate(idx):          # gather the sampled payloads / parities on the device, copy only those
+        o = int(lay["data_off"][g]); so = int(sub_lay["data_off"][j]); ln = int(lens[g])
+        sub[so:so + ln] = arena[o:o + ln].cpu().numpy()
+    want = np.zeros((P, sub_lay["plane_bytes"]), dtype=np.uint8)
+    oracle.rs_encode_batch(D, P, sub, sub_lay["data_off"], sub_len, want.reshape(-1), sub_lay["plane_bytes"], sub_lay["par_off"])
+    for j, g in enumerate(idx):
+        Lg = int(lay["L"][g]); o = int(lay["par_off"][g]); so = int(sub_lay["par_off"][j])
+        got = parity[:, o:o + Lg].cpu().numpy()
+        assert (got == want[:, so:so + Lg]).all(), "cfg4 parity check failed"
+    note = f"{len(idx)} sampled codewords bit-exact vs oracle"
     alg = int((lay["L"].astype(np.int64) * (D + P)).sum()) + n * 22
     if rank == 0:
         print(json.dumps({"metric": "RS shard GB/s, Crossword ragged encode + coverage tally", "value": alg / (ms * 1e-3) / 1e9,

@@ -94,7 +94,11 @@ static int pipeline_staging(ss_ctx *ctx, size_t in_bytes, size_t out_bytes) {
 }
 
 // ---- coefficient programs -----------------------------------------------------------------------
-static size_t prog_bytes(int d, int p) { return sizeof(ProgHeader) + 2 * size_t(p) * size_t(d) * 8 * 4; }
+// header + splats[p*d*8] + hmask[p*d*8] + (d <= 4) transposed masks hmT[p*8*4] (one uint4 = the masks of all
+// inputs for one (output, bit) pair)
+static size_t prog_bytes(int d, int p) {
+    return sizeof(ProgHeader) + 2 * size_t(p) * size_t(d) * 8 * 4 + (d <= 4 ? size_t(p) * 8 * 4 * 4 : 0);
+}
 
 // fills, for coefficient c = c[j][i] of a (p x d) program: the bit-plane splats, the Horner bit masks
 // (stored p*d*8 words after the splats) and the running top bit of row j
@@ -106,6 +110,7 @@ static void fill_coef(uint8_t *prog, int d, int p, int j, int i, uint8_t c) {
         const uint32_t b = gf::mul(c, static_cast<uint8_t>(1u << k));
         splat[(size_t(j) * d + i) * 8 + k] = b * 0x01010101u;
         hmask[(size_t(j) * d + i) * 8 + k] = ((c >> k) & 1u) ? 0xffffffffu : 0u;
+        if (d <= 4) (hmask + size_t(p) * d * 8)[(size_t(j) * 8 + k) * 4 + i] = ((c >> k) & 1u) ? 0xffffffffu : 0u;
         if (((c >> k) & 1u) && k > h->top[j]) h->top[j] = static_cast<uint8_t>(k);
     }
 }

@@ -203,15 +203,23 @@ __device__ __forceinline__ void rs32_word_fast(uint32_t a, uint32_t b, uint32_t 
 template <bool EMIT, bool MASKED>
 __device__ __forceinline__ void rs32_row_column(const uint8_t *__restrict__ src, uint8_t *__restrict__ out,
                                                 uint64_t plane_stride, uint32_t k, uint32_t o1, uint32_t o2,
-                                                uint32_t s1, uint32_t s2, int nva, int nvb, int nvc, int onv) {
-    // loads first (pairs adjacent so the second one hits the sectors the first just brought into L1)
-    uint4 a = dev::ldg128(src + k);
-    const uint4 b0 = dev::ldg128(src + o1);
+                                                uint32_t s0, uint32_t s1, uint32_t s2, int nva, int nvb, int nvc,
+                                                int onv) {
+    // `src` is the 16-byte-aligned address at or below the payload (payload = src + s0); o1/o2 are aligned
+    // offsets from src.  Loads first (pairs adjacent so the second one hits the sectors the first just
+    // brought into L1), then the byte funnels.
+    const uint4 a0 = dev::ldg128(src + k);
+    uint4 a1 = a0;
+    if (s0 != 0u && (!MASKED || static_cast<int>(s0) + nva > 16)) a1 = dev::ldg128(src + k + 16u);
+    uint4 b0 = make_uint4(0u, 0u, 0u, 0u);
+    if (!MASKED || nvb > 0) b0 = dev::ldg128(src + o1);   // a window entirely in the zero padding is never read
     uint4 b1 = b0;
     if (s1 != 0u && (!MASKED || static_cast<int>(s1) + nvb > 16)) b1 = dev::ldg128(src + o1 + 16u);
-    const uint4 c0 = dev::ldg128(src + o2);
+    uint4 c0 = make_uint4(0u, 0u, 0u, 0u);
+    if (!MASKED || nvc > 0) c0 = dev::ldg128(src + o2);
     uint4 c1 = c0;
     if (s2 != 0u && (!MASKED || static_cast<int>(s2) + nvc > 16)) c1 = dev::ldg128(src + o2 + 16u);
+    uint4 a = s0 != 0u ? funnel16(a0, a1, s0) : a0;
     uint4 b = s1 != 0u ? funnel16(b0, b1, s1) : b0;
     uint4 c = s2 != 0u ? funnel16(c0, c1, s2) : c0;
     if (MASKED) {
@@ -275,13 +283,13 @@ __global__ void __launch_bounds__(MAXT, MINB) rs32_encode_row_kernel(const __gri
         for (uint32_t g = g_begin; g < g_end; g += g_step)
             rs32_row_column<EMIT, false>(P.data + static_cast<uint64_t>(g) * P.data_stride,
                                          P.parity + static_cast<uint64_t>(g) * P.shard_stride, P.plane_stride, k, o1, o2,
-                                         s1, s2, 16, 16, 16, 16);
+                                         0u, s1, s2, 16, 16, 16, 16);
     } else {
 #pragma unroll 1
         for (uint32_t g = g_begin; g < g_end; g += g_step)
             rs32_row_column<EMIT, true>(P.data + static_cast<uint64_t>(g) * P.data_stride,
                                         P.parity + static_cast<uint64_t>(g) * P.shard_stride, P.plane_stride, k, o1, o2,
-                                        s1, s2, nva, nvb, nvc, onv);
+                                        0u, s1, s2, nva, nvb, nvc, onv);
     }
 }
 
@@ -296,19 +304,50 @@ struct EncRagged {
     uint32_t padded;
 };
 
-__global__ void __launch_bounds__(kThreads) rs32_encode_ragged_kernel(const __grid_constant__ EncRagged P) {
+__global__ void __launch_bounds__(kThreads, 4) rs32_encode_ragged_kernel(const __grid_constant__ EncRagged P) {
+    // a warp per codeword; the byte-funnel parameters are per-codeword, hence warp-uniform
     const uint32_t lane = threadIdx.x & 31u;
     const uint64_t warp = (static_cast<uint64_t>(blockIdx.x) * kThreads + threadIdx.x) >> 5;
     const uint64_t nwarps = (static_cast<uint64_t>(gridDim.x) * kThreads) >> 5;
+    const bool padded = (P.padded & 1u) != 0u, emit = (P.padded & 2u) != 0u;
+    auto clamp16 = [](int64_t r) { return r > 16 ? 16 : (r < 0 ? 0 : static_cast<int>(r)); };
+    // metadata of the next codeword is fetched while the current one is being encoded
+    uint32_t nx_len = 0; uint64_t nx_off = 0, nx_poff = 0;
+    if (warp < P.n) { nx_len = __ldg(P.data_len + warp); nx_off = __ldg(P.data_off + warp); nx_poff = __ldg(P.par_off + warp); }
     for (uint64_t g = warp; g < P.n; g += nwarps) {
-        const uint32_t len = __ldg(P.data_len + g);
+        const uint32_t len = nx_len;
+        const uint8_t *pay = P.data + nx_off;
+        uint8_t *out = P.parity + nx_poff;
+        if (g + nwarps < P.n) {
+            nx_len = __ldg(P.data_len + g + nwarps); nx_off = __ldg(P.data_off + g + nwarps); nx_poff = __ldg(P.par_off + g + nwarps);
+        }
         if (len == 0u) continue;                      // null codeword (rscoding.rs:451-453)
         const uint32_t L = (len + 2u) / 3u;           // rscoding.rs:177-181 with d = 3
         const uint32_t vpc = (L + 15u) >> 4;
-        const uint8_t *src = P.data + __ldg(P.data_off + g);
-        uint8_t *out = P.parity + __ldg(P.par_off + g);
-        for (uint32_t v = lane; v < vpc; v += 32u)
-            rs32_column(src, len, L, v * 16u, out, P.plane_stride, (P.padded & 1u) != 0u, (P.padded & 2u) != 0u);
+        if (!padded || emit) {                        // byte-exact outputs / emit: general masked path
+            for (uint32_t v = lane; v < vpc; v += 32u)
+                rs32_column(pay, len, L, v * 16u, out, P.plane_stride, padded, emit);
+            continue;
+        }
+        const uint32_t s0 = static_cast<uint32_t>(reinterpret_cast<uintptr_t>(pay)) & 15u;
+        const uint8_t *src = pay - s0;
+        const uint32_t s1 = (s0 + L) & 15u, s2 = (s0 + 2u * L) & 15u;
+        const uint32_t fast_cols = len >= 2u * L ? (((len - 2u * L) < L ? (len - 2u * L) : L) / 16u) : 0u;
+        for (uint32_t v0 = 0; v0 < vpc; v0 += 32u) {
+            const uint32_t v = v0 + lane;
+            if (v >= vpc) break;
+            const uint32_t k = v * 16u;
+            const uint32_t o1 = s0 + L + k - s1, o2 = s0 + 2u * L + k - s2;
+            if (v0 + 32u <= fast_cols) {
+                rs32_row_column<false, false>(src, out, P.plane_stride, k, o1, o2, s0, s1, s2, 16, 16, 16, 16);
+            } else {
+                rs32_row_column<false, true>(src, out, P.plane_stride, k, o1, o2, s0, s1, s2,
+                                             clamp16(static_cast<int64_t>(len) - k),
+                                             clamp16(static_cast<int64_t>(len) - L - k),
+                                             clamp16(static_cast<int64_t>(len) - 2ll * L - k),
+                                             clamp16(static_cast<int64_t>(L) - k));
+            }
+        }
     }
 }
 
@@ -395,6 +434,7 @@ struct DecArgs {
     int d;
     uint32_t padded;
     uint32_t hmask_off;       // words from the splat table to the Horner mask table (p*d*8)
+    uint32_t need_mask;       // shards that must be present for a codeword to need no work (data only, or all)
 };
 
 template <int P>
@@ -472,19 +512,52 @@ __device__ __forceinline__ uint4 horner_row(const uint4 (&x)[D], int d, const ui
     return acc;
 }
 
+// Horner row for d <= 4 with the transposed mask table: one 128-bit load per bit level brings the masks of
+// all inputs (hmT[(j*8 + k)*4 + i]).
 template <int D>
-__global__ void __launch_bounds__(kThreads) horner_reconstruct_kernel(const __grid_constant__ DecArgs A) {
+__device__ __forceinline__ uint4 horner_row_t(const uint4 (&x)[D], const uint4 *__restrict__ hmT_j, int top) {
+    uint4 acc = make_uint4(0u, 0u, 0u, 0u);
+    for (int k = top; k >= 0; --k) {
+        const uint4 hm = __ldg(hmT_j + k);   // compiler-visible load: may be hoisted / batched across bit levels
+        if (k != top) {
+            const uint4 m = make_uint4(msb_mask(acc.x), msb_mask(acc.y), msb_mask(acc.z), msb_mask(acc.w));
+            acc.x = ((acc.x * 2u) & 0xfefefefeu) ^ (m.x & 0x1d1d1d1du);
+            acc.y = ((acc.y * 2u) & 0xfefefefeu) ^ (m.y & 0x1d1d1d1du);
+            acc.z = ((acc.z * 2u) & 0xfefefefeu) ^ (m.z & 0x1d1d1d1du);
+            acc.w = ((acc.w * 2u) & 0xfefefefeu) ^ (m.w & 0x1d1d1d1du);
+        }
+        const uint32_t hmi[4] = {hm.x, hm.y, hm.z, hm.w};
+#pragma unroll
+        for (int i = 0; i < D; ++i) {
+            acc.x ^= x[i].x & hmi[i];
+            acc.y ^= x[i].y & hmi[i];
+            acc.z ^= x[i].z & hmi[i];
+            acc.w ^= x[i].w & hmi[i];
+        }
+    }
+    return acc;
+}
+
+template <int D>
+__global__ void __launch_bounds__(kThreads, 4) horner_reconstruct_kernel(const __grid_constant__ DecArgs A) {
     const uint32_t lane = threadIdx.x & 31u;
     const uint64_t warp = (static_cast<uint64_t>(blockIdx.x) * kThreads + threadIdx.x) >> 5;
     const uint64_t nwarps = (static_cast<uint64_t>(gridDim.x) * kThreads) >> 5;
     const int d = A.d;
+    uint32_t nx_len = 0, nx_pat = 0;
+    if (warp < A.n) { nx_len = __ldg(A.data_len + warp); nx_pat = __ldg(A.present + warp); }
     for (uint64_t g = warp; g < A.n; g += nwarps) {
-        const uint32_t len = __ldg(A.data_len + g);
+        const uint32_t len = nx_len;
+        const uint32_t pat = nx_pat & A.pattern_mask;
+        if (g + nwarps < A.n) { nx_len = __ldg(A.data_len + g + nwarps); nx_pat = __ldg(A.present + g + nwarps); }
         if (len == 0u) {                              // null codeword: rscoding.rs:495-497
             if (lane == 0u) A.status[g] = SS_ERR_INVALID_ARG;
             continue;
         }
-        const uint32_t pat = __ldg(A.present + g) & A.pattern_mask;
+        if ((pat & A.need_mask) == A.need_mask) {     // nothing to regenerate: no table look-up at all
+            if (lane == 0u) A.status[g] = SS_OK;
+            continue;
+        }
         const uint8_t *prog = A.progs + static_cast<uint64_t>(pat) * A.prog_stride;
         const ProgHeader *hdr = reinterpret_cast<const ProgHeader *>(prog);
         const int valid = hdr->valid;
@@ -495,14 +568,44 @@ __global__ void __launch_bounds__(kThreads) horner_reconstruct_kernel(const __gr
         const uint32_t L = (len + static_cast<uint32_t>(d) - 1u) / static_cast<uint32_t>(d);
         const uint32_t vpc = (L + 15u) >> 4;
         uint8_t *base = A.shards + __ldg(A.off + g);
+        if (D <= 4) {
+            const uint4 *hmT = reinterpret_cast<const uint4 *>(hmask + A.hmask_off);   // after the [p*d*8] mask table
+            const uint8_t *sp[D];
+#pragma unroll
+            for (int i = 0; i < D; ++i) sp[i] = base + static_cast<uint64_t>(hdr->src[i < d ? i : 0]) * A.plane_stride;
+            const int top0 = hdr->top[0], top1 = hdr->top[1];
+            uint8_t *dp0 = base + static_cast<uint64_t>(hdr->dst[0]) * A.plane_stride;
+            uint8_t *dp1 = base + static_cast<uint64_t>(hdr->dst[1]) * A.plane_stride;
+            for (uint32_t v = lane; v < vpc; v += 32u) {
+                const uint32_t k = v * 16u;
+                const int nv = static_cast<int>(L - k) > 16 ? 16 : static_cast<int>(L - k);
+                uint4 x[D];
+#pragma unroll
+                for (int i = 0; i < D; ++i) {
+                    x[i] = make_uint4(0u, 0u, 0u, 0u);
+                    if (i < d) x[i] = A.padded != 0u ? keep_bytes(dev::ldg128(sp[i] + k), nv) : load16(sp[i] + k, nv);
+                }
+                store16(dp0 + k, horner_row_t<D>(x, hmT, top0), nv, A.padded != 0u);
+                if (n_out > 1) store16(dp1 + k, horner_row_t<D>(x, hmT + 8, top1), nv, A.padded != 0u);
+                for (int j = 2; j < n_out; ++j)
+                    store16(base + static_cast<uint64_t>(hdr->dst[j]) * A.plane_stride + k,
+                            horner_row_t<D>(x, hmT + j * 8, hdr->top[j]), nv, A.padded != 0u);
+            }
+            continue;
+        }
         for (uint32_t v = lane; v < vpc; v += 32u) {
             const uint32_t k = v * 16u;
             const int nv = static_cast<int>(L - k) > 16 ? 16 : static_cast<int>(L - k);
             uint4 x[D];
 #pragma unroll
-            for (int i = 0; i < D; ++i)
-                x[i] = (i < d) ? load16(base + static_cast<uint64_t>(hdr->src[i]) * A.plane_stride + k, nv)
-                               : make_uint4(0u, 0u, 0u, 0u);
+            for (int i = 0; i < D; ++i) {
+                x[i] = make_uint4(0u, 0u, 0u, 0u);
+                if (i < d) {
+                    const uint8_t *sp = base + static_cast<uint64_t>(hdr->src[i]) * A.plane_stride + k;
+                    // padded layout: every shard slot is 16-byte aligned -> one aligned 128-bit load
+                    x[i] = A.padded != 0u ? keep_bytes(dev::ldg128(sp), nv) : load16(sp, nv);
+                }
+            }
             for (int j = 0; j < n_out; ++j) {
                 const uint4 acc = horner_row<D>(x, d, hmask + j * d * 8, hdr->top[j]);
                 store16(base + static_cast<uint64_t>(hdr->dst[j]) * A.plane_stride + k, acc, nv, A.padded != 0u);
@@ -786,6 +889,7 @@ int launch_rs_reconstruct(ss_rs_coder *coder, uint8_t *shards, uint64_t plane_st
     A.d = coder->d;
     A.padded = padded ? 1u : 0u;
     A.hmask_off = static_cast<uint32_t>(coder->p * coder->d * 8);
+    A.need_mask = data_only ? ((1u << coder->d) - 1u) : A.pattern_mask;
     const uint32_t grid = ragged_grid(ctx, n);
     if (coder->d <= 8 && (coder->variant & 15) != 5) {
         SS_TRY(dispatch_d(coder->d, [&](auto DC) {
