@@ -59,6 +59,25 @@ def measured_peaks():
     return 6650.0, "fallback 6.65 TB/s (B200_PROFILING.md)"
 
 
+def copy_bandwidth_here(torch, dev):
+    """STREAM-style copy on THIS box, measured the way MEASURED_PEAKS.json was (b.copy_(a), 1 Gi bf16 elements,
+    read+write bytes, best of 10): boxes of the pool differ by several percent, so the live figure is reported
+    beside the pool-wide denominator."""
+    try:
+        a = torch.empty(1 << 30, dtype=torch.bfloat16, device=dev)
+        b = torch.empty_like(a)
+        a.fill_(1.0)
+        best = 0.0
+        for _ in range(10):
+            s = torch.cuda.Event(enable_timing=True); e = torch.cuda.Event(enable_timing=True)
+            s.record(); b.copy_(a); e.record(); torch.cuda.synchronize()
+            best = max(best, 2 * a.numel() * 2 / (s.elapsed_time(e) * 1e-3) / 1e9)
+        del a, b
+        return best
+    except Exception:
+        return None
+
+
 def profile_traffic(workload: str):
     """dram bytes per launch from the committed ncu --set full capture (profiles/), or None."""
     f = ROOT / "profiles" / "traffic.json"
@@ -336,6 +355,11 @@ def run_ours(args):
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": profile_traffic(args.workload), "kernel": rs.last_kernel() if args.workload != "cfg2" else "tally_planes_kernel",
                 "kernel_ms": kernel_ms, "algorithmic_bytes_per_launch": alg * n, "peak_source": peak_src + " (burst figure; kernel timed alone)"}
+    if rank == 0:
+        here = copy_bandwidth_here(torch, dev)
+        if here:
+            roofline["copy_gbs_this_box"] = here
+            roofline["frac_of_copy_this_box"] = achieved / here
 
     extra = {}
     if rank == 0 and args.workload == "cfg3" and world == 1:
