@@ -45,6 +45,7 @@ def parse_args():
     ap.add_argument("--workload", default="cfg3", choices=["cfg3", "cfg2", "cfg5", "cfg3b", "cfg4"])
     ap.add_argument("--groups", type=int, default=G_PER_GPU, help="groups per GPU")
     ap.add_argument("--variant", type=int, default=0, help="encode kernel variant (tuning)")
+    ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"], help="N>1: how shard planes reach the simulated peers")
     ap.add_argument("--no-tally", action="store_true", help="tuning: time the encode alone")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
@@ -246,6 +247,27 @@ def run_ours(args):
     ack_recv = torch.empty((R, n), dtype=torch.int64, device=dev) if world > 1 else None
     rounds = sharding.exchange_rounds(R, world, rank) if world > 1 else []
     flags = SS_RS_OUT_PADDED16 | (2 if world > 1 else 0)
+    p2p = None
+    if world > 1 and args.exchange == "p2p":
+        # every rank hosts R shard planes (replica r of the groups led from rank (me - r) % world) and the R ack
+        # planes of its own groups; peers map both through CUDA IPC and the kernels store straight into them.
+        log = ctx.dev_alloc(R * n * ds)
+        acks = ctx.dev_alloc(R * n * 8)
+        handles = [None] * world
+        dist.all_gather_object(handles, (ctx.ipc_export(log), ctx.ipc_export(acks)))
+        peer_log, peer_acks = {}, {}
+        for q in range(world):
+            if q == rank:
+                peer_log[q], peer_acks[q] = log, acks
+            else:
+                peer_log[q] = ctx.ipc_open(handles[q][0], R * n * ds)
+                peer_acks[q] = ctx.ipc_open(handles[q][1], R * n * 8)
+        shard_ptrs = [peer_log[sharding.replica_rank(rank, r, world)].ptr + r * n * ds for r in range(R)]
+        acks_t = acks.tensor().view(torch.int64).view(R, n)
+        acks_t.copy_(planes)
+        tiny = torch.zeros(1, dtype=torch.int32, device=dev)
+        p2p = dict(log=log, acks=acks, peer_log=peer_log, peer_acks=peer_acks, shard_ptrs=shard_ptrs, acks_t=acks_t)
+        dist.barrier()
 
     def exchange():
         # shard plane r of my groups -> rank (rank + r) % world ; then each simulated follower acks:
@@ -266,6 +288,16 @@ def run_ours(args):
             return
         if args.no_tally:
             check(ctx.lib.ss_rs_encode_uniform_dev(rs.h, data.data_ptr(), DATA_LEN, DATA_LEN, n, parity.data_ptr(), ps, ds, flags))
+            return
+        if p2p is not None:
+            # ONE kernel: tally the ack planes the followers wrote last step, RS-encode, and store shard r of
+            # every local group into the HBM of the GPU that simulates replica r (NVLink stores)
+            rs.accept_step_replicate(data, DATA_LEN, p2p["shard_ptrs"], ds, p2p["acks_t"], THRESH_RSPAXOS, committed, bar)
+            # the simulated follower (home h, replica r) on this rank acks: its ack plane goes to h's ack buffer
+            for r in range(R):
+                h = (rank - r) % world
+                ctx.copy_d2d(p2p["peer_acks"][h].ptr + r * n * 8, planes[r].data_ptr(), n * 8)
+            dist.all_reduce(tiny)          # stream-ordered barrier: every rank's stores of this step are done
             return
         check(ctx.lib.ss_accept_step_fused_dev(rs.h, data.data_ptr(), DATA_LEN, DATA_LEN, n, parity.data_ptr(), ps, ds,
                                                flags, (ack_recv if world > 1 else planes).data_ptr(), R,
@@ -309,6 +341,8 @@ def run_ours(args):
         a.record()
         if world == 1:
             step()
+        elif p2p is not None:
+            rs.accept_step_replicate(data, DATA_LEN, p2p["shard_ptrs"], ds, p2p["acks_t"], THRESH_RSPAXOS, committed, bar)
         else:
             check(ctx.lib.ss_accept_step_fused_dev(rs.h, data.data_ptr(), DATA_LEN, DATA_LEN, n, parity.data_ptr(), ps, ds,
                                                    flags, ack_recv.data_ptr(), R, THRESH_RSPAXOS, committed.data_ptr(),
@@ -330,9 +364,16 @@ def run_ours(args):
         idx = torch.arange(0, n, max(1, n // 128), device=dev)
         if args.workload != "cfg2":
             want = oracle.rs_encode_uniform(D, P, data[idx].cpu().numpy(), DATA_LEN)
-            got = parity[:, idx].cpu().numpy()
+            if p2p is not None:
+                # read my groups' shards back from wherever the kernel put them (peer HBM through the IPC mapping)
+                got = np.stack([p2p["peer_log"][sharding.replica_rank(rank, r, world)].tensor().view(R, n, ds)[r][idx].cpu().numpy()
+                                for r in range(D, D + P)])
+                dshard = p2p["peer_log"][sharding.replica_rank(rank, 1, world)].tensor().view(R, n, ds)[1][idx].cpu().numpy()
+                assert (dshard[:, :L] == data[idx][:, L:2 * L].cpu().numpy()).all(), "bench data-shard check failed"
+            else:
+                got = parity[:, idx].cpu().numpy()
             assert (got == want).all(), "bench parity check failed"
-        src = (ack_recv if world > 1 else planes)
+        src = (p2p["acks_t"] if p2p is not None else (ack_recv if world > 1 else planes))
         if args.no_tally:
             committed.zero_()
             ctx.tally_planes(src, THRESH_RSPAXOS if args.workload != "cfg2" else THRESH_MULTIPAXOS, True, committed, bar)
@@ -355,6 +396,17 @@ def run_ours(args):
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": profile_traffic(args.workload), "kernel": rs.last_kernel() if args.workload != "cfg2" else "tally_planes_kernel",
                 "kernel_ms": kernel_ms, "algorithmic_bytes_per_launch": alg * n, "peak_source": peak_src + " (burst figure; kernel timed alone)"}
+    if world > 1 and args.workload == "cfg3":
+        remote = sum(1 for r in range(R) if sharding.replica_rank(rank, r, world) != rank)
+        nv_bytes = remote * n * L
+        nv_ms = nv_bytes / 770e9 * 1e3
+        roofline["comm"] = {"exchange": args.exchange if p2p is not None or args.exchange == "nccl" else "nccl",
+                            "remote_planes_per_rank": remote, "nvlink_bytes_per_rank_per_step": nv_bytes,
+                            "nvlink_ref_gbs": 770.0, "nvlink_bound_ms": nv_ms, "hbm_bound_ms": alg * n / (peak * 1e9) * 1e3,
+                            "step_ms": ms_per_step, "frac_of_slower_bound": max(nv_ms, alg * n / (peak * 1e9) * 1e3) / ms_per_step,
+                            "note": "target time = slower of HBM bytes / measured copy bandwidth and NVLink bytes / 770 GB/s "
+                                    "(measured peer-copy reference, B200_PROFILING.md); remote shards are written by the encode "
+                                    "kernel itself into peer HBM" if p2p is not None else "NCCL all-to-all baseline"}
     if rank == 0:
         here = copy_bandwidth_here(torch, dev)
         if here:

@@ -91,6 +91,19 @@ int ss_host_free(ss_ctx *ctx, void *hptr);
 int ss_copy_h2d(ss_ctx *ctx, void *dst_dev, const void *src_host, size_t bytes); /* async */
 int ss_copy_d2h(ss_ctx *ctx, void *dst_host, const void *src_dev, size_t bytes); /* async */
 
+int ss_copy_d2d(ss_ctx *ctx, void *dst_dev, const void *src_dev, size_t bytes);  /* async; dst/src may be peer memory */
+
+/* ---- cross-process peer memory (one process per GPU, NVLink) ---------------------------------
+ * ss_ipc_export gives a 64-byte handle for a buffer obtained from ss_dev_alloc; another process on the same
+ * box turns it into a device pointer with ss_ipc_open (peer access is enabled on first use).  The pointers
+ * can be passed to ss_accept_step_replicate_dev / ss_copy_d2d: kernels then store straight into the peer
+ * GPU's HBM over NVLink -- the replacement for TransportHub::send_msg of a shard (server/transport.rs:258-345,
+ * rspaxos/request.rs:127-142) when the simulated replicas of a group live on the GPUs of one box. */
+#define SS_IPC_HANDLE_BYTES 64
+int ss_ipc_export(ss_ctx *ctx, void *dptr, uint8_t handle[SS_IPC_HANDLE_BYTES]);
+int ss_ipc_open(ss_ctx *ctx, const uint8_t handle[SS_IPC_HANDLE_BYTES], void **dptr);
+int ss_ipc_close(ss_ctx *ctx, void *dptr);
+
 /* ---- Reed-Solomon coder --------------------------------------------------------------------
  * Replaces ReedSolomon::new(d, p) (constructors at rspaxos/mod.rs:606, crossword/mod.rs:827,
  * craft/mod.rs:534, benches/rse_bench.rs:51).  GF(2^8) poly 0x11D; systematic matrix
@@ -234,6 +247,17 @@ int ss_accept_step_fused_dev(ss_rs_coder *coder, const uint8_t *data, uint64_t d
                              uint64_t plane_stride, uint64_t shard_stride, uint32_t flags,
                              const uint64_t *planes, uint32_t n_replicas, uint32_t threshold,
                              uint64_t *committed, uint32_t *commit_bar);
+
+/* Fused encode + tally + REPLICATE (the multi-GPU accept step): as ss_accept_step_fused_dev, but shard j of the
+ * local groups (data shards included) is written to shard_planes[j] + g*shard_stride, where each shard_planes[j]
+ * is a device pointer into LOCAL memory or into a PEER GPU's memory (ss_ipc_open): the encode kernel itself
+ * delivers every replica's shard over NVLink -- no pack pass, no separate collective.  shard_planes is a HOST
+ * array of d+p pointers; every target slot is 16-byte aligned with capacity round_up(L,16).  RS(3,2) with
+ * 16-byte-aligned uniform payloads only (SS_ERR_UNSUPPORTED otherwise). */
+int ss_accept_step_replicate_dev(ss_rs_coder *coder, const uint8_t *data, uint64_t data_stride, uint32_t data_len,
+                                 uint64_t n_groups, uint8_t *const *shard_planes, uint64_t shard_stride,
+                                 const uint64_t *planes, uint32_t n_replicas, uint32_t threshold,
+                                 uint64_t *committed, uint32_t *commit_bar);
 
 /* ---- tuning / introspection (bench + tests) ------------------------------------------------ */
 /* selects the encode kernel variant: 0 = auto, 1 = direct-LDG, 2 = bulk-copy (TMA) ring */

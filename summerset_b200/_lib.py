@@ -53,6 +53,11 @@ SIGNATURES = {
     "ss_host_free": (_i, [_vp, _vp]),
     "ss_copy_h2d": (_i, [_vp, _vp, _vp, _sz]),
     "ss_copy_d2h": (_i, [_vp, _vp, _vp, _sz]),
+    "ss_copy_d2d": (_i, [_vp, _vp, _vp, _sz]),
+    "ss_ipc_export": (_i, [_vp, _vp, _vp]),
+    "ss_ipc_open": (_i, [_vp, _vp, C.POINTER(_vp)]),
+    "ss_ipc_close": (_i, [_vp, _vp]),
+    "ss_accept_step_replicate_dev": (_i, [_vp, _vp, _u64, _u32, _u64, C.POINTER(_vp), _u64, _vp, _u32, _u32, _vp, _vp]),
     "ss_rs_coder_create": (_i, [_vp, _i, _i, C.POINTER(_vp)]),
     "ss_rs_coder_destroy": (_i, [_vp]),
     "ss_rs_data_shard_count": (_i, [_vp]),

@@ -78,6 +78,26 @@ class Context:
         except Exception:
             pass
 
+    # ---- raw device buffers + cross-process peer memory ----------------------------------------------
+    def dev_alloc(self, nbytes: int) -> "DevBuffer":
+        p = C.c_void_p()
+        check(self.lib.ss_dev_alloc(self.h, nbytes, C.byref(p)))
+        return DevBuffer(self, p.value, nbytes, owned=True)
+
+    def ipc_export(self, buf: "DevBuffer") -> bytes:
+        h = (C.c_uint8 * 64)()
+        check(self.lib.ss_ipc_export(self.h, buf.ptr, h))
+        return bytes(h)
+
+    def ipc_open(self, handle: bytes, nbytes: int) -> "DevBuffer":
+        h = (C.c_uint8 * 64).from_buffer_copy(handle)
+        p = C.c_void_p()
+        check(self.lib.ss_ipc_open(self.h, h, C.byref(p)))
+        return DevBuffer(self, p.value, nbytes, owned=False)
+
+    def copy_d2d(self, dst_ptr: int, src_ptr: int, nbytes: int) -> None:
+        check(self.lib.ss_copy_d2d(self.h, dst_ptr, src_ptr, nbytes))
+
     # ---- tallies -------------------------------------------------------------------------------
     def tally_planes(self, planes: torch.Tensor, threshold: int, want_bar: bool = True,
                      committed: Optional[torch.Tensor] = None, commit_bar: Optional[torch.Tensor] = None):
@@ -147,6 +167,26 @@ class Context:
         check(self.lib.ss_raft_commit_scan_dev(self.h, _ptr(match), P, G, _ptr(last_commit), _ptr(log_end),
                                                _ptr(curr_term), _ptr(terms), W, threshold, _ptr(out)))
         return out
+
+
+class DevBuffer:
+    """A raw device allocation from ss_dev_alloc (or a peer GPU's buffer opened through CUDA IPC).
+    Exposes __cuda_array_interface__ so `torch.as_tensor(buf, device=...)` views it without a copy."""
+
+    def __init__(self, ctx: "Context", ptr: int, nbytes: int, owned: bool):
+        self.ctx, self.ptr, self.nbytes, self.owned = ctx, ptr, nbytes, owned
+        self.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (ptr, False), "version": 2}
+
+    def tensor(self) -> torch.Tensor:
+        return torch.as_tensor(self, device=torch.device("cuda", self.ctx.device))
+
+    def free(self) -> None:
+        if self.ptr:
+            if self.owned:
+                self.ctx.lib.ss_dev_free(self.ctx.h, self.ptr)
+            else:
+                self.ctx.lib.ss_ipc_close(self.ctx.h, self.ptr)
+            self.ptr = 0
 
 
 class ReedSolomon:
@@ -282,6 +322,17 @@ class ReedSolomon:
         check(self.lib.ss_accept_step_fused_dev(self.h, _ptr(data), data.shape[1], data_len, n, _ptr(parity), ps, ds,
                                                 SS_RS_OUT_PADDED16, _ptr(planes), R, threshold, _ptr(committed),
                                                 _ptr(commit_bar)))
+
+    def accept_step_replicate(self, data: torch.Tensor, data_len: int, shard_planes: Sequence[int], shard_stride: int,
+                              planes: Optional[torch.Tensor], threshold: int, committed: Optional[torch.Tensor],
+                              commit_bar: Optional[torch.Tensor]) -> None:
+        """Multi-GPU accept step: encode + tally + write every shard plane to its (local or peer) destination.
+        shard_planes: d+p raw device pointers (ints)."""
+        arr = (C.c_void_p * len(shard_planes))(*shard_planes)
+        n = data.shape[0]
+        R = planes.shape[0] if planes is not None else 0
+        check(self.lib.ss_accept_step_replicate_dev(self.h, _ptr(data), data.shape[1], data_len, n, arr, shard_stride,
+                                                    _ptr(planes), R, threshold, _ptr(committed), _ptr(commit_bar)))
 
     def encode_uniform_host(self, data: np.ndarray, data_len: int, parity: np.ndarray) -> None:
         """HOST buffers through ss_rs_encode_uniform: data uint8 [n, stride]; parity uint8 [p, n, shard_stride]."""

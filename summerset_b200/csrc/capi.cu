@@ -326,6 +326,37 @@ int ss_copy_d2h(ss_ctx *ctx, void *dst_host, const void *src_dev, size_t bytes) 
     return SS_OK;
 }
 
+int ss_copy_d2d(ss_ctx *ctx, void *dst_dev, const void *src_dev, size_t bytes) {
+    SS_TRY(ctx_bind(ctx));
+    SS_CUDA(cudaMemcpyAsync(dst_dev, src_dev, bytes, cudaMemcpyDefault, ctx->stream));
+    return SS_OK;
+}
+
+int ss_ipc_export(ss_ctx *ctx, void *dptr, uint8_t handle[SS_IPC_HANDLE_BYTES]) {
+    SS_TRY(ctx_bind(ctx));
+    if (dptr == nullptr || handle == nullptr) return set_error(SS_ERR_INVALID_ARG, "null argument");
+    static_assert(sizeof(cudaIpcMemHandle_t) == SS_IPC_HANDLE_BYTES, "IPC handle size");
+    cudaIpcMemHandle_t h;
+    SS_CUDA(cudaIpcGetMemHandle(&h, dptr));
+    memcpy(handle, &h, sizeof(h));
+    return SS_OK;
+}
+
+int ss_ipc_open(ss_ctx *ctx, const uint8_t handle[SS_IPC_HANDLE_BYTES], void **dptr) {
+    SS_TRY(ctx_bind(ctx));
+    if (dptr == nullptr || handle == nullptr) return set_error(SS_ERR_INVALID_ARG, "null argument");
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle, sizeof(h));
+    SS_CUDA(cudaIpcOpenMemHandle(dptr, h, cudaIpcMemLazyEnablePeerAccess));
+    return SS_OK;
+}
+
+int ss_ipc_close(ss_ctx *ctx, void *dptr) {
+    SS_TRY(ctx_bind(ctx));
+    SS_CUDA(cudaIpcCloseMemHandle(dptr));
+    return SS_OK;
+}
+
 // ---- coder --------------------------------------------------------------------------------------
 int ss_rs_coder_create(ss_ctx *ctx, int d, int p, ss_rs_coder **out) {
     if (out == nullptr) return set_error(SS_ERR_INVALID_ARG, "null out pointer");
@@ -540,6 +571,41 @@ int ss_accept_step_fused_dev(ss_rs_coder *c, const uint8_t *data, uint64_t data_
     t.planes = planes; t.R = n_replicas; t.threshold = threshold; t.G = n_groups; t.committed = committed;
     t.commit_bar = commit_bar;
     return launch_rs_encode(c, g, &t);
+}
+
+int ss_accept_step_replicate_dev(ss_rs_coder *c, const uint8_t *data, uint64_t data_stride, uint32_t data_len,
+                                 uint64_t n_groups, uint8_t *const *shard_planes, uint64_t shard_stride,
+                                 const uint64_t *planes, uint32_t n_replicas, uint32_t threshold,
+                                 uint64_t *committed, uint32_t *commit_bar) {
+    if (c == nullptr) return set_error(SS_ERR_INVALID_ARG, "null coder");
+    if (n_groups == 0) return SS_OK;
+    if (!data || !shard_planes) return set_error(SS_ERR_INVALID_ARG, "null buffer");
+    if (!c->is_rs32) return set_error(SS_ERR_UNSUPPORTED, "replicate step is implemented for RS(3,2) (coder is %d,%d)", c->d, c->p);
+    const uint64_t L = (uint64_t(data_len) + 2) / 3, vpc = (L + 15) / 16;
+    if (data_len == 0 || vpc > 256 || ((reinterpret_cast<uintptr_t>(data) | data_stride | shard_stride) & 15u) ||
+        shard_stride < vpc * 16)
+        return set_error(SS_ERR_UNSUPPORTED, "replicate step needs 16-byte aligned uniform payloads of at most 12 KB");
+    for (int j = 0; j < 5; ++j)
+        if (shard_planes[j] == nullptr || (reinterpret_cast<uintptr_t>(shard_planes[j]) & 15u))
+            return set_error(SS_ERR_INVALID_ARG, "shard plane %d is null or not 16-byte aligned", j);
+    EncGeom g{};
+    g.data = data; g.data_off = nullptr; g.data_stride = data_stride; g.uni_len = data_len;
+    g.parity = shard_planes[3]; g.plane_stride = 16; g.shard_stride = shard_stride; g.n = n_groups;
+    g.flags = SS_RS_OUT_PADDED16 | SS_RS_EMIT_DATA;
+    g.planes5 = shard_planes;
+    TallyArgs t;
+    const bool with_tally = planes != nullptr;
+    if (with_tally) {
+        if (!committed) return set_error(SS_ERR_INVALID_ARG, "null committed buffer");
+        if (n_replicas == 0 || n_replicas > 16) return set_error(SS_ERR_INVALID_ARG, "n_replicas must be 1..16");
+        t.planes = planes; t.R = n_replicas; t.threshold = threshold; t.G = n_groups; t.committed = committed;
+        t.commit_bar = commit_bar;
+    }
+    const int saved = c->variant;
+    if ((c->variant & 15) == 1) c->variant &= ~15;     // the flat kernel has no peer-plane mode
+    const int rc = launch_rs_encode(c, g, with_tally ? &t : nullptr);
+    c->variant = saved;
+    return rc;
 }
 
 // ---- host-buffer batch encode: chunked, copy/compute overlapped -----------------------------------

@@ -149,8 +149,9 @@ __global__ void __launch_bounds__(kThreads) rs32_encode_uniform_kernel(const __g
 struct Enc32Row {
     const uint8_t *data;
     uint64_t data_stride;
-    uint8_t *parity;
-    uint64_t plane_stride, shard_stride;
+    uint8_t *plane[5];        // base of shard plane j (local memory, or a peer GPU's memory mapped over NVLink);
+                              // planes 0..2 (data shards) are only written when emit_data is set
+    uint64_t shard_stride;
     uint32_t n, len, L, vpc;
     uint32_t fast_cols;       // columns [0, fast_cols) need no masking
     uint32_t s1, s2;          // (L & 15), (2L & 15): misalignment of shards 1 and 2
@@ -201,8 +202,8 @@ __device__ __forceinline__ void rs32_word_fast(uint32_t a, uint32_t b, uint32_t 
 // one column of the row kernel.  MASKED: this warp owns the codeword's last column(s): inputs past data_len
 // are zeroed, outputs past L are zeroed, and a second aligned load is issued only when it holds a valid byte.
 template <bool EMIT, bool MASKED>
-__device__ __forceinline__ void rs32_row_column(const uint8_t *__restrict__ src, uint8_t *__restrict__ out,
-                                                uint64_t plane_stride, uint32_t k, uint32_t o1, uint32_t o2,
+__device__ __forceinline__ void rs32_row_column(const uint8_t *__restrict__ src, uint8_t *const (&out)[5],
+                                                uint32_t k, uint32_t o1, uint32_t o2,
                                                 uint32_t s0, uint32_t s1, uint32_t s2, int nva, int nvb, int nvc,
                                                 int onv) {
     // `src` is the 16-byte-aligned address at or below the payload (payload = src + s0); o1/o2 are aligned
@@ -236,12 +237,12 @@ __device__ __forceinline__ void rs32_row_column(const uint8_t *__restrict__ src,
         p0 = keep_bytes(p0, onv);
         p1 = keep_bytes(p1, onv);
     }
-    dev::stg128_cs(out + k, p0);
-    dev::stg128_cs(out + plane_stride + k, p1);
-    if (EMIT) {
-        dev::stg128_cs(out - 3 * plane_stride + k, MASKED ? keep_bytes(a, onv) : a);
-        dev::stg128_cs(out - 2 * plane_stride + k, MASKED ? keep_bytes(b, onv) : b);
-        dev::stg128_cs(out - 1 * plane_stride + k, MASKED ? keep_bytes(c, onv) : c);
+    dev::stg128_cs(out[3] + k, p0);
+    dev::stg128_cs(out[4] + k, p1);
+    if (EMIT) {   // data shards into their planes too: the pack-for-send of subset_copy (rscoding.rs:255-293)
+        dev::stg128_cs(out[0] + k, MASKED ? keep_bytes(a, onv) : a);
+        dev::stg128_cs(out[1] + k, MASKED ? keep_bytes(b, onv) : b);
+        dev::stg128_cs(out[2] + k, MASKED ? keep_bytes(c, onv) : c);
     }
 }
 
@@ -280,16 +281,22 @@ __global__ void __launch_bounds__(MAXT, MINB) rs32_encode_row_kernel(const __gri
     const uint32_t g_end = P.chunk ? (g_begin + P.chunk < P.n ? g_begin + P.chunk : P.n) : P.n;
     if (!warp_masked) {
 #pragma unroll 1
-        for (uint32_t g = g_begin; g < g_end; g += g_step)
-            rs32_row_column<EMIT, false>(P.data + static_cast<uint64_t>(g) * P.data_stride,
-                                         P.parity + static_cast<uint64_t>(g) * P.shard_stride, P.plane_stride, k, o1, o2,
-                                         0u, s1, s2, 16, 16, 16, 16);
+        for (uint32_t g = g_begin; g < g_end; g += g_step) {
+            const uint64_t so = static_cast<uint64_t>(g) * P.shard_stride;
+            uint8_t *const out[5] = {EMIT ? P.plane[0] + so : nullptr, EMIT ? P.plane[1] + so : nullptr,
+                                     EMIT ? P.plane[2] + so : nullptr, P.plane[3] + so, P.plane[4] + so};
+            rs32_row_column<EMIT, false>(P.data + static_cast<uint64_t>(g) * P.data_stride, out, k, o1, o2, 0u, s1, s2,
+                                         16, 16, 16, 16);
+        }
     } else {
 #pragma unroll 1
-        for (uint32_t g = g_begin; g < g_end; g += g_step)
-            rs32_row_column<EMIT, true>(P.data + static_cast<uint64_t>(g) * P.data_stride,
-                                        P.parity + static_cast<uint64_t>(g) * P.shard_stride, P.plane_stride, k, o1, o2,
-                                        0u, s1, s2, nva, nvb, nvc, onv);
+        for (uint32_t g = g_begin; g < g_end; g += g_step) {
+            const uint64_t so = static_cast<uint64_t>(g) * P.shard_stride;
+            uint8_t *const out[5] = {EMIT ? P.plane[0] + so : nullptr, EMIT ? P.plane[1] + so : nullptr,
+                                     EMIT ? P.plane[2] + so : nullptr, P.plane[3] + so, P.plane[4] + so};
+            rs32_row_column<EMIT, true>(P.data + static_cast<uint64_t>(g) * P.data_stride, out, k, o1, o2, 0u, s1, s2,
+                                        nva, nvb, nvc, onv);
+        }
     }
 }
 
@@ -338,10 +345,11 @@ __global__ void __launch_bounds__(kThreads, 4) rs32_encode_ragged_kernel(const _
             if (v >= vpc) break;
             const uint32_t k = v * 16u;
             const uint32_t o1 = s0 + L + k - s1, o2 = s0 + 2u * L + k - s2;
+            uint8_t *const outs[5] = {nullptr, nullptr, nullptr, out, out + P.plane_stride};
             if (v0 + 32u <= fast_cols) {
-                rs32_row_column<false, false>(src, out, P.plane_stride, k, o1, o2, s0, s1, s2, 16, 16, 16, 16);
+                rs32_row_column<false, false>(src, outs, k, o1, o2, s0, s1, s2, 16, 16, 16, 16);
             } else {
-                rs32_row_column<false, true>(src, out, P.plane_stride, k, o1, o2, s0, s1, s2,
+                rs32_row_column<false, true>(src, outs, k, o1, o2, s0, s1, s2,
                                              clamp16(static_cast<int64_t>(len) - k),
                                              clamp16(static_cast<int64_t>(len) - L - k),
                                              clamp16(static_cast<int64_t>(len) - 2ll * L - k),
@@ -743,13 +751,16 @@ int launch_rs_encode(ss_rs_coder *coder, const EncGeom &g, const TallyArgs *tall
             ((reinterpret_cast<uintptr_t>(g.data) | g.data_stride) & 15u) == 0u &&
             (tally == nullptr || tally->planes == nullptr || tally->G == g.n)) {
             Enc32Row Rw;
-            Rw.data = g.data; Rw.data_stride = g.data_stride; Rw.parity = g.parity;
-            Rw.plane_stride = g.plane_stride; Rw.shard_stride = g.shard_stride;
+            Rw.data = g.data; Rw.data_stride = g.data_stride; Rw.shard_stride = g.shard_stride;
+            for (int j = 0; j < 5; ++j) {
+                if (g.planes5 != nullptr) Rw.plane[j] = g.planes5[j];
+                else Rw.plane[j] = g.parity + (static_cast<int64_t>(j) - 3) * static_cast<int64_t>(g.plane_stride);
+            }
             Rw.n = static_cast<uint32_t>(g.n); Rw.len = len; Rw.L = L; Rw.vpc = vpc;
             const uint32_t lim = (len - 2u * L) < L ? (len - 2u * L) : L;     // bytes of shard 2 inside the payload
             Rw.fast_cols = len >= 2u * L ? lim / 16u : 0u;
             Rw.s1 = L & 15u; Rw.s2 = (2u * L) & 15u;
-            Rw.emit_data = (g.flags & SS_RS_EMIT_DATA) ? 1u : 0u;
+            Rw.emit_data = ((g.flags & SS_RS_EMIT_DATA) || g.planes5 != nullptr) ? 1u : 0u;
             Rw.planes = nullptr; Rw.R = 0; Rw.threshold = 0; Rw.committed = nullptr; Rw.commit_bar = nullptr;
             if (tally != nullptr && tally->planes != nullptr) {
                 Rw.planes = tally->planes; Rw.R = tally->R; Rw.threshold = tally->threshold;

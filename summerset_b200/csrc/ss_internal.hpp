@@ -103,6 +103,7 @@ struct EncGeom {
     uint64_t shard_stride;      // uniform
     uint64_t n;
     uint32_t flags;
+    uint8_t *const *planes5 = nullptr;   // RS(3,2) replicate mode: 5 explicit plane bases (local or peer memory)
 };
 
 struct TallyArgs {              // optional fused tally
