@@ -30,6 +30,58 @@ tally_planes_kernel(const uint64_t *__restrict__ planes, uint32_t R, uint64_t G,
     }
 }
 
+// two adjacent groups per thread: 128-bit loads/stores (G even, planes 16-byte aligned)
+__device__ __forceinline__ uint64_t ge_threshold(const uint64_t (&cb)[5], uint32_t threshold) {
+    if (threshold == 0u) return ~0ull;
+    if (threshold > 31u) return 0ull;
+    uint64_t lt = 0ull, eq = ~0ull;
+#pragma unroll
+    for (int b = 4; b >= 0; --b) {
+        const uint64_t tb = ((threshold >> b) & 1u) ? ~0ull : 0ull;
+        lt |= eq & ~cb[b] & tb;
+        eq &= ~(cb[b] ^ tb);
+    }
+    return ~lt;
+}
+
+template <int RT>   // RT > 0: replica count known at compile time (loads fully unrolled and issued up front)
+__global__ void __launch_bounds__(kTallyThreads)
+tally_planes_x2_kernel(const ulonglong2 *__restrict__ planes, uint32_t R, uint64_t G2, uint32_t threshold,
+                       ulonglong2 *__restrict__ committed, uint2 *__restrict__ commit_bar) {
+    const uint64_t stride = static_cast<uint64_t>(gridDim.x) * kTallyThreads;
+    for (uint64_t g = static_cast<uint64_t>(blockIdx.x) * kTallyThreads + threadIdx.x; g < G2; g += stride) {
+        uint64_t a[5] = {0, 0, 0, 0, 0}, b[5] = {0, 0, 0, 0, 0};
+        auto add = [&](const ulonglong2 &x) {
+            uint64_t c = x.x, t;
+            t = a[0] & c; a[0] ^= c; c = t;
+            t = a[1] & c; a[1] ^= c; c = t;
+            t = a[2] & c; a[2] ^= c; c = t;
+            t = a[3] & c; a[3] ^= c; c = t;
+            a[4] ^= c;
+            c = x.y;
+            t = b[0] & c; b[0] ^= c; c = t;
+            t = b[1] & c; b[1] ^= c; c = t;
+            t = b[2] & c; b[2] ^= c; c = t;
+            t = b[3] & c; b[3] ^= c; c = t;
+            b[4] ^= c;
+        };
+        if constexpr (RT > 0) {
+            ulonglong2 v[RT];
+#pragma unroll
+            for (int r = 0; r < RT; ++r) v[r] = __ldg(planes + static_cast<uint64_t>(r) * G2 + g);
+#pragma unroll
+            for (int r = 0; r < RT; ++r) add(v[r]);
+        } else {
+            for (uint32_t r = 0; r < R; ++r) add(__ldg(planes + static_cast<uint64_t>(r) * G2 + g));
+        }
+        ulonglong2 w;
+        w.x = ge_threshold(a, threshold);
+        w.y = ge_threshold(b, threshold);
+        committed[g] = w;
+        if (commit_bar != nullptr) commit_bar[g] = make_uint2(dev::commit_prefix(w.x), dev::commit_prefix(w.y));
+    }
+}
+
 // ------------------------------------------------------------------------------------------------
 // per-instance vote masks: SWAR popcount of 16 one-byte Bitmaps per 128-bit load
 // ------------------------------------------------------------------------------------------------
@@ -236,7 +288,14 @@ raft_scan_kernel(const uint32_t *__restrict__ match, uint32_t n_peers, uint64_t 
             if (any && upper <= lc) any = false;
         }
         uint32_t result = lc;
-        // ---- cooperative part: for each group of the batch, find the last slot in (lc, upper]
+        // ---- probe: the highest candidate slot usually IS a current-term entry (a leader appends in its own
+        //      term), so each lane first checks terms[upper] for its own group: one 4-byte load instead of the
+        //      whole window.  Only groups whose top candidate is an older-term entry take the cooperative scan.
+        if (live && any) {
+            const uint32_t o = upper - lc - 1u;
+            if (o < W && __ldg(terms + g * W + o) == ct) { result = upper; any = false; }
+        }
+        // ---- cooperative part: for each remaining group of the batch, find the last slot in (lc, upper]
         //      whose term equals curr_term (raft/messages.rs:261-263,271-274: last one wins) ----
         const uint32_t todo = __ballot_sync(0xffffffffu, live && any);
         uint32_t rem = todo;
@@ -280,6 +339,22 @@ int launch_tally_planes(ss_ctx *ctx, const uint64_t *planes, uint32_t R, uint64_
     SS_TRY(ctx_bind(ctx));
     if (R == 0 || R > 16) return set_error(SS_ERR_INVALID_ARG, "n_replicas must be 1..16, got %u", R);
     if (G == 0) return SS_OK;
+    const bool al16 = ((reinterpret_cast<uintptr_t>(planes) | reinterpret_cast<uintptr_t>(committed)) & 15u) == 0u &&
+                      (reinterpret_cast<uintptr_t>(commit_bar) & 7u) == 0u;
+    if ((G & 1ull) == 0ull && al16) {
+        const uint64_t G2 = G / 2;
+        const uint32_t grid = static_cast<uint32_t>((G2 + kTallyThreads - 1) / kTallyThreads);
+        const ulonglong2 *p2 = reinterpret_cast<const ulonglong2 *>(planes);
+        ulonglong2 *c2 = reinterpret_cast<ulonglong2 *>(committed);
+        uint2 *b2 = reinterpret_cast<uint2 *>(commit_bar);
+        if (R == 5) tally_planes_x2_kernel<5><<<grid, kTallyThreads, 0, ctx->stream>>>(p2, R, G2, thr, c2, b2);
+        else if (R == 3) tally_planes_x2_kernel<3><<<grid, kTallyThreads, 0, ctx->stream>>>(p2, R, G2, thr, c2, b2);
+        else if (R == 7) tally_planes_x2_kernel<7><<<grid, kTallyThreads, 0, ctx->stream>>>(p2, R, G2, thr, c2, b2);
+        else tally_planes_x2_kernel<0><<<grid, kTallyThreads, 0, ctx->stream>>>(p2, R, G2, thr, c2, b2);
+        SS_CUDA(cudaGetLastError());
+        ctx->launches++;
+        return SS_OK;
+    }
     tally_planes_kernel<<<stream_grid(ctx, G), kTallyThreads, 0, ctx->stream>>>(planes, R, G, thr, committed, commit_bar);
     SS_CUDA(cudaGetLastError());
     ctx->launches++;
