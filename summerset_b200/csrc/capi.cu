@@ -112,6 +112,7 @@ static void fill_coef(uint8_t *prog, int d, int p, int j, int i, uint8_t c) {
         hmask[(size_t(j) * d + i) * 8 + k] = ((c >> k) & 1u) ? 0xffffffffu : 0u;
         if (d <= 4) (hmask + size_t(p) * d * 8)[(size_t(j) * 8 + k) * 4 + i] = ((c >> k) & 1u) ? 0xffffffffu : 0u;
         if (((c >> k) & 1u) && k > h->top[j]) h->top[j] = static_cast<uint8_t>(k);
+        if (j < 2 && h->top[j] > h->topT[j]) h->topT[j] = h->top[j];
     }
 }
 
@@ -139,6 +140,24 @@ static void build_decode_program(const gf::Matrix &M, int d, int p, uint32_t pre
         ++n_out;
     }
     h->n_missing_data = static_cast<uint8_t>(n_out);
+    // XOR chain (d <= 4 fast path only): when exactly two data shards r0 < r1 are missing and the all-ones parity
+    // row (index d) is among the sources, d_r1 = p_0 ^ d_r0 ^ (the available data shards): the second output
+    // needs no dense row, only XORs of sources plus the first output.
+    if (d <= 4 && n_out == 2) {
+        bool ones = true;
+        for (int c = 0; c < d; ++c) ones = ones && M.at(d, c) == 1;
+        bool has_p0 = false;
+        for (int i = 0; i < d; ++i) has_p0 = has_p0 || src[i] == d;
+        if (ones && has_p0) {
+            uint32_t *hmT = reinterpret_cast<uint32_t *>(out + sizeof(ProgHeader)) + 2 * size_t(p) * d * 8;
+            for (int k = 0; k < 8; ++k)
+                for (int i = 0; i < 4; ++i) hmT[(size_t(1) * 8 + k) * 4 + i] = 0u;
+            for (int i = 0; i < d; ++i)                                   // p_0 and the available data shards only
+                if (src[i] <= d) hmT[(size_t(1) * 8 + 0) * 4 + i] = 0xffffffffu;
+            h->topT[1] = 0;
+            h->chain1 = 1;
+        }
+    }
     if (!data_only) {
         for (int q = d; q < t; ++q) {
             if ((present >> q) & 1u) continue;
@@ -396,6 +415,30 @@ int ss_rs_coder_create(ss_ctx *ctx, int d, int p, ss_rs_coder **out) {
             build_decode_program(M, d, p, static_cast<uint32_t>(pat), false, all.data() + pat * c->prog_stride);
             build_decode_program(M, d, p, static_cast<uint32_t>(pat), true, dat.data() + pat * c->prog_stride);
         }
+        if (d <= 4) {
+            // compact copies for the small-code kernel: header fields + the transposed mask rows only
+            c->fast_stride = sizeof(FastProgHeader) + size_t(p) * 8 * 16;
+            std::vector<uint8_t> fa(npat * c->fast_stride, 0), fd(npat * c->fast_stride, 0);
+            auto compact = [&](const std::vector<uint8_t> &full, std::vector<uint8_t> &fast) {
+                for (size_t pat = 0; pat < npat; ++pat) {
+                    const uint8_t *src = full.data() + pat * c->prog_stride;
+                    const ProgHeader *h = reinterpret_cast<const ProgHeader *>(src);
+                    uint8_t *dst = fast.data() + pat * c->fast_stride;
+                    FastProgHeader *f = reinterpret_cast<FastProgHeader *>(dst);
+                    f->valid = h->valid; f->n_out = h->n_out; f->chain1 = h->chain1;
+                    for (int i = 0; i < 4; ++i) f->src[i] = h->src[i];
+                    for (int j = 0; j < kMaxP; ++j) { f->dst[j] = h->dst[j]; f->top[j] = j < 2 ? h->topT[j] : h->top[j]; }
+                    memcpy(dst + sizeof(FastProgHeader), src + sizeof(ProgHeader) + 2 * size_t(p) * d * 8 * 4, size_t(p) * 8 * 16);
+                }
+            };
+            compact(all, fa);
+            compact(dat, fd);
+            cudaError_t e2 = cudaMalloc(&c->fast_progs, fa.size());
+            if (e2 == cudaSuccess) e2 = cudaMalloc(&c->fast_progs_data, fd.size());
+            if (e2 == cudaSuccess) e2 = cudaMemcpy(c->fast_progs, fa.data(), fa.size(), cudaMemcpyHostToDevice);
+            if (e2 == cudaSuccess) e2 = cudaMemcpy(c->fast_progs_data, fd.data(), fd.size(), cudaMemcpyHostToDevice);
+            if (e2 != cudaSuccess) { ss_rs_coder_destroy(c); return cuda_error(e2, "upload compact decode programs", __FILE__, __LINE__); }
+        }
         cudaError_t e = cudaMalloc(&c->dec_progs, all.size());
         if (e == cudaSuccess) e = cudaMalloc(&c->dec_progs_data, dat.size());
         if (e == cudaSuccess) e = cudaMemcpy(c->dec_progs, all.data(), all.size(), cudaMemcpyHostToDevice);
@@ -415,6 +458,8 @@ int ss_rs_coder_destroy(ss_rs_coder *c) {
     if (c->enc_prog) cudaFree(c->enc_prog);
     if (c->dec_progs) cudaFree(c->dec_progs);
     if (c->dec_progs_data) cudaFree(c->dec_progs_data);
+    if (c->fast_progs) cudaFree(c->fast_progs);
+    if (c->fast_progs_data) cudaFree(c->fast_progs_data);
     delete c;
     return SS_OK;
 }

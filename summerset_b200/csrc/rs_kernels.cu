@@ -443,6 +443,8 @@ struct DecArgs {
     uint32_t padded;
     uint32_t hmask_off;       // words from the splat table to the Horner mask table (p*d*8)
     uint32_t need_mask;       // shards that must be present for a codeword to need no work (data only, or all)
+    const uint8_t *fast_progs; // d <= 4: compact programs
+    uint32_t fast_stride, fast_bytes;
 };
 
 template <int P>
@@ -522,11 +524,11 @@ __device__ __forceinline__ uint4 horner_row(const uint4 (&x)[D], int d, const ui
 
 // Horner row for d <= 4 with the transposed mask table: one 128-bit load per bit level brings the masks of
 // all inputs (hmT[(j*8 + k)*4 + i]).
-template <int D>
+template <int D, bool SMEM>
 __device__ __forceinline__ uint4 horner_row_t(const uint4 (&x)[D], const uint4 *__restrict__ hmT_j, int top) {
     uint4 acc = make_uint4(0u, 0u, 0u, 0u);
     for (int k = top; k >= 0; --k) {
-        const uint4 hm = __ldg(hmT_j + k);   // compiler-visible load: may be hoisted / batched across bit levels
+        const uint4 hm = SMEM ? hmT_j[k] : __ldg(hmT_j + k);
         if (k != top) {
             const uint4 m = make_uint4(msb_mask(acc.x), msb_mask(acc.y), msb_mask(acc.z), msb_mask(acc.w));
             acc.x = ((acc.x * 2u) & 0xfefefefeu) ^ (m.x & 0x1d1d1d1du);
@@ -576,31 +578,6 @@ __global__ void __launch_bounds__(kThreads, 4) horner_reconstruct_kernel(const _
         const uint32_t L = (len + static_cast<uint32_t>(d) - 1u) / static_cast<uint32_t>(d);
         const uint32_t vpc = (L + 15u) >> 4;
         uint8_t *base = A.shards + __ldg(A.off + g);
-        if (D <= 4) {
-            const uint4 *hmT = reinterpret_cast<const uint4 *>(hmask + A.hmask_off);   // after the [p*d*8] mask table
-            const uint8_t *sp[D];
-#pragma unroll
-            for (int i = 0; i < D; ++i) sp[i] = base + static_cast<uint64_t>(hdr->src[i < d ? i : 0]) * A.plane_stride;
-            const int top0 = hdr->top[0], top1 = hdr->top[1];
-            uint8_t *dp0 = base + static_cast<uint64_t>(hdr->dst[0]) * A.plane_stride;
-            uint8_t *dp1 = base + static_cast<uint64_t>(hdr->dst[1]) * A.plane_stride;
-            for (uint32_t v = lane; v < vpc; v += 32u) {
-                const uint32_t k = v * 16u;
-                const int nv = static_cast<int>(L - k) > 16 ? 16 : static_cast<int>(L - k);
-                uint4 x[D];
-#pragma unroll
-                for (int i = 0; i < D; ++i) {
-                    x[i] = make_uint4(0u, 0u, 0u, 0u);
-                    if (i < d) x[i] = A.padded != 0u ? keep_bytes(dev::ldg128(sp[i] + k), nv) : load16(sp[i] + k, nv);
-                }
-                store16(dp0 + k, horner_row_t<D>(x, hmT, top0), nv, A.padded != 0u);
-                if (n_out > 1) store16(dp1 + k, horner_row_t<D>(x, hmT + 8, top1), nv, A.padded != 0u);
-                for (int j = 2; j < n_out; ++j)
-                    store16(base + static_cast<uint64_t>(hdr->dst[j]) * A.plane_stride + k,
-                            horner_row_t<D>(x, hmT + j * 8, hdr->top[j]), nv, A.padded != 0u);
-            }
-            continue;
-        }
         for (uint32_t v = lane; v < vpc; v += 32u) {
             const uint32_t k = v * 16u;
             const int nv = static_cast<int>(L - k) > 16 ? 16 : static_cast<int>(L - k);
@@ -618,6 +595,83 @@ __global__ void __launch_bounds__(kThreads, 4) horner_reconstruct_kernel(const _
                 const uint4 acc = horner_row<D>(x, d, hmask + j * d * 8, hdr->top[j]);
                 store16(base + static_cast<uint64_t>(hdr->dst[j]) * A.plane_stride + k, acc, nv, A.padded != 0u);
             }
+        }
+    }
+}
+
+
+// ------------------------------------------------------------------------------------------------
+// reconstruct for small codes (d <= 4, i.e. every 3/5/7-replica deployment): compact per-pattern programs
+// staged in shared memory (no dependent global look-ups between a codeword's metadata and its shard loads),
+// Horner rows from one 128-bit mask word per bit level, XOR chain for the second of two missing data shards.
+// ------------------------------------------------------------------------------------------------
+template <int D, bool SMEM>
+__global__ void __launch_bounds__(kThreads, 4) rs_reconstruct_small_kernel(const __grid_constant__ DecArgs A) {
+    extern __shared__ uint4 s_prog[];
+    const uint8_t *table = A.fast_progs;
+    if (SMEM) {
+        const uint4 *gsrc = reinterpret_cast<const uint4 *>(A.fast_progs);
+        for (uint32_t i = threadIdx.x; i < A.fast_bytes / 16u; i += kThreads) s_prog[i] = __ldg(gsrc + i);
+        __syncthreads();
+        table = reinterpret_cast<const uint8_t *>(s_prog);
+    }
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint64_t warp = (static_cast<uint64_t>(blockIdx.x) * kThreads + threadIdx.x) >> 5;
+    const uint64_t nwarps = (static_cast<uint64_t>(gridDim.x) * kThreads) >> 5;
+    const int d = A.d;
+    const bool padded = A.padded != 0u;
+    uint32_t nx_len = 0, nx_pat = 0; uint64_t nx_off = 0;
+    if (warp < A.n) { nx_len = __ldg(A.data_len + warp); nx_pat = __ldg(A.present + warp); nx_off = __ldg(A.off + warp); }
+    for (uint64_t g = warp; g < A.n; g += nwarps) {
+        const uint32_t len = nx_len;
+        const uint32_t pat = nx_pat & A.pattern_mask;
+        uint8_t *base = A.shards + nx_off;
+        if (g + nwarps < A.n) {
+            nx_len = __ldg(A.data_len + g + nwarps); nx_pat = __ldg(A.present + g + nwarps); nx_off = __ldg(A.off + g + nwarps);
+        }
+        if (len == 0u) {                              // null codeword: rscoding.rs:495-497
+            if (lane == 0u) A.status[g] = SS_ERR_INVALID_ARG;
+            continue;
+        }
+        if ((pat & A.need_mask) == A.need_mask) {     // nothing to regenerate
+            if (lane == 0u) A.status[g] = SS_OK;
+            continue;
+        }
+        const uint8_t *prog = table + pat * A.fast_stride;
+        const FastProgHeader *hdr = reinterpret_cast<const FastProgHeader *>(prog);
+        const int valid = hdr->valid;
+        const int n_out = hdr->n_out;
+        if (lane == 0u) A.status[g] = valid ? SS_OK : SS_ERR_TOO_FEW_SHARDS_PRESENT;
+        if (!valid || n_out == 0) continue;           // never partial output
+        const uint4 *hmT = reinterpret_cast<const uint4 *>(prog + sizeof(FastProgHeader));
+        const uint32_t L = (len + static_cast<uint32_t>(d) - 1u) / static_cast<uint32_t>(d);
+        const uint32_t vpc = (L + 15u) >> 4;
+        const uint8_t *sp[D];
+#pragma unroll
+        for (int i = 0; i < D; ++i) sp[i] = base + static_cast<uint64_t>(hdr->src[i < d ? i : 0]) * A.plane_stride;
+        const int top0 = hdr->top[0], top1 = hdr->top[1];
+        const bool chain1 = hdr->chain1 != 0;
+        uint8_t *dp0 = base + static_cast<uint64_t>(hdr->dst[0]) * A.plane_stride;
+        uint8_t *dp1 = base + static_cast<uint64_t>(hdr->dst[1]) * A.plane_stride;
+        for (uint32_t v = lane; v < vpc; v += 32u) {
+            const uint32_t k = v * 16u;
+            const int nv = static_cast<int>(L - k) > 16 ? 16 : static_cast<int>(L - k);
+            uint4 x[D];
+#pragma unroll
+            for (int i = 0; i < D; ++i) {
+                x[i] = make_uint4(0u, 0u, 0u, 0u);
+                if (i < d) x[i] = padded ? keep_bytes(dev::ldg128(sp[i] + k), nv) : load16(sp[i] + k, nv);
+            }
+            const uint4 y0 = horner_row_t<D, SMEM>(x, hmT, top0);
+            store16(dp0 + k, y0, nv, padded);
+            if (n_out > 1) {
+                uint4 y1 = horner_row_t<D, SMEM>(x, hmT + 8, top1);
+                if (chain1) { y1.x ^= y0.x; y1.y ^= y0.y; y1.z ^= y0.z; y1.w ^= y0.w; }
+                store16(dp1 + k, y1, nv, padded);
+            }
+            for (int j = 2; j < n_out; ++j)
+                store16(base + static_cast<uint64_t>(hdr->dst[j]) * A.plane_stride + k,
+                        horner_row_t<D, SMEM>(x, hmT + j * 8, hdr->top[j]), nv, padded);
         }
     }
 }
@@ -902,7 +956,23 @@ int launch_rs_reconstruct(ss_rs_coder *coder, uint8_t *shards, uint64_t plane_st
     A.hmask_off = static_cast<uint32_t>(coder->p * coder->d * 8);
     A.need_mask = data_only ? ((1u << coder->d) - 1u) : A.pattern_mask;
     const uint32_t grid = ragged_grid(ctx, n);
-    if (coder->d <= 8 && (coder->variant & 15) != 5) {
+    A.fast_progs = static_cast<const uint8_t *>(data_only ? coder->fast_progs_data : coder->fast_progs);
+    A.fast_stride = static_cast<uint32_t>(coder->fast_stride);
+    A.fast_bytes = static_cast<uint32_t>(coder->fast_stride << (coder->d + coder->p));
+    if (coder->d <= 4 && A.fast_progs != nullptr && (coder->variant & 15) != 5 && (coder->variant & 15) != 8) {
+        const bool smem = A.fast_bytes <= 40u * 1024u;
+        const size_t sb = smem ? A.fast_bytes : 0;
+#define SS_SMALL(DD)                                                                                       \
+        do {                                                                                                   \
+            if (smem) rs_reconstruct_small_kernel<DD, true><<<grid, kThreads, sb, ctx->stream>>>(A);           \
+            else rs_reconstruct_small_kernel<DD, false><<<grid, kThreads, 0, ctx->stream>>>(A);                \
+        } while (0)
+        if (coder->d <= 2) SS_SMALL(2);
+        else if (coder->d == 3) SS_SMALL(3);
+        else SS_SMALL(4);
+#undef SS_SMALL
+        coder->last_kernel = smem ? "rs_reconstruct_small_kernel(smem programs)" : "rs_reconstruct_small_kernel";
+    } else if (coder->d <= 8 && (coder->variant & 15) != 5) {
         SS_TRY(dispatch_d(coder->d, [&](auto DC) {
             horner_reconstruct_kernel<decltype(DC)::value><<<grid, kThreads, 0, ctx->stream>>>(A);
             return SS_OK;

@@ -40,10 +40,25 @@ struct ProgHeader {           // 64 bytes, followed by p*d*8 uint32 splats, then
     uint8_t src[kMaxD];       // source shard index per input
     uint8_t dst[kMaxP];       // destination shard index per output
     uint8_t top[kMaxP];       // highest set bit over the coefficients of output j (Horner start), 0 if all zero
-    uint8_t pad1[12];
+    // d <= 4 fast path (transposed mask table hmT): its rows may use the XOR chain below instead of a dense row
+    uint8_t topT[2];          // Horner start of hmT rows 0 and 1
+    uint8_t chain1;           // 1: output 1 = (hmT row 1 applied to the sources) ^ output 0
+    uint8_t pad1[9];
 };
 // Horner masks: hmask[(j*d + i)*8 + k] = 0xffffffff if bit k of c[j][i] is set, else 0.
 static_assert(sizeof(ProgHeader) == 64, "ProgHeader must be 64 bytes");
+
+// Compact per-pattern program of the small-code reconstruct kernel (d <= 4): 32-byte header followed by
+// p rows of 8 uint4 (row j, bit k: the 0/~0 masks of the up-to-4 sources).  The whole table of 2^(d+p)
+// programs is staged in shared memory when it fits.
+struct FastProgHeader {
+    uint8_t valid, n_out, chain1, pad0;
+    uint8_t src[4];
+    uint8_t dst[kMaxP];
+    uint8_t top[kMaxP];
+    uint8_t pad1[8];
+};
+static_assert(sizeof(FastProgHeader) == 32, "FastProgHeader must be 32 bytes");
 
 }  // namespace ssb
 
@@ -78,6 +93,9 @@ struct ss_rs_coder {
     void *enc_prog = nullptr;         // ProgHeader + splats for encode
     void *dec_progs = nullptr;        // one program per present-pattern (2^(d+p) of them), or null
     void *dec_progs_data = nullptr;   // same, data_only flavour
+    void *fast_progs = nullptr;       // d <= 4: compact programs (FastProgHeader + hmT rows), all patterns
+    void *fast_progs_data = nullptr;
+    size_t fast_stride = 0;
     size_t prog_stride = 0;           // bytes per program
     bool batch_ok = false;            // d,p within the batched kernels' limits
     bool dec_ok = false;              // d+p small enough for the per-pattern decode table

@@ -162,7 +162,7 @@ def test_encode_uniform_matches_oracle(ctx, oracle, d, p, data_len):
     assert rs.last_kernel().startswith("rs32_" if (d, p) == (3, 2) else ("horner_" if d <= 8 else "generic_"))
 
 
-@pytest.mark.parametrize("variant", [1, 3, 4, 5])
+@pytest.mark.parametrize("variant", [1, 2, 3, 5, 6, 8])
 def test_encode_kernel_variants(ctx, oracle, variant):
     """every selectable kernel variant (flat v1, register budgets of the row kernel, bit-plane generic) is bit-exact"""
     for d, p, data_len, n in [(3, 2, 4096, 2500), (3, 2, 100, 700), (3, 2, 16 * 200, 33), (4, 3, 4096, 300), (5, 4, 1000, 300)]:
@@ -171,10 +171,10 @@ def test_encode_kernel_variants(ctx, oracle, variant):
         data = wl.payload_uniform(n, data_len, seed_extra=variant)
         got = _gpu_encode_uniform(rs, data, data_len)
         assert (got == oracle.rs_encode_uniform(d, p, data, data_len)).all(), (variant, d, p, data_len, rs.last_kernel())
-    # reconstruct with the bit-plane kernel too
-    if variant == 5:
+    # reconstruct with the bit-plane kernel (5) and the global-table Horner kernel (8) too
+    if variant in (5, 8):
         d, p, data_len = 3, 2, 777
-        rs = ReedSolomon(ctx, d, p); rs.set_variant(5)
+        rs = ReedSolomon(ctx, d, p); rs.set_variant(variant)
         n = 32
         data = wl.payload_uniform(n, data_len, seed_extra=1)
         full, L, ds = _planes_from(oracle, d, p, data, data_len)
@@ -184,7 +184,7 @@ def test_encode_kernel_variants(ctx, oracle, variant):
         st = rs.reconstruct_batch(sh, n * ds, off, torch.full((n,), data_len, dtype=torch.int32, device=DEV),
                                   torch.from_numpy(present.astype(np.int32)).to(DEV), False)
         torch.cuda.synchronize()
-        assert rs.last_kernel() == "generic_reconstruct_kernel"
+        assert rs.last_kernel() == ("generic_reconstruct_kernel" if variant == 5 else "horner_reconstruct_kernel")
         assert (sh.cpu().numpy()[:, :, :L] == full[:, :, :L]).all()
         assert [int(x) for x in st.cpu()] == [0 if bin(pt).count("1") >= d else -10 for pt in range(n)]
 
