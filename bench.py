@@ -637,7 +637,7 @@ def run_cfg4(args, ctx, rs, dev, world, rank, peak, peak_src):
     from oracle import pyoracle as oracle
     from summerset_b200 import workloads as wl
     n = args.groups
-    lens, spr = wl.cfg4_lengths(n, seed_extra=rank)
+    lens, spr = wl.cfg4_lengths(n, seed_extra=0)      # same sizes on every rank (payload bytes differ by rank)
     lay = wl.ragged_layout(lens, D)
     gen = torch.Generator(device=dev); gen.manual_seed(wl.SEED_BASE + 4 + rank)
     arena = torch.randint(0, 256, (lay["data_bytes"] + 256,), dtype=torch.uint8, device=dev, generator=gen)
@@ -649,14 +649,45 @@ def run_cfg4(args, ctx, rs, dev, world, rank, peak, peak_src):
     pidx = torch.from_numpy((spr - 1).astype(np.uint8)).to(dev)
     policies = [list(map(int, oracle.cw_brr_assignment(5, 5, s))) for s in (1, 2, 3)]
 
+    # replica logs for the distribute step: replica r of my groups lives on rank (rank + r) % world
+    import torch.distributed as dist
+    from summerset_b200 import sharding
+    Lp = (lay["L"].astype(np.int64) + 15) // 16 * 16
+    slot_bytes = spr.astype(np.int64) * Lp
+    rep_off_np = np.concatenate([[0], np.cumsum(slot_bytes)[:-1]]).astype(np.int64)
+    region = int(slot_bytes.sum() + 255) // 256 * 256
+    log = ctx.dev_alloc(5 * region)
+    peer_log = {rank: log}
+    if world > 1:
+        handles = [None] * world
+        dist.all_gather_object(handles, ctx.ipc_export(log))
+        for q in range(world):
+            if q != rank:
+                peer_log[q] = ctx.ipc_open(handles[q], 5 * region)
+        tiny = torch.zeros(1, dtype=torch.int32, device=dev)
+    rep_ptrs = [peer_log[sharding.replica_rank(rank, r, world)].ptr + r * region for r in range(5)]
+    rep_off = torch.from_numpy(rep_off_np).to(dev)
+    spr_t = torch.from_numpy(spr).to(dev)
+
     def step():
-        rs.encode_batch(arena, doff, dlen, parity, lay["plane_bytes"], poff)
-        return ctx.tally_crossword(masks, pidx, policies, 5, 3, 3, 2, True)
+        # lens were drawn with the same seed on every rank, so all regions have the same size
+        rs.crossword_distribute(arena, doff, dlen, spr_t, rep_off, rep_ptrs)
+        out = ctx.tally_crossword(masks, pidx, policies, 5, 3, 3, 2, True)
+        if world > 1:
+            dist.all_reduce(tiny)
+        return out
 
     l0 = ctx.launches
     ms = _time_steps(torch, step, args.steps, args.warmup)
     launches = ctx.launches - l0
+    dist_kernel = rs.last_kernel()
     ms_enc = _time_steps(torch, lambda: rs.encode_batch(arena, doff, dlen, parity, lay["plane_bytes"], poff), args.steps, 1)
+    if world > 1:
+        tt = torch.tensor([ms, ms_enc], dtype=torch.float64, device=dev)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        ms, ms_enc = float(tt[0]), float(tt[1])
+    # the follower view: replica 1 of my groups (wherever it lives) holds shard (1 + k) % 5 in slot k
+    chk = peer_log[sharding.replica_rank(rank, 1, world)].tensor()[region:2 * region]
     # spot check vs oracle
     idx = np.arange(0, n, max(1, n // 64))
     sub_len = lens[idx]; sub_lay = wl.ragged_layout(sub_len, D)
@@ -670,20 +701,35 @@ def run_cfg4(args, ctx, rs, dev, world, rank, peak, peak_src):
         Lg = int(lay["L"][g]); o = int(lay["par_off"][g]); so = int(sub_lay["par_off"][j])
         got = parity[:, o:o + Lg].cpu().numpy()
         assert (got == want[:, so:so + Lg]).all(), "cfg4 parity check failed"
-    note = f"{len(idx)} sampled codewords bit-exact vs oracle"
+        if spr[g] == 3:     # replica 1, slot 2 = shard 3 = parity 0
+            o2 = int(rep_off_np[g]) + 2 * int(Lp[g])
+            assert (chk[o2:o2 + Lg].cpu().numpy() == want[0, so:so + Lg]).all(), "cfg4 distribute check failed"
+    note = f"{len(idx)} sampled codewords bit-exact vs oracle (parity planes and replica-1 log)"
     alg = int((lay["L"].astype(np.int64) * (D + P)).sum()) + n * 22
+    alg_dist = int((lay["L"].astype(np.int64) * (D + 5 * spr.astype(np.int64))).sum()) + n * 31
+    remote = sum(1 for r in range(5) if sharding.replica_rank(rank, r, world) != rank)
+    nv_bytes = int((lay["L"].astype(np.int64) * spr.astype(np.int64)).sum()) * remote
     if rank == 0:
-        print(json.dumps({"metric": "RS shard GB/s, Crossword ragged encode + coverage tally", "value": alg / (ms * 1e-3) / 1e9,
+        print(json.dumps({"metric": "RS shard GB/s, Crossword ragged encode + distribute-by-assignment + coverage tally",
+                          "value": alg * world / (ms * 1e-3) / 1e9,
+                          "distribute": {"kernel": dist_kernel, "step_ms": ms, "hbm_bytes_per_rank": alg_dist,
+                                         "hbm_GBps_per_rank": alg_dist / (ms * 1e-3) / 1e9,
+                                         "nvlink_bytes_per_rank": nv_bytes, "nvlink_bound_ms": nv_bytes / 770e9 * 1e3,
+                                         "hbm_bound_ms": alg_dist / (peak * 1e9) * 1e3,
+                                         "frac_of_slower_bound": max(nv_bytes / 770e9 * 1e3, alg_dist / (peak * 1e9) * 1e3) / ms},
                           "unit": "GB/s", "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": ms,
                           "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
                           "config": {"workload": "cfg4: Crossword n=5 d=3 T=5 f=2, 2^20 codewords, data_len uniform over {256..65536}, spr uniform {1,2,3}",
                                      "payload_bytes": int(lens.astype(np.int64).sum())},
-                          "slots_committed_per_s": n / (ms * 1e-3), "encode_only_ms": ms_enc, "parity_check": note,
-                          "kernel": rs.last_kernel(),
+                          "slots_committed_per_s": n * world / (ms * 1e-3), "encode_only_ms": ms_enc, "parity_check": note,
+                          "kernel": "rs32_encode_ragged_kernel",
                           "roofline": {"bound": "hbm", "achieved": alg / (ms_enc * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
                                        "frac": alg / (ms_enc * 1e-3) / 1e9 / peak, "traffic": None,
                                        "algorithmic_bytes_per_launch": alg, "peak_source": peak_src},
                           "gpu_launches": int(launches), "e2e": None, "cpu_baseline": None}))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
 
 
 def main():

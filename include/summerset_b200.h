@@ -238,6 +238,29 @@ int ss_raft_commit_scan_dev(ss_ctx *ctx, const uint32_t *match, uint32_t n_peers
                             const uint32_t *curr_term, const uint32_t *terms, uint32_t window,
                             uint32_t threshold, uint32_t *new_commit);
 
+/* k-th largest peer match per group.  k = threshold - 1 gives CRaft's shadow_last_commit
+ * (craft/messages.rs:677-690: match slots sorted descending, element [threshold-2], threshold =
+ * majority + fault_tolerance, or majority in full-copy mode); k = n_peers gives the bound of Raft's
+ * last_snap scan (raft/messages.rs:298-309: every server has the entry). */
+int ss_raft_kth_match_dev(ss_ctx *ctx, const uint32_t *match, uint32_t n_peers, uint64_t n_groups, uint32_t k,
+                          uint32_t *out);
+
+/* Prepare-phase shard merge + decision for n_instances recovering instances (leader fail-over;
+ * rspaxos/messages.rs:182-259, crossword/messages.rs:233-312).  vote_bal[r*N+i] / vote_mask[r*N+i] = the
+ * (ballot, shards carried) of replica r's PrepareReply vote for instance i; vote_mask == 0 means "no vote".
+ * merged[i] = shard set inst.reqs_cw ends with (shards voted at the highest ballot; max_bal[i] that ballot;
+ * order-independent because absorb_other only adds).  action[i]: bit0 USE (>= data_shards shards), bit1 NULL
+ * request batch (fewer, but acks_cnt[i] >= population - fault_tolerance), 0 = not yet; bit2 reconstruct_data
+ * needed; bit3 compute_parity needed (avail shards < POPULATION, as the reference compares).  The regeneration
+ * itself is ss_rs_reconstruct_batch_dev(present = merged, data_only = 0). */
+#define SS_PM_USE 1u
+#define SS_PM_NULL 2u
+#define SS_PM_RECONSTRUCT 4u
+#define SS_PM_PARITY 8u
+int ss_prepare_merge_dev(ss_ctx *ctx, const uint64_t *vote_bal, const uint32_t *vote_mask, uint32_t n_replicas,
+                         uint64_t n_instances, const uint8_t *acks_cnt, uint32_t data_shards, uint32_t population,
+                         uint32_t fault_tolerance, uint64_t *max_bal, uint32_t *merged, uint8_t *action);
+
 /* ---- fused accept step (BASELINE config 3: RSPaxos encode + quorum) -------------------------
  * ONE kernel launch that, for n_groups groups: RS-encodes each group's new request batch
  * (as ss_rs_encode_uniform_dev) and tallies the group's 64-slot ack window
@@ -258,6 +281,16 @@ int ss_accept_step_replicate_dev(ss_rs_coder *coder, const uint8_t *data, uint64
                                  uint64_t n_groups, uint8_t *const *shard_planes, uint64_t shard_stride,
                                  const uint64_t *planes, uint32_t n_replicas, uint32_t threshold,
                                  uint64_t *committed, uint32_t *commit_bar);
+
+/* Crossword encode + distribute (BASELINE config 4; crossword/request.rs:82-87,137-185): RS(3,2)-encodes a
+ * ragged batch and writes, for every codeword g, the spr[g] shards the balanced round-robin assignment gives
+ * replica r -- shards {(r + k) mod 5 : k < spr[g]} (crossword/mod.rs:866-888 with n = T = 5) -- into
+ * replica_logs[r] at rep_off[g] + k*round_up(L_g,16), k = 0..spr-1 (bytes past L_g zero).  replica_logs is a
+ * HOST array of 5 device pointers, local or peer (ss_ipc_open): the kernel's stores are the shard transfer.
+ * Per codeword (n-1)*spr*L_g bytes cross to other replicas, as in the reference.  n = 5 / RS(3,2) only. */
+int ss_crossword_distribute_dev(ss_rs_coder *coder, const uint8_t *data, const uint64_t *data_off,
+                                const uint32_t *data_len, const uint8_t *spr, const uint64_t *rep_off,
+                                uint64_t n, uint8_t *const *replica_logs);
 
 /* ---- tuning / introspection (bench + tests) ------------------------------------------------ */
 /* selects the encode kernel variant: 0 = auto, 1 = direct-LDG, 2 = bulk-copy (TMA) ring */

@@ -259,3 +259,32 @@ def raft_scan_batch(match: np.ndarray, last_commit, log_end, curr_term, terms: n
                                _p(np.ascontiguousarray(curr_term, dtype=np.uint32)), _p(terms), W, threshold, _p(out),
                                threads)
     return out
+
+
+# ---- CRaft / prepare merge ---------------------------------------------------------------------
+def craft_threshold(majority: int, f: int, full_copy: bool) -> int:
+    lib().ssor_craft_threshold.restype = C.c_uint32
+    return int(lib().ssor_craft_threshold(majority, f, 1 if full_copy else 0))
+
+
+def craft_shadow_last_commit(match: Sequence[int], threshold: int) -> int:
+    m = np.ascontiguousarray(match, dtype=np.uint32)
+    lib().ssor_craft_shadow_last_commit.restype = C.c_uint32
+    return int(lib().ssor_craft_shadow_last_commit(_p(m), len(m), threshold))
+
+
+PM_USE, PM_NULL, PM_RECONSTRUCT, PM_PARITY = 1, 2, 4, 8
+
+
+def prepare_merge_stream(has_vote, bal, mask):
+    hv = np.ascontiguousarray(has_vote, dtype=np.uint8)
+    b = np.ascontiguousarray(bal, dtype=np.uint64)
+    m = np.ascontiguousarray(mask, dtype=np.uint32)
+    mb = C.c_uint64(0); mm = C.c_uint32(0)
+    lib().ssor_prepare_merge_stream(_p(hv), _p(b), _p(m), len(hv), C.byref(mb), C.byref(mm))
+    return int(mb.value), int(mm.value)
+
+
+def prepare_decide(merged: int, acks_cnt: int, d: int, population: int, f: int) -> int:
+    lib().ssor_prepare_decide.restype = C.c_uint32
+    return int(lib().ssor_prepare_decide(merged, acks_cnt, d, population, f))

@@ -552,3 +552,59 @@ void ssor_raft_scan_batch(const uint32_t *match, uint32_t npeers, uint64_t G,
                                        terms + g * (uint64_t)W, threshold);
     }
 }
+
+/* ------------------------------------------------------------------------------------------
+ * CRaft (craft/messages.rs:288-314, :677-690)
+ * ------------------------------------------------------------------------------------------ */
+uint32_t ssor_craft_threshold(uint32_t majority, uint32_t fault_tolerance, int full_copy_mode) {
+    return full_copy_mode ? majority : majority + fault_tolerance;          /* :300-308 */
+}
+
+uint32_t ssor_craft_shadow_last_commit(const uint32_t *match, uint32_t npeers, uint32_t threshold) {
+    /* :680-689: collect, sort_unstable, reverse, index [threshold - 2] */
+    uint32_t v[64];
+    if (npeers > 64 || threshold < 2 || threshold - 2 >= npeers) return 0;
+    for (uint32_t i = 0; i < npeers; i++) v[i] = match[i];
+    for (uint32_t i = 0; i < npeers; i++)
+        for (uint32_t j = i + 1; j < npeers; j++)
+            if (v[j] > v[i]) { uint32_t t = v[i]; v[i] = v[j]; v[j] = t; }
+    return v[threshold - 2];
+}
+
+/* ------------------------------------------------------------------------------------------
+ * Prepare-phase merge (rspaxos/messages.rs:182-259, crossword/messages.rs:233-312)
+ * ------------------------------------------------------------------------------------------ */
+void ssor_prepare_merge_stream(const uint8_t *has_vote, const uint64_t *bal, const uint32_t *mask,
+                               uint32_t n_rep, uint64_t *max_bal, uint32_t *merged) {
+    uint64_t prepare_max_bal = 0;     /* LeaderBookkeeping.prepare_max_bal starts at 0 */
+    uint32_t cw = 0;                  /* shard set of inst.reqs_cw (null codeword) */
+    for (uint32_t i = 0; i < n_rep; i++) {
+        if (!has_vote[i]) continue;                      /* voted == None */
+        if (bal[i] > prepare_max_bal) {                  /* discard current, take the replied codeword */
+            prepare_max_bal = bal[i];
+            cw = mask[i];
+        } else if (bal[i] == prepare_max_bal) {          /* absorb_other: takes shards not yet held */
+            cw |= mask[i];
+        }
+    }
+    *max_bal = prepare_max_bal;
+    *merged = cw;
+}
+
+uint32_t ssor_prepare_decide(uint32_t merged, uint32_t acks_cnt, uint32_t data_shards, uint32_t population,
+                             uint32_t fault_tolerance) {
+    uint32_t avail = popc32(merged);
+    uint32_t avail_data = popc32(merged & ((data_shards >= 32) ? 0xffffffffu : ((1u << data_shards) - 1u)));
+    uint32_t act;
+    if (avail >= data_shards) {
+        act = SSOR_PM_USE;
+        if (avail_data < data_shards) act |= SSOR_PM_RECONSTRUCT;
+    } else if (acks_cnt >= population - fault_tolerance) {
+        act = SSOR_PM_NULL;
+        avail = data_shards;          /* from_data(empty batch): all d data shards present, no parity */
+    } else {
+        return 0;                     /* "not yet for this instance" */
+    }
+    if (avail < population) act |= SSOR_PM_PARITY;
+    return act;
+}

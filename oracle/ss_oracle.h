@@ -152,6 +152,28 @@ void ssor_raft_scan_batch(const uint32_t *match, uint32_t npeers, uint64_t G,
                           const uint32_t *curr_term, const uint32_t *terms, uint32_t W,
                           uint32_t threshold, uint32_t *new_commit, int threads);
 
+/* ---- CRaft ----
+ * commit threshold (craft/messages.rs:300-308): full_copy_mode ? majority : majority + fault_tolerance */
+uint32_t ssor_craft_threshold(uint32_t majority, uint32_t fault_tolerance, int full_copy_mode);
+/* shadow_last_commit (craft/messages.rs:677-690): peers' match slots sorted descending, element
+ * [threshold - 2]; i.e. the (threshold-1)-th largest peer match */
+uint32_t ssor_craft_shadow_last_commit(const uint32_t *match, uint32_t npeers, uint32_t threshold);
+
+/* ---- prepare-phase shard merge ----
+ * Incremental restatement of the PrepareReply bookkeeping (rspaxos/messages.rs:182-196,
+ * crossword/messages.rs:233-248) for ONE instance: replies i = 0..n_rep-1 in arrival order, reply i
+ * has_vote[i] ? (bal[i], shard mask[i]) : None.  Outputs the final prepare_max_bal and the shard set
+ * held by inst.reqs_cw (absorb_other keeps what is already there, so the set is the union). */
+void ssor_prepare_merge_stream(const uint8_t *has_vote, const uint64_t *bal, const uint32_t *mask,
+                               uint32_t n_rep, uint64_t *max_bal, uint32_t *merged);
+/* decision once prepare_acks_cnt >= majority (rspaxos/messages.rs:227-259, crossword/messages.rs:279-312):
+ * bit0 USE (>= d shards of the highest ballot), bit1 NULL (fewer, but acks >= n - f), neither = wait;
+ * bit2 needs reconstruct_data (avail data shards < d), bit3 needs compute_parity (avail shards <
+ * POPULATION -- the reference compares with population, not rs_total_shards). */
+enum { SSOR_PM_USE = 1, SSOR_PM_NULL = 2, SSOR_PM_RECONSTRUCT = 4, SSOR_PM_PARITY = 8 };
+uint32_t ssor_prepare_decide(uint32_t merged, uint32_t acks_cnt, uint32_t data_shards, uint32_t population,
+                             uint32_t fault_tolerance);
+
 #ifdef __cplusplus
 }
 #endif

@@ -78,6 +78,9 @@ SIGNATURES = {
     "ss_ack_ingest_dev": (_i, [_vp, _vp, _vp, _vp, _vp, _u64, _vp, _vp, _vp, _u32, _u64, _vp]),
     "ss_tally_crossword_dev": (_i, [_vp, _vp, _u32, _vp, _u64, _vp, _u32, _u32, _u32, _u32, _u32, _u32, _i, _vp]),
     "ss_raft_commit_scan_dev": (_i, [_vp, _vp, _u32, _u64, _vp, _vp, _vp, _vp, _u32, _u32, _vp]),
+    "ss_crossword_distribute_dev": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _u64, C.POINTER(_vp)]),
+    "ss_raft_kth_match_dev": (_i, [_vp, _vp, _u32, _u64, _u32, _vp]),
+    "ss_prepare_merge_dev": (_i, [_vp, _vp, _vp, _u32, _u64, _vp, _u32, _u32, _u32, _vp, _vp, _vp]),
     "ss_accept_step_fused_dev": (_i, [_vp, _vp, _u64, _u32, _u64, _vp, _u64, _u64, _u32, _vp, _u32, _u32, _vp, _vp]),
     "ss_rs_set_variant": (_i, [_vp, _i]),
     "ss_rs_last_kernel": (C.c_char_p, [_vp]),

@@ -169,6 +169,40 @@ class Context:
         return out
 
 
+def _ctx_extras():
+    def raft_kth_match(self, match: torch.Tensor, k: int) -> torch.Tensor:
+        """k-th largest peer match per group (CRaft shadow_last_commit with k = threshold - 1)."""
+        assert match.dtype == torch.int32 and match.is_contiguous()
+        P, G = match.shape
+        out = torch.empty(G, dtype=torch.int32, device=match.device)
+        check(self.lib.ss_raft_kth_match_dev(self.h, _ptr(match), P, G, k, _ptr(out)))
+        return out
+
+    def prepare_merge(self, vote_bal: torch.Tensor, vote_mask: torch.Tensor, acks_cnt: torch.Tensor, data_shards: int,
+                      population: int, fault_tolerance: int):
+        """vote_bal int64 [R, N], vote_mask int32 [R, N] (0 = no vote), acks_cnt uint8 [N]."""
+        assert vote_bal.dtype == torch.int64 and vote_mask.dtype == torch.int32 and acks_cnt.dtype == torch.uint8
+        R, N = vote_bal.shape
+        dev = vote_bal.device
+        max_bal = torch.empty(N, dtype=torch.int64, device=dev)
+        merged = torch.empty(N, dtype=torch.int32, device=dev)
+        action = torch.empty(N, dtype=torch.uint8, device=dev)
+        check(self.lib.ss_prepare_merge_dev(self.h, _ptr(vote_bal), _ptr(vote_mask), R, N, _ptr(acks_cnt), data_shards,
+                                            population, fault_tolerance, _ptr(max_bal), _ptr(merged), _ptr(action)))
+        return max_bal, merged, action
+
+    Context.raft_kth_match = raft_kth_match
+    Context.prepare_merge = prepare_merge
+
+
+_ctx_extras()
+
+
+def craft_threshold(majority: int, fault_tolerance: int, full_copy_mode: bool) -> int:
+    """craft/messages.rs:300-308"""
+    return majority if full_copy_mode else majority + fault_tolerance
+
+
 class DevBuffer:
     """A raw device allocation from ss_dev_alloc (or a peer GPU's buffer opened through CUDA IPC).
     Exposes __cuda_array_interface__ so `torch.as_tensor(buf, device=...)` views it without a copy."""
@@ -333,6 +367,14 @@ class ReedSolomon:
         R = planes.shape[0] if planes is not None else 0
         check(self.lib.ss_accept_step_replicate_dev(self.h, _ptr(data), data.shape[1], data_len, n, arr, shard_stride,
                                                     _ptr(planes), R, threshold, _ptr(committed), _ptr(commit_bar)))
+
+    def crossword_distribute(self, data: torch.Tensor, data_off: torch.Tensor, data_len: torch.Tensor, spr: torch.Tensor,
+                             rep_off: torch.Tensor, replica_logs: Sequence[int]) -> None:
+        """Crossword (n = 5): encode the ragged batch and write replica r's spr[g] shards into replica_logs[r]."""
+        assert data_off.dtype == torch.int64 and data_len.dtype == torch.int32 and spr.dtype == torch.uint8 and rep_off.dtype == torch.int64
+        arr = (C.c_void_p * 5)(*replica_logs)
+        check(self.lib.ss_crossword_distribute_dev(self.h, _ptr(data), _ptr(data_off), _ptr(data_len), _ptr(spr),
+                                                   _ptr(rep_off), data_len.numel(), arr))
 
     def encode_uniform_host(self, data: np.ndarray, data_len: int, parity: np.ndarray) -> None:
         """HOST buffers through ss_rs_encode_uniform: data uint8 [n, stride]; parity uint8 [p, n, shard_stride]."""

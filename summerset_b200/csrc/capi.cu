@@ -775,4 +775,28 @@ int ss_raft_commit_scan_dev(ss_ctx *ctx, const uint32_t *match, uint32_t n_peers
                             new_commit);
 }
 
+int ss_crossword_distribute_dev(ss_rs_coder *c, const uint8_t *data, const uint64_t *data_off, const uint32_t *data_len,
+                                const uint8_t *spr, const uint64_t *rep_off, uint64_t n, uint8_t *const *replica_logs) {
+    if (c == nullptr) return set_error(SS_ERR_INVALID_ARG, "null coder");
+    if (n == 0) return SS_OK;
+    if (!data || !data_off || !data_len || !spr || !rep_off || !replica_logs) return set_error(SS_ERR_INVALID_ARG, "null buffer");
+    return launch_crossword_distribute(c, data, data_off, data_len, spr, rep_off, n, replica_logs);
+}
+
+int ss_raft_kth_match_dev(ss_ctx *ctx, const uint32_t *match, uint32_t n_peers, uint64_t G, uint32_t k, uint32_t *out) {
+    if (ctx == nullptr) return set_error(SS_ERR_INVALID_ARG, "null context");
+    if (G == 0) return SS_OK;
+    if (!match || !out) return set_error(SS_ERR_INVALID_ARG, "null buffer");
+    return launch_kth_match(ctx, match, n_peers, G, k, out);
+}
+
+int ss_prepare_merge_dev(ss_ctx *ctx, const uint64_t *vote_bal, const uint32_t *vote_mask, uint32_t R, uint64_t N,
+                         const uint8_t *acks_cnt, uint32_t d, uint32_t population, uint32_t f, uint64_t *max_bal,
+                         uint32_t *merged, uint8_t *action) {
+    if (ctx == nullptr) return set_error(SS_ERR_INVALID_ARG, "null context");
+    if (N == 0) return SS_OK;
+    if (!vote_bal || !vote_mask || !acks_cnt || !max_bal || !merged || !action) return set_error(SS_ERR_INVALID_ARG, "null buffer");
+    return launch_prepare_merge(ctx, vote_bal, vote_mask, R, N, acks_cnt, d, population, f, max_bal, merged, action);
+}
+
 }  // extern "C"

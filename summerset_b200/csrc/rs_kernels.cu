@@ -772,6 +772,103 @@ static int dispatch_p(int p, F &&f) {
     }
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// Crossword distribute (BASELINE config 4, n = 5 replicas, RS(3,2), T = 5 total shards, dj = 1):
+// encode a ragged batch and write, for every codeword g, the spr[g] shards of replica r --
+// shards {(r + k) mod 5 : k < spr} (balanced round-robin assignment, crossword/mod.rs:866-888) -- into
+// replica r's log at rep_off[g] + k * round_up(L_g,16).  The five log bases may be local memory or peer
+// GPUs' HBM (CUDA IPC): this is crossword/request.rs:137-185 (subset_copy per peer + send_msg) for a
+// whole batch, with the NVLink transfer done by the encode kernel's own stores.
+// ------------------------------------------------------------------------------------------------
+struct CwDistribute {
+    const uint8_t *data;
+    const uint64_t *data_off;
+    const uint32_t *data_len;
+    const uint8_t *spr;        // shards per replica of codeword g (1..3)
+    const uint64_t *rep_off;   // byte offset of codeword g's slots inside every replica log
+    uint8_t *rep[5];           // replica log bases
+    uint64_t n;
+};
+
+__global__ void __launch_bounds__(kThreads, 4) rs32_crossword_distribute_kernel(const __grid_constant__ CwDistribute P) {
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint64_t warp = (static_cast<uint64_t>(blockIdx.x) * kThreads + threadIdx.x) >> 5;
+    const uint64_t nwarps = (static_cast<uint64_t>(gridDim.x) * kThreads) >> 5;
+    auto clamp16 = [](int64_t r) { return r > 16 ? 16 : (r < 0 ? 0 : static_cast<int>(r)); };
+    for (uint64_t g = warp; g < P.n; g += nwarps) {
+        const uint32_t len = __ldg(P.data_len + g);
+        if (len == 0u) continue;
+        const uint32_t spr = __ldg(P.spr + g);
+        const uint32_t L = (len + 2u) / 3u;
+        const uint32_t vpc = (L + 15u) >> 4;
+        const uint32_t Lpad = vpc * 16u;
+        const uint8_t *pay = P.data + __ldg(P.data_off + g);
+        const uint64_t ro = __ldg(P.rep_off + g);
+        const uint32_t s0 = static_cast<uint32_t>(reinterpret_cast<uintptr_t>(pay)) & 15u;
+        const uint8_t *src = pay - s0;
+        const uint32_t s1 = (s0 + L) & 15u, s2 = (s0 + 2u * L) & 15u;
+        for (uint32_t v = lane; v < vpc; v += 32u) {
+            const uint32_t k = v * 16u;
+            const int nva = clamp16(static_cast<int64_t>(len) - k);
+            const int nvb = clamp16(static_cast<int64_t>(len) - L - k);
+            const int nvc = clamp16(static_cast<int64_t>(len) - 2ll * L - k);
+            const int onv = clamp16(static_cast<int64_t>(L) - k);
+            const uint32_t o1 = s0 + L + k - s1, o2 = s0 + 2u * L + k - s2;
+            // loads + funnels + masks (the masked column path: ragged tails are everywhere in this workload)
+            const uint4 a0 = dev::ldg128(src + k);
+            uint4 a1 = a0;
+            if (s0 != 0u && static_cast<int>(s0) + nva > 16) a1 = dev::ldg128(src + k + 16u);
+            uint4 b0 = make_uint4(0u, 0u, 0u, 0u), c0 = make_uint4(0u, 0u, 0u, 0u);
+            if (nvb > 0) b0 = dev::ldg128(src + o1);
+            uint4 b1 = b0;
+            if (s1 != 0u && static_cast<int>(s1) + nvb > 16) b1 = dev::ldg128(src + o1 + 16u);
+            if (nvc > 0) c0 = dev::ldg128(src + o2);
+            uint4 c1 = c0;
+            if (s2 != 0u && static_cast<int>(s2) + nvc > 16) c1 = dev::ldg128(src + o2 + 16u);
+            uint4 sh[5];
+            sh[0] = keep_bytes(s0 != 0u ? funnel16(a0, a1, s0) : a0, nva < onv ? nva : onv);
+            sh[1] = keep_bytes(s1 != 0u ? funnel16(b0, b1, s1) : b0, nvb < onv ? nvb : onv);
+            sh[2] = keep_bytes(s2 != 0u ? funnel16(c0, c1, s2) : c0, nvc < onv ? nvc : onv);
+            rs32_word_fast(sh[0].x, sh[1].x, sh[2].x, sh[3].x, sh[4].x);
+            rs32_word_fast(sh[0].y, sh[1].y, sh[2].y, sh[3].y, sh[4].y);
+            rs32_word_fast(sh[0].z, sh[1].z, sh[2].z, sh[3].z, sh[4].z);
+            rs32_word_fast(sh[0].w, sh[1].w, sh[2].w, sh[3].w, sh[4].w);
+            sh[3] = keep_bytes(sh[3], onv);
+            sh[4] = keep_bytes(sh[4], onv);
+            // replica r, slot kk holds shard (r + kk) mod 5
+#pragma unroll
+            for (int r = 0; r < 5; ++r) {
+                uint8_t *dst = P.rep[r] + ro + k;
+#pragma unroll
+                for (int kk = 0; kk < 3; ++kk)
+                    if (static_cast<uint32_t>(kk) < spr) dev::stg128_cs(dst + static_cast<uint64_t>(kk) * Lpad, sh[(r + kk) % 5]);
+            }
+        }
+    }
+}
+
+int launch_crossword_distribute(ss_rs_coder *coder, const uint8_t *data, const uint64_t *data_off,
+                                const uint32_t *data_len, const uint8_t *spr, const uint64_t *rep_off, uint64_t n,
+                                uint8_t *const *replica_logs) {
+    ss_ctx *ctx = coder->ctx;
+    SS_TRY(ctx_bind(ctx));
+    if (!coder->is_rs32) return set_error(SS_ERR_UNSUPPORTED, "crossword distribute is implemented for n = 5, RS(3,2)");
+    if (n == 0) return SS_OK;
+    CwDistribute P;
+    P.data = data; P.data_off = data_off; P.data_len = data_len; P.spr = spr; P.rep_off = rep_off; P.n = n;
+    for (int r = 0; r < 5; ++r) {
+        if (replica_logs[r] == nullptr || (reinterpret_cast<uintptr_t>(replica_logs[r]) & 15u))
+            return set_error(SS_ERR_INVALID_ARG, "replica log %d is null or not 16-byte aligned", r);
+        P.rep[r] = replica_logs[r];
+    }
+    rs32_crossword_distribute_kernel<<<ragged_grid(ctx, n), kThreads, 0, ctx->stream>>>(P);
+    coder->last_kernel = "rs32_crossword_distribute_kernel";
+    SS_CUDA(cudaGetLastError());
+    ctx->launches++;
+    return SS_OK;
+}
+
 int launch_rs_encode(ss_rs_coder *coder, const EncGeom &g, const TallyArgs *tally) {
     ss_ctx *ctx = coder->ctx;
     SS_TRY(ctx_bind(ctx));

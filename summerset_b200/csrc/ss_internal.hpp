@@ -152,4 +152,13 @@ int launch_raft_scan(ss_ctx *ctx, const uint32_t *match, uint32_t n_peers, uint6
                      const uint32_t *last_commit, const uint32_t *log_end, const uint32_t *curr_term,
                      const uint32_t *terms, uint32_t window, uint32_t threshold, uint32_t *new_commit);
 
+int launch_kth_match(ss_ctx *ctx, const uint32_t *match, uint32_t n_peers, uint64_t G, uint32_t k, uint32_t *out);
+int launch_prepare_merge(ss_ctx *ctx, const uint64_t *vote_bal, const uint32_t *vote_mask, uint32_t R, uint64_t N,
+                         const uint8_t *acks_cnt, uint32_t d, uint32_t population, uint32_t f, uint64_t *max_bal,
+                         uint32_t *merged, uint8_t *action);
+
+int launch_crossword_distribute(ss_rs_coder *coder, const uint8_t *data, const uint64_t *data_off,
+                                const uint32_t *data_len, const uint8_t *spr, const uint64_t *rep_off, uint64_t n,
+                                uint8_t *const *replica_logs);
+
 }  // namespace ssb

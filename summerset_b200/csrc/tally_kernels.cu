@@ -323,6 +323,66 @@ raft_scan_kernel(const uint32_t *__restrict__ match, uint32_t n_peers, uint64_t 
     }
 }
 
+// k-th largest peer match per group: CRaft's shadow_last_commit (craft/messages.rs:677-690) with
+// k = threshold - 1; also Raft's last_snap bound with k = n_peers (raft/messages.rs:298-309).
+template <int NP>
+__global__ void __launch_bounds__(kTallyThreads)
+kth_match_kernel(const uint32_t *__restrict__ match, uint32_t n_peers, uint64_t G, uint32_t k, uint32_t *__restrict__ out) {
+    const uint64_t stride = static_cast<uint64_t>(gridDim.x) * kTallyThreads;
+    for (uint64_t g = static_cast<uint64_t>(blockIdx.x) * kTallyThreads + threadIdx.x; g < G; g += stride) {
+        uint32_t mv[NP];
+#pragma unroll
+        for (int q = 0; q < NP; ++q) mv[q] = (static_cast<uint32_t>(q) < n_peers) ? __ldg(match + static_cast<uint64_t>(q) * G + g) : 0u;
+        uint32_t kth = 0;
+#pragma unroll
+        for (int q = 0; q < NP; ++q) {
+            if (static_cast<uint32_t>(q) < n_peers) {
+                uint32_t rank = 0;
+#pragma unroll
+                for (int r = 0; r < NP; ++r)
+                    if (static_cast<uint32_t>(r) < n_peers) rank += (mv[r] > mv[q] || (mv[r] == mv[q] && r < q)) ? 1u : 0u;
+                if (rank == k - 1u) kth = mv[q];
+            }
+        }
+        out[g] = kth;
+    }
+}
+
+// Prepare-phase shard merge + decision, one instance per thread (rspaxos/messages.rs:182-259,
+// crossword/messages.rs:233-312): keep the shards voted at the highest ballot (the union over the replies
+// carrying that ballot is what the chain of absorb_other calls leaves in inst.reqs_cw, in any arrival order),
+// then decide use / null / wait and whether reconstruct_data and compute_parity are needed.
+__global__ void __launch_bounds__(kTallyThreads)
+prepare_merge_kernel(const uint64_t *__restrict__ vote_bal, const uint32_t *__restrict__ vote_mask, uint32_t R, uint64_t N,
+                     const uint8_t *__restrict__ acks_cnt, uint32_t d, uint32_t population, uint32_t f,
+                     uint64_t *__restrict__ max_bal, uint32_t *__restrict__ merged, uint8_t *__restrict__ action) {
+    const uint64_t stride = static_cast<uint64_t>(gridDim.x) * kTallyThreads;
+    const uint32_t data_mask = d >= 32u ? 0xffffffffu : ((1u << d) - 1u);
+    for (uint64_t i = static_cast<uint64_t>(blockIdx.x) * kTallyThreads + threadIdx.x; i < N; i += stride) {
+        uint64_t mb = 0;              // prepare_max_bal starts at 0
+        uint32_t cw = 0;
+        for (uint32_t r = 0; r < R; ++r) {
+            const uint32_t m = __ldg(vote_mask + static_cast<uint64_t>(r) * N + i);
+            if (m == 0u) continue;    // voted == None
+            const uint64_t b = __ldg(vote_bal + static_cast<uint64_t>(r) * N + i);
+            if (b > mb) { mb = b; cw = m; }
+            else if (b == mb) cw |= m;
+        }
+        uint32_t avail = __popc(cw), act = 0;
+        if (avail >= d) {
+            act = 1u;
+            if (static_cast<uint32_t>(__popc(cw & data_mask)) < d) act |= 4u;
+        } else if (acks_cnt[i] >= population - f) {
+            act = 2u;
+            avail = d;
+        }
+        if (act != 0u && avail < population) act |= 8u;
+        max_bal[i] = mb;
+        merged[i] = cw;
+        action[i] = static_cast<uint8_t>(act);
+    }
+}
+
 // ------------------------------------------------------------------------------------------------
 // host launchers
 // ------------------------------------------------------------------------------------------------
@@ -453,6 +513,36 @@ int launch_raft_scan(ss_ctx *ctx, const uint32_t *match, uint32_t n_peers, uint6
     else if (n_peers <= 8) SS_RAFT_LAUNCH(8);
     else SS_RAFT_LAUNCH(16);
 #undef SS_RAFT_LAUNCH
+    SS_CUDA(cudaGetLastError());
+    ctx->launches++;
+    return SS_OK;
+}
+
+int launch_kth_match(ss_ctx *ctx, const uint32_t *match, uint32_t n_peers, uint64_t G, uint32_t k, uint32_t *out) {
+    SS_TRY(ctx_bind(ctx));
+    if (n_peers == 0 || n_peers > kRaftMaxPeers) return set_error(SS_ERR_INVALID_ARG, "n_peers must be 1..%d, got %u", kRaftMaxPeers, n_peers);
+    if (k == 0 || k > n_peers) return set_error(SS_ERR_INVALID_ARG, "k must be 1..n_peers, got %u", k);
+    if (G == 0) return SS_OK;
+    const uint32_t grid = stream_grid(ctx, G);
+    if (n_peers <= 2) kth_match_kernel<2><<<grid, kTallyThreads, 0, ctx->stream>>>(match, n_peers, G, k, out);
+    else if (n_peers <= 4) kth_match_kernel<4><<<grid, kTallyThreads, 0, ctx->stream>>>(match, n_peers, G, k, out);
+    else if (n_peers <= 6) kth_match_kernel<6><<<grid, kTallyThreads, 0, ctx->stream>>>(match, n_peers, G, k, out);
+    else if (n_peers <= 8) kth_match_kernel<8><<<grid, kTallyThreads, 0, ctx->stream>>>(match, n_peers, G, k, out);
+    else kth_match_kernel<16><<<grid, kTallyThreads, 0, ctx->stream>>>(match, n_peers, G, k, out);
+    SS_CUDA(cudaGetLastError());
+    ctx->launches++;
+    return SS_OK;
+}
+
+int launch_prepare_merge(ss_ctx *ctx, const uint64_t *vote_bal, const uint32_t *vote_mask, uint32_t R, uint64_t N,
+                         const uint8_t *acks_cnt, uint32_t d, uint32_t population, uint32_t f, uint64_t *max_bal,
+                         uint32_t *merged, uint8_t *action) {
+    SS_TRY(ctx_bind(ctx));
+    if (R == 0 || R > 32) return set_error(SS_ERR_INVALID_ARG, "n_replicas must be 1..32, got %u", R);
+    if (f > population) return set_error(SS_ERR_INVALID_ARG, "fault_tolerance > population");
+    if (N == 0) return SS_OK;
+    prepare_merge_kernel<<<stream_grid(ctx, N), kTallyThreads, 0, ctx->stream>>>(vote_bal, vote_mask, R, N, acks_cnt, d,
+                                                                                population, f, max_bal, merged, action);
     SS_CUDA(cudaGetLastError());
     ctx->launches++;
     return SS_OK;

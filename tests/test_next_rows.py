@@ -1,0 +1,186 @@
+"""SURVEY 8f "next" rows built so far: CRaft thresholds / shadow_last_commit (f1) and the prepare-phase shard
+merge + decision (f3).  CPU tests pin the oracle restatements against independent models; GPU tests compare
+the kernels with the oracle, bit-exact."""
+import itertools
+
+import numpy as np
+import pytest
+import torch
+
+from summerset_b200 import workloads as wl
+
+DEV = "cuda:0"
+
+
+# ---------------------------------------------------------------------------------------------
+# CPU: oracle semantics
+# ---------------------------------------------------------------------------------------------
+def test_craft_threshold_and_shadow_commit(oracle):
+    """craft/messages.rs:300-308, :677-690"""
+    assert oracle.craft_threshold(3, 1, False) == 4 and oracle.craft_threshold(3, 1, True) == 3
+    rng = np.random.default_rng(0)
+    for n, f in [(5, 1), (7, 1), (7, 2), (3, 0), (9, 2)]:
+        majority = n // 2 + 1
+        for full in (False, True):
+            thr = oracle.craft_threshold(majority, f, full)
+            for _ in range(200):
+                match = rng.integers(0, 50, n - 1)
+                want = sorted(match, reverse=True)[thr - 2]
+                assert oracle.craft_shadow_last_commit(match, thr) == want
+                # consistency with the scan: with every entry in the current term, new_commit == min(shadow, log_end-1)
+                lc, le = 0, 60
+                terms = np.full(64, 7, dtype=np.uint32)
+                got = oracle.raft_scan(match, lc, le, 7, terms, thr)
+                assert got == max(lc, min(int(want), le - 1))
+
+
+def test_prepare_merge_is_order_independent_and_decides_like_the_handler(oracle):
+    """rspaxos/messages.rs:182-259: the merged shard set does not depend on reply order; decision table."""
+    rng = np.random.default_rng(1)
+    for _ in range(300):
+        R = 5
+        has = rng.random(R) < 0.7
+        bal = rng.integers(0, 4, R).astype(np.uint64)
+        mask = np.array([1 << r for r in range(R)], dtype=np.uint32)       # RSPaxos: replica r voted shard r
+        base = oracle.prepare_merge_stream(has, bal, mask)
+        for perm in itertools.islice(itertools.permutations(range(R)), 24):
+            p = list(perm)
+            assert oracle.prepare_merge_stream(has[p], bal[p], mask[p]) == base
+        votes = [(int(bal[r]), int(mask[r])) for r in range(R) if has[r]]
+        mb = max([b for b, _ in votes], default=0)
+        want = 0
+        for b, m in votes:
+            if b == mb:
+                want |= m
+        assert base == (mb, want)
+    # decision table, n=5 d=3 f=1
+    U, N, RC, PA = oracle.PM_USE, oracle.PM_NULL, oracle.PM_RECONSTRUCT, oracle.PM_PARITY
+    assert oracle.prepare_decide(0b00111, 3, 3, 5, 1) == U | PA                 # all data, parity to compute
+    assert oracle.prepare_decide(0b11111, 3, 3, 5, 1) == U                      # complete codeword
+    assert oracle.prepare_decide(0b11001, 3, 3, 5, 1) == U | RC | PA            # enough shards, data missing
+    assert oracle.prepare_decide(0b00011, 3, 3, 5, 1) == 0                      # too few, acks < n - f: wait
+    assert oracle.prepare_decide(0b00011, 4, 3, 5, 1) == N | PA                 # too few, acks >= n - f: null batch
+    assert oracle.prepare_decide(0, 5, 3, 5, 1) == N | PA
+    # Crossword quirk: T = 10 > population = 5: 6 shards present -> parity NOT recomputed
+    assert oracle.prepare_decide(0b0000111111, 3, 6, 5, 2) == U
+
+
+# ---------------------------------------------------------------------------------------------
+# GPU parity
+# ---------------------------------------------------------------------------------------------
+def _t(a):
+    a = np.ascontiguousarray(a)
+    if a.dtype == np.uint64:
+        a = a.view(np.int64)
+    elif a.dtype == np.uint32:
+        a = a.view(np.int32)
+    return torch.from_numpy(a).to(DEV)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("n,f", [(5, 1), (7, 2), (3, 0), (9, 2)])
+def test_craft_on_gpu(ctx, oracle, n, f):
+    majority = n // 2 + 1
+    G = 5003
+    w = wl.cfg5_raft(G, n, 64, seed_extra=n + f)
+    for full in (False, True):
+        thr = oracle.craft_threshold(majority, f, full)
+        out = ctx.raft_commit_scan(_t(w["match"]), _t(w["last_commit"]), _t(w["log_end"]), _t(w["curr_term"]),
+                                   _t(w["terms"]), thr)
+        sh = ctx.raft_kth_match(_t(w["match"]), thr - 1) if thr >= 2 else None
+        torch.cuda.synchronize()
+        want = oracle.raft_scan_batch(w["match"], w["last_commit"], w["log_end"], w["curr_term"], w["terms"], thr)
+        assert (out.cpu().numpy().view(np.uint32) == want).all()
+        if sh is not None:
+            want_sh = np.array([oracle.craft_shadow_last_commit(w["match"][:, g], thr) for g in range(G)], dtype=np.uint32)
+            assert (sh.cpu().numpy().view(np.uint32) == want_sh).all()
+    # last_snap bound: every server has the entry (raft/messages.rs:298-309)
+    allm = ctx.raft_kth_match(_t(w["match"]), n - 1)
+    torch.cuda.synchronize()
+    assert (allm.cpu().numpy().view(np.uint32) == w["match"].min(axis=0)).all()
+
+
+@pytest.mark.gpu
+def test_prepare_merge_on_gpu_and_recovery_roundtrip(ctx, oracle):
+    """merge + decision vs oracle, then the full fail-over data path on the GPU: reconstruct_all on the merged
+    shard sets regenerates the codewords the USE decision promises (rspaxos/messages.rs:227-259)."""
+    from summerset_b200.api import ReedSolomon, round_up, shard_len
+    rng = np.random.default_rng(2)
+    R, d, p, population, f = 5, 3, 2, 5, 1
+    N = 4099
+    has = rng.random((R, N)) < 0.75
+    bal = rng.integers(1, 4, (R, N)).astype(np.uint64)
+    mask = np.where(has, (1 << np.arange(R))[:, None], 0).astype(np.uint32)
+    acks = rng.integers(3, 6, N).astype(np.uint8)
+    mb, mg, act = ctx.prepare_merge(_t(bal), _t(mask), torch.from_numpy(acks).to(DEV), d, population, f)
+    torch.cuda.synchronize()
+    mb, mg, act = mb.cpu().numpy().view(np.uint64), mg.cpu().numpy().view(np.uint32), act.cpu().numpy()
+    for i in range(N):
+        wb, wm = oracle.prepare_merge_stream(has[:, i], bal[:, i], mask[:, i])
+        assert (int(mb[i]), int(mg[i])) == (wb, wm)
+        assert int(act[i]) == oracle.prepare_decide(wm, int(acks[i]), d, population, f)
+    # data path: codewords whose action has USE are reconstructed in full from the merged shard set
+    data_len = 1000
+    rs = ReedSolomon(ctx, d, p)
+    data = wl.payload_uniform(N, data_len, seed_extra=5)
+    L = shard_len(data_len, d); ds = round_up(L, 16)
+    full = np.zeros((d + p, N, ds), dtype=np.uint8)
+    for g in range(N):
+        full[:d, g, :L] = oracle.cw_split(data[g, :data_len].tobytes(), d)
+    full[d:] = oracle.rs_encode_uniform(d, p, data, data_len)
+    damaged = full.copy()
+    for j in range(d + p):
+        damaged[j, ((mg >> j) & 1) == 0] = 0xEE
+    sh = torch.from_numpy(damaged).to(DEV)
+    off = torch.arange(N, dtype=torch.int64, device=DEV) * ds
+    st = rs.reconstruct_batch(sh, N * ds, off, torch.full((N,), data_len, dtype=torch.int32, device=DEV), _t(mg), False)
+    torch.cuda.synchronize()
+    got = sh.cpu().numpy(); st = st.cpu().numpy()
+    use = (act & 1) == 1
+    assert (st[use] == 0).all() and (st[~use & (np.array([bin(int(m)).count("1") for m in mg]) < d)] == -10).all()
+    assert (got[:, use, :L] == full[:, use, :L]).all()
+
+
+@pytest.mark.gpu
+def test_crossword_distribute_matches_assignment_and_oracle(ctx, oracle):
+    """config 4 distribute (crossword/request.rs:137-185): every replica's log holds exactly the shards the balanced
+    round-robin assignment gives it (crossword/mod.rs:866-888), bytes equal to the oracle's encode."""
+    from summerset_b200.api import ReedSolomon
+    rng = np.random.default_rng(6)
+    d, p, n_rep = 3, 2, 5
+    rs = ReedSolomon(ctx, d, p)
+    lens = np.concatenate([rng.integers(1, 3000, 300), wl.CFG4_SIZES, [0, 1, 2, 16, 48, 4096]]).astype(np.uint32)
+    rng.shuffle(lens)
+    n = len(lens)
+    spr = rng.integers(1, 4, n).astype(np.uint8)
+    lay = wl.ragged_layout(lens, d)
+    arena = rng.integers(0, 256, lay["data_bytes"] + 64, dtype=np.uint8)
+    L = lay["L"].astype(np.int64)
+    Lpad = (L + 15) // 16 * 16
+    slot_bytes = spr.astype(np.int64) * Lpad
+    rep_off = np.concatenate([[0], np.cumsum(slot_bytes)[:-1]]).astype(np.int64)
+    total = int(slot_bytes.sum())
+    logs = torch.full((n_rep, total + 64), 0x33, dtype=torch.uint8, device=DEV)
+    rs.crossword_distribute(torch.from_numpy(arena).to(DEV), torch.from_numpy(lay["data_off"].astype(np.int64)).to(DEV),
+                            torch.from_numpy(lens.astype(np.int32)).to(DEV), torch.from_numpy(spr).to(DEV),
+                            torch.from_numpy(rep_off).to(DEV), [logs[r].data_ptr() for r in range(n_rep)])
+    torch.cuda.synchronize()
+    assert rs.last_kernel() == "rs32_crossword_distribute_kernel"
+    got = logs.cpu().numpy()
+    par = np.zeros((p, lay["plane_bytes"]), dtype=np.uint8)
+    oracle.rs_encode_batch(d, p, arena, lay["data_off"], lens, par.reshape(-1), lay["plane_bytes"], lay["par_off"])
+    for g in range(n):
+        if lens[g] == 0:
+            continue
+        Lg = int(L[g]); lp = int(Lpad[g])
+        shards = list(oracle.cw_split(arena[int(lay["data_off"][g]):int(lay["data_off"][g]) + int(lens[g])].tobytes(), d))
+        shards += [par[j, int(lay["par_off"][g]):int(lay["par_off"][g]) + Lg] for j in range(p)]
+        asg = oracle.cw_brr_assignment(n_rep, 5, int(spr[g]))
+        for r in range(n_rep):
+            held = [(r + k) % 5 for k in range(int(spr[g]))]
+            assert sum(1 << j for j in held) == int(asg[r])              # the reference's assignment, bit for bit
+            for k, j in enumerate(held):
+                o = int(rep_off[g]) + k * lp
+                assert (got[r, o:o + Lg] == shards[j]).all(), (g, r, k, j)
+                assert (got[r, o + Lg:o + lp] == 0).all()
+    assert (got[:, total:] == 0x33).all()                               # nothing written past the logs
