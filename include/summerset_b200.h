@@ -152,11 +152,11 @@ int ss_rs_verify(ss_rs_coder *coder, const uint8_t *const *shards, size_t n_shar
  *   SS_RS_OUT_PADDED16  every parity slot starts 16-byte aligned and has capacity
  *                       round_up(L_g,16); bytes [L_g, round_up) are written as zeros.  This is
  *                       the fast path (128-bit stores).  Without it stores are byte-exact.
- * The payload arena must be a CUDA allocation (the kernel issues aligned 16-byte loads that may
- * cover up to 15 bytes either side of a payload, inside the allocation's 256-byte granule).
  *   SS_RS_EMIT_DATA     `parity` is plane d of a (d+p)-plane shard store with the same plane_stride:
  *                       the kernel ALSO copies data shard i into plane i (parity - (d-i)*plane_stride),
- *                       so all d+p planes are packed per-destination send buffers after one pass. */
+ *                       so all d+p planes are packed per-destination send buffers after one pass.
+ * The payload arena must be a CUDA allocation (the kernel issues aligned 16-byte loads that may
+ * cover up to 15 bytes either side of a payload, inside the allocation's 256-byte granule). */
 #define SS_RS_OUT_PADDED16 1u
 #define SS_RS_EMIT_DATA 2u
 int ss_rs_encode_batch_dev(ss_rs_coder *coder, const uint8_t *data, const uint64_t *data_off,

@@ -34,6 +34,16 @@ def test_craft_threshold_and_shadow_commit(oracle):
                 assert got == max(lc, min(int(want), le - 1))
 
 
+def test_raft_last_snap_is_min_match(oracle):
+    """raft/messages.rs:298-309: the loop keeps the last slot every server has == min(min peer match, end_slot)."""
+    rng = np.random.default_rng(3)
+    for _ in range(500):
+        match = rng.integers(0, 40, 6)
+        last_snap, end_slot = int(rng.integers(0, 20)), int(rng.integers(0, 40))
+        want = max(last_snap, min(int(match.min()), end_slot)) if end_slot > last_snap else last_snap
+        assert oracle.raft_snap_scan(match, last_snap, end_slot) == want
+
+
 def test_prepare_merge_is_order_independent_and_decides_like_the_handler(oracle):
     """rspaxos/messages.rs:182-259: the merged shard set does not depend on reply order; decision table."""
     rng = np.random.default_rng(1)
