@@ -38,3 +38,31 @@ def test_cpp_reference_tests_on_gpu():
     r = subprocess.run([str(BIN), "gpu"], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stdout + r.stderr
     assert "gpu: 0 failure(s)" in r.stdout
+
+
+DEMO = ROOT / "examples" / "c_abi_demo"
+
+
+def _build_demo():
+    from summerset_b200 import build as b
+    b.build()
+    gcc = "/usr/bin/gcc" if os.path.exists("/usr/bin/gcc") else "gcc"
+    subprocess.run([gcc, "-O2", "-Wall", "-std=c11", str(ROOT / "examples" / "c_abi_demo.c"), f"-I{ROOT / 'include'}",
+                    f"-L{ROOT / 'summerset_b200'}", "-lsummerset_b200", f"-Wl,-rpath,{ROOT / 'summerset_b200'}",
+                    "-o", str(DEMO)], check=True)
+
+
+def test_plain_c_client_compiles_and_refuses_without_gpu():
+    """the header is valid C11 and a plain-C client links; without a GPU it gets SS_ERR_NO_DEVICE, never a fallback"""
+    _build_demo()
+    if not torch.cuda.is_available():
+        r = subprocess.run([str(DEMO)], capture_output=True, text=True, timeout=60)
+        assert r.returncode == 3 and "no CPU fallback" in r.stderr
+
+
+@pytest.mark.gpu
+def test_plain_c_client_on_gpu():
+    _build_demo()
+    r = subprocess.run([str(DEMO)], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "bit-exact" in r.stdout and "verify after encode: ok" in r.stdout and "-> -10" in r.stdout
