@@ -292,6 +292,21 @@ int ss_crossword_distribute_dev(ss_rs_coder *coder, const uint8_t *data, const u
                                 const uint32_t *data_len, const uint8_t *spr, const uint64_t *rep_off,
                                 uint64_t n, uint8_t *const *replica_logs);
 
+/* Accept-frame packer (the step after the path): for n uniform codewords, builds the byte frames an
+ * unmodified Summerset peer reads off its TCP connection -- 8-byte big-endian body length (utils/safetcp.rs:30-88)
+ * + bincode(PeerMessage::Msg { msg: PeerMsg::Accept { slot, ballot, reqs_cw } }) (server/transport.rs:37-40,
+ * rspaxos/mod.rs:283-288) where reqs_cw = the codeword holding only shard `shard_idx` (what subset_copy builds for
+ * that peer, rspaxos/request.rs:127-142), encoded per utils/rscoding.rs:54-71 with data_copy = None.
+ * shard_plane: shard `shard_idx` of codeword g at shard_plane + g*shard_stride.  Frame g is written inside
+ * out[g*frame_stride .. (g+1)*frame_stride) at frame_off[g] (so that the shard bytes are 16-byte aligned) and is
+ * frame_len[g] bytes long.  frame_stride: multiple of 16, >= shard_len + 96 + d + p.  msg_variant = the index of
+ * the Accept variant in the protocol's PeerMsg enum (2 for RSPaxos).  bincode layout from knowledge of the crate:
+ * unpinned against the reference (it cannot run here); tested byte-for-byte against summerset_b200/wire.py. */
+int ss_frame_accept_batch_dev(ss_ctx *ctx, const uint8_t *shard_plane, uint64_t shard_stride, uint32_t shard_idx,
+                              uint32_t data_shards, uint32_t parity_shards, uint32_t data_len, uint32_t msg_variant,
+                              const uint64_t *slot, const uint64_t *ballot, uint64_t n, uint8_t *out,
+                              uint64_t frame_stride, uint64_t *frame_off, uint32_t *frame_len);
+
 /* ---- tuning / introspection (bench + tests) ------------------------------------------------ */
 /* selects the encode kernel variant: 0 = auto, 1 = direct-LDG, 2 = bulk-copy (TMA) ring */
 int ss_rs_set_variant(ss_rs_coder *coder, int variant);

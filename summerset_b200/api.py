@@ -191,6 +191,21 @@ def _ctx_extras():
                                             population, fault_tolerance, _ptr(max_bal), _ptr(merged), _ptr(action)))
         return max_bal, merged, action
 
+    def frame_accept_batch(self, shard_plane: torch.Tensor, shard_idx: int, d: int, p: int, data_len: int, slot: torch.Tensor,
+                           ballot: torch.Tensor, msg_variant: int = 2):
+        """shard_plane uint8 [n, shard_stride]; returns (out uint8 [n, frame_stride], frame_off int64 [n], frame_len int32 [n])."""
+        n, ss = shard_plane.shape
+        L = shard_len(data_len, d)
+        stride = round_up(L + 96 + d + p, 16)
+        dev = shard_plane.device
+        out = torch.zeros((n, stride), dtype=torch.uint8, device=dev)
+        off = torch.empty(n, dtype=torch.int64, device=dev)
+        ln = torch.empty(n, dtype=torch.int32, device=dev)
+        check(self.lib.ss_frame_accept_batch_dev(self.h, _ptr(shard_plane), ss, shard_idx, d, p, data_len, msg_variant,
+                                                 _ptr(slot), _ptr(ballot), n, _ptr(out), stride, _ptr(off), _ptr(ln)))
+        return out, off, ln
+
+    Context.frame_accept_batch = frame_accept_batch
     Context.raft_kth_match = raft_kth_match
     Context.prepare_merge = prepare_merge
 

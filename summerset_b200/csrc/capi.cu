@@ -783,6 +783,17 @@ int ss_crossword_distribute_dev(ss_rs_coder *c, const uint8_t *data, const uint6
     return launch_crossword_distribute(c, data, data_off, data_len, spr, rep_off, n, replica_logs);
 }
 
+int ss_frame_accept_batch_dev(ss_ctx *ctx, const uint8_t *shard_plane, uint64_t shard_stride, uint32_t shard_idx, uint32_t d,
+                              uint32_t p, uint32_t data_len, uint32_t msg_variant, const uint64_t *slot,
+                              const uint64_t *ballot, uint64_t n, uint8_t *out, uint64_t frame_stride, uint64_t *frame_off,
+                              uint32_t *frame_len) {
+    if (ctx == nullptr) return set_error(SS_ERR_INVALID_ARG, "null context");
+    if (n == 0) return SS_OK;
+    if (!shard_plane || !slot || !ballot || !out || !frame_off || !frame_len) return set_error(SS_ERR_INVALID_ARG, "null buffer");
+    return launch_frame_accept(ctx, shard_plane, shard_stride, shard_idx, d, p, data_len, msg_variant, slot, ballot, n, out,
+                               frame_stride, frame_off, frame_len);
+}
+
 int ss_raft_kth_match_dev(ss_ctx *ctx, const uint32_t *match, uint32_t n_peers, uint64_t G, uint32_t k, uint32_t *out) {
     if (ctx == nullptr) return set_error(SS_ERR_INVALID_ARG, "null context");
     if (G == 0) return SS_OK;

@@ -384,6 +384,80 @@ prepare_merge_kernel(const uint64_t *__restrict__ vote_bal, const uint32_t *__re
 }
 
 // ------------------------------------------------------------------------------------------------
+// Accept-frame packer: turns one shard plane into the exact byte frames an unmodified Summerset
+// peer decodes -- 8-byte big-endian length (utils/safetcp.rs) + bincode(PeerMessage::Msg{PeerMsg::Accept{slot,
+// ballot, reqs_cw}}) where reqs_cw carries the single shard of the destination replica and data_copy = None
+// (rspaxos/request.rs:127-142, utils/rscoding.rs:54-71).  A warp per frame; the frame is placed inside its
+// fixed-stride slot so that the SHARD BYTES land 16-byte aligned: the bulk of the work is an aligned 128-bit copy.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ int put_varint(uint8_t *p, uint64_t v) {
+    if (v < 251ull) { p[0] = static_cast<uint8_t>(v); return 1; }
+    int nb; uint8_t tag;
+    if (v < (1ull << 16)) { nb = 2; tag = 251; }
+    else if (v < (1ull << 32)) { nb = 4; tag = 252; }
+    else { nb = 8; tag = 253; }
+    p[0] = tag;
+    for (int i = 0; i < nb; ++i) p[1 + i] = static_cast<uint8_t>(v >> (8 * i));
+    return 1 + nb;
+}
+
+struct FrameArgs {
+    const uint8_t *plane;      // shard `shard_idx` of codeword g at plane + g*shard_stride (16-byte aligned)
+    uint64_t shard_stride;
+    uint32_t shard_idx, d, p, data_len, L;
+    uint32_t msg_variant;      // PeerMsg::Accept variant index (2 for RSPaxos)
+    const uint64_t *slot, *ballot;
+    uint64_t n;
+    uint8_t *out;
+    uint64_t frame_stride;
+    uint64_t *frame_off;
+    uint32_t *frame_len;
+};
+
+__global__ void __launch_bounds__(kTallyThreads) frame_accept_kernel(const __grid_constant__ FrameArgs A) {
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint64_t warp = (static_cast<uint64_t>(blockIdx.x) * kTallyThreads + threadIdx.x) >> 5;
+    const uint64_t nwarps = (static_cast<uint64_t>(gridDim.x) * kTallyThreads) >> 5;
+    for (uint64_t g = warp; g < A.n; g += nwarps) {
+        // body header: PeerMessage::Msg (0), PeerMsg::Accept, slot, ballot, d, p, data_len, shard_len, #shards,
+        // `shard_idx` Nones, Some tag, shard byte length
+        uint8_t hdr[64];
+        int h = 0;
+        hdr[h++] = 0;
+        h += put_varint(hdr + h, A.msg_variant);
+        h += put_varint(hdr + h, __ldg(A.slot + g));
+        h += put_varint(hdr + h, __ldg(A.ballot + g));
+        hdr[h++] = static_cast<uint8_t>(A.d);
+        hdr[h++] = static_cast<uint8_t>(A.p);
+        h += put_varint(hdr + h, A.data_len);
+        h += put_varint(hdr + h, A.L);
+        h += put_varint(hdr + h, A.d + A.p);
+        for (uint32_t j = 0; j < A.shard_idx; ++j) hdr[h++] = 0;
+        hdr[h++] = 1;
+        h += put_varint(hdr + h, A.L);
+        const uint32_t tail = (A.d + A.p - 1u - A.shard_idx) + 1u;       // remaining Nones + data_copy None
+        const uint64_t body = static_cast<uint64_t>(h) + A.L + tail;
+        const uint32_t pre = 8u + static_cast<uint32_t>(h);              // bytes before the shard payload
+        const uint32_t pad = (16u - (pre & 15u)) & 15u;                  // so that the payload is 16-byte aligned
+        uint8_t *slot_base = A.out + g * A.frame_stride;
+        uint8_t *f = slot_base + pad;
+        if (lane == 0u) {
+            for (int i = 0; i < 8; ++i) f[i] = static_cast<uint8_t>(body >> (8 * (7 - i)));
+            for (int i = 0; i < h; ++i) f[8 + i] = hdr[i];
+            A.frame_off[g] = g * A.frame_stride + pad;
+            A.frame_len[g] = static_cast<uint32_t>(8u + body);
+        }
+        uint8_t *pay = f + pre;
+        const uint8_t *src = A.plane + g * A.shard_stride;
+        const uint32_t full = A.L >> 4;
+        for (uint32_t v = lane; v < full; v += 32u) dev::stg128_cs(pay + v * 16u, dev::ldg128(src + v * 16u));
+        const uint32_t rem = A.L & 15u;
+        if (lane < rem) pay[full * 16u + lane] = src[full * 16u + lane];
+        if (lane < tail) pay[A.L + lane] = 0;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // host launchers
 // ------------------------------------------------------------------------------------------------
 static inline uint32_t stream_grid(ss_ctx *ctx, uint64_t items) {
@@ -543,6 +617,31 @@ int launch_prepare_merge(ss_ctx *ctx, const uint64_t *vote_bal, const uint32_t *
     if (N == 0) return SS_OK;
     prepare_merge_kernel<<<stream_grid(ctx, N), kTallyThreads, 0, ctx->stream>>>(vote_bal, vote_mask, R, N, acks_cnt, d,
                                                                                 population, f, max_bal, merged, action);
+    SS_CUDA(cudaGetLastError());
+    ctx->launches++;
+    return SS_OK;
+}
+
+int launch_frame_accept(ss_ctx *ctx, const uint8_t *plane, uint64_t shard_stride, uint32_t shard_idx, uint32_t d, uint32_t p,
+                        uint32_t data_len, uint32_t msg_variant, const uint64_t *slot, const uint64_t *ballot, uint64_t n,
+                        uint8_t *out, uint64_t frame_stride, uint64_t *frame_off, uint32_t *frame_len) {
+    SS_TRY(ctx_bind(ctx));
+    if (d == 0 || shard_idx >= d + p || d + p > 250) return set_error(SS_ERR_INVALID_ARG, "bad shard geometry");
+    if (data_len == 0) return set_error(SS_ERR_INVALID_ARG, "null codeword cannot be framed");
+    const uint32_t L = (data_len + d - 1) / d;
+    if (frame_stride < static_cast<uint64_t>(L) + 96u + (d + p) || (frame_stride & 15u) ||
+        ((reinterpret_cast<uintptr_t>(out) | reinterpret_cast<uintptr_t>(plane) | shard_stride) & 15u))
+        return set_error(SS_ERR_INVALID_ARG, "frame_stride must be a multiple of 16 and >= shard_len + 96 + d + p; buffers 16-byte aligned");
+    if (n == 0) return SS_OK;
+    FrameArgs A;
+    A.plane = plane; A.shard_stride = shard_stride; A.shard_idx = shard_idx; A.d = d; A.p = p; A.data_len = data_len; A.L = L;
+    A.msg_variant = msg_variant; A.slot = slot; A.ballot = ballot; A.n = n; A.out = out; A.frame_stride = frame_stride;
+    A.frame_off = frame_off; A.frame_len = frame_len;
+    const uint64_t warps = n;
+    uint64_t ctas = (warps + (kTallyThreads / 32) - 1) / (kTallyThreads / 32);
+    const uint64_t cap = static_cast<uint64_t>(ctx->sm_count) * 8ull * 8ull;
+    if (ctas > cap) ctas = cap;
+    frame_accept_kernel<<<static_cast<uint32_t>(ctas), kTallyThreads, 0, ctx->stream>>>(A);
     SS_CUDA(cudaGetLastError());
     ctx->launches++;
     return SS_OK;

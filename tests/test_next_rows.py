@@ -75,6 +75,24 @@ def test_prepare_merge_is_order_independent_and_decides_like_the_handler(oracle)
     assert oracle.prepare_decide(0b0000111111, 3, 6, 5, 2) == U
 
 
+def test_wire_format_encoders():
+    """summerset_b200/wire.py: bincode-standard varints, RSCodeword Encode (rscoding.rs:54-71), framing (safetcp.rs)."""
+    from summerset_b200 import wire
+    assert wire.varint(0) == b"\x00" and wire.varint(250) == b"\xfa" and wire.varint(251) == b"\xfb\xfb\x00"
+    assert wire.varint(65535) == b"\xfb\xff\xff" and wire.varint(65536) == b"\xfc\x00\x00\x01\x00"
+    assert wire.varint((1 << 32) - 1) == b"\xfc\xff\xff\xff\xff" and wire.varint(1 << 32) == b"\xfd" + (1 << 32).to_bytes(8, "little")
+    for v in [0, 1, 250, 251, 300, 65535, 65536, 1 << 31, (1 << 32) - 1, 1 << 32, (1 << 64) - 1]:
+        assert wire.read_varint(wire.varint(v) + b"zz", 0) == (v, len(wire.varint(v)))
+    # TestData("interesting_value") codeword, the shard replica 1 receives (SURVEY 8c KAT)
+    f = wire.rspaxos_accept_frame(7, 300, 3, 2, 18, 1, bytes.fromhex("657374696e67"))
+    assert f.hex() == "0000000000000018" + "00" + "02" + "07" + "fb2c01" + "03" + "02" + "12" + "06" + "05" + "00" + "0106" + "657374696e67" + "000000" + "00"
+    cw, pos = wire.decode_rscodeword(f, 8 + 2 + 1 + 3)
+    assert pos == len(f) and cw["shards"] == [None, b"esting", None, None, None] and not cw["has_copy"]
+    assert (cw["d"], cw["p"], cw["data_len"], cw["shard_len"]) == (3, 2, 18, 6)
+    assert wire.rspaxos_accept_reply_frame(5, 9) == (4).to_bytes(8, "big") + bytes([0, 3, 5, 9])
+    assert wire.wal_commit_slot(1000) == bytes([2, 251]) + (1000).to_bytes(2, "little")
+
+
 # ---------------------------------------------------------------------------------------------
 # GPU parity
 # ---------------------------------------------------------------------------------------------
@@ -194,3 +212,32 @@ def test_crossword_distribute_matches_assignment_and_oracle(ctx, oracle):
                 assert (got[r, o:o + Lg] == shards[j]).all(), (g, r, k, j)
                 assert (got[r, o + Lg:o + lp] == 0).all()
     assert (got[:, total:] == 0x33).all()                               # nothing written past the logs
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("d,p,data_len,shard_idx", [(3, 2, 4096, 0), (3, 2, 4096, 4), (3, 2, 18, 1), (3, 2, 1, 2), (4, 3, 1000, 5), (3, 2, 80000, 3)])
+def test_accept_frames_match_host_encoder(ctx, oracle, d, p, data_len, shard_idx):
+    """GPU-built Accept frames == summerset_b200.wire byte for byte, for slots / ballots on every varint boundary."""
+    from summerset_b200 import wire
+    from summerset_b200.api import ReedSolomon, round_up, shard_len
+    rng = np.random.default_rng(8)
+    n = 257
+    rs = ReedSolomon(ctx, d, p)
+    data = wl.payload_uniform(n, data_len, seed_extra=shard_idx)
+    L = shard_len(data_len, d); ds = round_up(L, 16)
+    planes = np.zeros((d + p, n, ds), dtype=np.uint8)
+    for g in range(n):
+        planes[:d, g, :L] = oracle.cw_split(data[g, :data_len].tobytes(), d)
+    planes[d:] = oracle.rs_encode_uniform(d, p, data, data_len)
+    special = [0, 1, 250, 251, 252, 65535, 65536, (1 << 32) - 1, 1 << 32, (1 << 63) + 5]
+    slot = np.array([special[i % len(special)] if i < 40 else int(rng.integers(0, 1 << 40)) for i in range(n)], dtype=np.uint64)
+    ballot = np.array([special[(i // 3) % len(special)] if i < 60 else int(rng.integers(0, 1 << 20)) for i in range(n)], dtype=np.uint64)
+    out, off, ln = ctx.frame_accept_batch(torch.from_numpy(planes[shard_idx]).to(DEV), shard_idx, d, p, data_len,
+                                          _t(slot), _t(ballot))
+    torch.cuda.synchronize()
+    out = out.cpu().numpy().reshape(-1); off = off.cpu().numpy(); ln = ln.cpu().numpy()
+    for g in range(n):
+        want = wire.rspaxos_accept_frame(int(slot[g]), int(ballot[g]), d, p, data_len, shard_idx, planes[shard_idx, g, :L].tobytes())
+        got = out[int(off[g]):int(off[g]) + int(ln[g])].tobytes()
+        assert got == want, (g, int(slot[g]), int(ballot[g]))
+        assert (int(off[g]) + 8 + (len(want) - 8 - L - (d + p - shard_idx))) % 16 == 0     # payload 16-byte aligned
