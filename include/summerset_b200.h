@@ -307,6 +307,17 @@ int ss_frame_accept_batch_dev(ss_ctx *ctx, const uint8_t *shard_plane, uint64_t 
                               const uint64_t *slot, const uint64_t *ballot, uint64_t n, uint8_t *out,
                               uint64_t frame_stride, uint64_t *frame_off, uint32_t *frame_len);
 
+/* Crossword follower gossip planning (crossword/gossiping.rs:35-84 gossip_targets_excl) for
+ * n_instances committed-but-incomplete instances of replica `me`: walking peers me+1, me+2, ... (mod population) and
+ * skipping the instance's source peer (src_peer[i]) and peers absent from `peer_alive`, a peer is selected when its
+ * assigned shards (policies[policy_idx[i]][peer], as in ss_tally_crossword_dev) include one not yet held/asked for;
+ * excl[peer*N + i] = the availability map at that moment (what the Reconstruct message tells the peer to leave out,
+ * crossword/messages.rs:577-632); the walk stops once data_shards shards are covered.  targets[i] = selected peers.
+ * excl entries of unselected peers are left untouched. */
+int ss_gossip_plan_dev(ss_ctx *ctx, uint32_t me, uint32_t population, uint32_t data_shards, const uint8_t *src_peer,
+                       const uint32_t *avail, const uint8_t *policy_idx, const uint32_t *policies_host,
+                       uint32_t n_policies, uint32_t peer_alive, uint64_t n_instances, uint32_t *targets, uint32_t *excl);
+
 /* ---- tuning / introspection (bench + tests) ------------------------------------------------ */
 /* selects the encode kernel variant: 0 = auto, 1 = direct-LDG, 2 = bulk-copy (TMA) ring */
 int ss_rs_set_variant(ss_rs_coder *coder, int variant);

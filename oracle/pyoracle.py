@@ -288,3 +288,11 @@ def prepare_merge_stream(has_vote, bal, mask):
 def prepare_decide(merged: int, acks_cnt: int, d: int, population: int, f: int) -> int:
     lib().ssor_prepare_decide.restype = C.c_uint32
     return int(lib().ssor_prepare_decide(merged, acks_cnt, d, population, f))
+
+
+def gossip_targets_excl(me: int, population: int, d: int, src_peer: int, avail: int, assignment, peer_alive: int):
+    a = np.ascontiguousarray(assignment, dtype=np.uint32)
+    excl = np.zeros(population, dtype=np.uint32)
+    lib().ssor_gossip_targets_excl.restype = C.c_uint32
+    t = int(lib().ssor_gossip_targets_excl(me, population, d, src_peer, avail, _p(a), peer_alive, _p(excl)))
+    return t, excl

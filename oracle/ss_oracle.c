@@ -608,3 +608,22 @@ uint32_t ssor_prepare_decide(uint32_t merged, uint32_t acks_cnt, uint32_t data_s
     if (avail < population) act |= SSOR_PM_PARITY;
     return act;
 }
+
+/* crossword/gossiping.rs:35-84 */
+uint32_t ssor_gossip_targets_excl(uint32_t me, uint32_t population, uint32_t data_shards, uint32_t src_peer,
+                                  uint32_t avail, const uint32_t *assignment, uint32_t peer_alive, uint32_t *excl) {
+    uint32_t targets = 0;
+    for (uint32_t pp = me + 1; pp < me + population; pp++) {          /* :54 */
+        uint32_t peer = pp % population;
+        if (peer == src_peer) continue;                               /* :56-59 */
+        if (!((peer_alive >> peer) & 1u)) continue;                   /* :60-63 */
+        uint32_t useful = assignment[peer] & ~avail;                  /* :67-72 */
+        if (useful != 0) {
+            excl[peer] = avail;                                       /* :74 (clone before marking) */
+            targets |= 1u << peer;
+            avail |= useful;                                          /* :75-77 */
+        }
+        if (popc32(avail) >= data_shards) break;                      /* :80-82 */
+    }
+    return targets;
+}

@@ -174,6 +174,15 @@ enum { SSOR_PM_USE = 1, SSOR_PM_NULL = 2, SSOR_PM_RECONSTRUCT = 4, SSOR_PM_PARIT
 uint32_t ssor_prepare_decide(uint32_t merged, uint32_t acks_cnt, uint32_t data_shards, uint32_t population,
                              uint32_t fault_tolerance);
 
+/* ---- Crossword follower gossip planning (crossword/gossiping.rs:35-84) ----
+ * gossip_targets_excl for ONE instance: greedily walk peers me+1, me+2, ... (mod n), skipping the source peer and
+ * peers not alive; a peer is selected when its assigned shards include one not yet available/asked for; the
+ * exclusion set sent to it is the availability map at that moment.  Stops once >= d shards are covered.
+ * assignment[r] = shard bitmask of replica r.  Returns the selected-peer bitmask; excl[peer] is written for the
+ * selected peers (others left untouched). */
+uint32_t ssor_gossip_targets_excl(uint32_t me, uint32_t population, uint32_t data_shards, uint32_t src_peer,
+                                  uint32_t avail, const uint32_t *assignment, uint32_t peer_alive, uint32_t *excl);
+
 #ifdef __cplusplus
 }
 #endif

@@ -205,6 +205,19 @@ def _ctx_extras():
                                                  _ptr(slot), _ptr(ballot), n, _ptr(out), stride, _ptr(off), _ptr(ln)))
         return out, off, ln
 
+    def gossip_plan(self, me: int, population: int, data_shards: int, src_peer: torch.Tensor, avail: torch.Tensor,
+                    policy_idx: torch.Tensor, policies: Sequence[Sequence[int]], peer_alive: int):
+        """returns (targets int32 [N], excl int32 [population, N]); excl rows of unselected peers stay -1."""
+        assert src_peer.dtype == torch.uint8 and avail.dtype == torch.int32 and policy_idx.dtype == torch.uint8
+        pol = np.ascontiguousarray(np.array(policies, dtype=np.uint32))
+        N = avail.numel()
+        targets = torch.empty(N, dtype=torch.int32, device=avail.device)
+        excl = torch.full((population, N), -1, dtype=torch.int32, device=avail.device)
+        check(self.lib.ss_gossip_plan_dev(self.h, me, population, data_shards, _ptr(src_peer), _ptr(avail), _ptr(policy_idx),
+                                          pol.ctypes.data, pol.shape[0], peer_alive, N, _ptr(targets), _ptr(excl)))
+        return targets, excl
+
+    Context.gossip_plan = gossip_plan
     Context.frame_accept_batch = frame_accept_batch
     Context.raft_kth_match = raft_kth_match
     Context.prepare_merge = prepare_merge

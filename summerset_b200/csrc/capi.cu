@@ -794,6 +794,16 @@ int ss_frame_accept_batch_dev(ss_ctx *ctx, const uint8_t *shard_plane, uint64_t 
                                frame_stride, frame_off, frame_len);
 }
 
+int ss_gossip_plan_dev(ss_ctx *ctx, uint32_t me, uint32_t population, uint32_t d, const uint8_t *src_peer, const uint32_t *avail,
+                       const uint8_t *policy_idx, const uint32_t *policies_host, uint32_t n_policies, uint32_t peer_alive,
+                       uint64_t N, uint32_t *targets, uint32_t *excl) {
+    if (ctx == nullptr) return set_error(SS_ERR_INVALID_ARG, "null context");
+    if (N == 0) return SS_OK;
+    if (!src_peer || !avail || !policy_idx || !policies_host || !targets || !excl) return set_error(SS_ERR_INVALID_ARG, "null buffer");
+    return launch_gossip_plan(ctx, me, population, d, src_peer, avail, policy_idx, policies_host, n_policies, peer_alive, N,
+                              targets, excl);
+}
+
 int ss_raft_kth_match_dev(ss_ctx *ctx, const uint32_t *match, uint32_t n_peers, uint64_t G, uint32_t k, uint32_t *out) {
     if (ctx == nullptr) return set_error(SS_ERR_INVALID_ARG, "null context");
     if (G == 0) return SS_OK;

@@ -165,4 +165,8 @@ int launch_frame_accept(ss_ctx *ctx, const uint8_t *plane, uint64_t shard_stride
                         uint32_t data_len, uint32_t msg_variant, const uint64_t *slot, const uint64_t *ballot, uint64_t n,
                         uint8_t *out, uint64_t frame_stride, uint64_t *frame_off, uint32_t *frame_len);
 
+int launch_gossip_plan(ss_ctx *ctx, uint32_t me, uint32_t population, uint32_t d, const uint8_t *src_peer,
+                       const uint32_t *avail, const uint8_t *policy_idx, const uint32_t *policies_host, uint32_t n_policies,
+                       uint32_t peer_alive, uint64_t N, uint32_t *targets, uint32_t *excl);
+
 }  // namespace ssb

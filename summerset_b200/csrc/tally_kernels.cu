@@ -457,6 +457,36 @@ __global__ void __launch_bounds__(kTallyThreads) frame_accept_kernel(const __gri
     }
 }
 
+// Crossword follower gossip planning, one instance per thread (crossword/gossiping.rs:35-84): greedy walk over the
+// peers after `me`; selected peers get the availability map of that moment as their exclusion set.
+__global__ void __launch_bounds__(kTallyThreads)
+gossip_plan_kernel(uint32_t me, uint32_t population, uint32_t d, const uint8_t *__restrict__ src_peer,
+                   const uint32_t *__restrict__ avail_in, const uint8_t *__restrict__ policy_idx,
+                   const uint32_t *__restrict__ policies, uint32_t n_policies, uint32_t peer_alive, uint64_t N,
+                   uint32_t *__restrict__ targets, uint32_t *__restrict__ excl /* [population][N] */) {
+    const uint64_t stride = static_cast<uint64_t>(gridDim.x) * kTallyThreads;
+    for (uint64_t i = static_cast<uint64_t>(blockIdx.x) * kTallyThreads + threadIdx.x; i < N; i += stride) {
+        uint32_t avail = __ldg(avail_in + i);
+        const uint32_t src = src_peer[i];
+        uint32_t k = policy_idx[i];
+        if (k >= n_policies) k = 0;
+        const uint32_t *asg = policies + k * population;
+        uint32_t t = 0;
+        for (uint32_t pp = me + 1u; pp < me + population; ++pp) {
+            const uint32_t peer = pp % population;
+            if (peer == src || !((peer_alive >> peer) & 1u)) continue;
+            const uint32_t useful = __ldg(asg + peer) & ~avail;
+            if (useful != 0u) {
+                excl[static_cast<uint64_t>(peer) * N + i] = avail;
+                t |= 1u << peer;
+                avail |= useful;
+            }
+            if (static_cast<uint32_t>(__popc(avail)) >= d) break;
+        }
+        targets[i] = t;
+    }
+}
+
 // ------------------------------------------------------------------------------------------------
 // host launchers
 // ------------------------------------------------------------------------------------------------
@@ -642,6 +672,26 @@ int launch_frame_accept(ss_ctx *ctx, const uint8_t *plane, uint64_t shard_stride
     const uint64_t cap = static_cast<uint64_t>(ctx->sm_count) * 8ull * 8ull;
     if (ctas > cap) ctas = cap;
     frame_accept_kernel<<<static_cast<uint32_t>(ctas), kTallyThreads, 0, ctx->stream>>>(A);
+    SS_CUDA(cudaGetLastError());
+    ctx->launches++;
+    return SS_OK;
+}
+
+int launch_gossip_plan(ss_ctx *ctx, uint32_t me, uint32_t population, uint32_t d, const uint8_t *src_peer,
+                       const uint32_t *avail, const uint8_t *policy_idx, const uint32_t *policies_host, uint32_t n_policies,
+                       uint32_t peer_alive, uint64_t N, uint32_t *targets, uint32_t *excl) {
+    SS_TRY(ctx_bind(ctx));
+    if (population == 0 || population > 32 || me >= population) return set_error(SS_ERR_INVALID_ARG, "bad me/population");
+    if (n_policies == 0 || n_policies > 16) return set_error(SS_ERR_INVALID_ARG, "n_policies must be 1..16");
+    if (N == 0) return SS_OK;
+    const size_t pol_bytes = sizeof(uint32_t) * n_policies * population;
+    void *scratch = nullptr;
+    SS_TRY(ctx_scratch(ctx, pol_bytes, &scratch));
+    SS_CUDA(cudaMemcpyAsync(scratch, policies_host, pol_bytes, cudaMemcpyHostToDevice, ctx->stream));
+    SS_CUDA(cudaStreamSynchronize(ctx->stream));       // policies_host may be reused by the caller
+    gossip_plan_kernel<<<stream_grid(ctx, N), kTallyThreads, 0, ctx->stream>>>(
+        me, population, d, src_peer, avail, policy_idx, static_cast<const uint32_t *>(scratch), n_policies, peer_alive, N,
+        targets, excl);
     SS_CUDA(cudaGetLastError());
     ctx->launches++;
     return SS_OK;

@@ -75,6 +75,24 @@ def test_prepare_merge_is_order_independent_and_decides_like_the_handler(oracle)
     assert oracle.prepare_decide(0b0000111111, 3, 6, 5, 2) == U
 
 
+def test_gossip_targets_excl_semantics(oracle):
+    """crossword/gossiping.rs:35-84 on hand cases (n=5, d=3, balanced spr=1: replica r holds shard r)."""
+    asg = oracle.cw_brr_assignment(5, 5, 1)
+    # I am replica 2 holding shard 2, leader was 0, everyone alive: ask 3 (shard 3) then 4 (shard 4) -> 3 shards, stop
+    t, excl = oracle.gossip_targets_excl(2, 5, 3, 0, 0b00100, asg, 0b11111)
+    assert t == 0b11000 and excl[3] == 0b00100 and excl[4] == 0b01100
+    # peer 3 dead: ask 4, skip source 0, then 1
+    t, excl = oracle.gossip_targets_excl(2, 5, 3, 0, 0b00100, asg, 0b10111)
+    assert t == 0b10010 and excl[4] == 0b00100 and excl[1] == 0b10100
+    # spr=2 assignment: one peer already covers two missing shards
+    asg2 = oracle.cw_brr_assignment(5, 5, 2)
+    t, excl = oracle.gossip_targets_excl(2, 5, 3, 0, int(asg2[2]), asg2, 0b11111)
+    assert t == 0b01000 and excl[3] == int(asg2[2])
+    # coverage is checked AFTER a peer is considered (:80-82): even with d shards held the first useful peer is asked
+    t, excl = oracle.gossip_targets_excl(2, 5, 3, 0, 0b00111, asg, 0b11111)
+    assert t == 0b01000 and excl[3] == 0b00111
+
+
 def test_wire_format_encoders():
     """summerset_b200/wire.py: bincode-standard varints, RSCodeword Encode (rscoding.rs:54-71), framing (safetcp.rs)."""
     from summerset_b200 import wire
@@ -241,3 +259,31 @@ def test_accept_frames_match_host_encoder(ctx, oracle, d, p, data_len, shard_idx
         got = out[int(off[g]):int(off[g]) + int(ln[g])].tobytes()
         assert got == want, (g, int(slot[g]), int(ballot[g]))
         assert (int(off[g]) + 8 + (len(want) - 8 - L - (d + p - shard_idx))) % 16 == 0     # payload 16-byte aligned
+
+
+@pytest.mark.gpu
+def test_gossip_plan_on_gpu(ctx, oracle):
+    rng = np.random.default_rng(11)
+    for n, T, d in [(5, 5, 3), (7, 7, 4), (5, 10, 6)]:
+        dj = T // n
+        policies = [oracle.cw_brr_assignment(n, T, spr) for spr in range(dj, d + 1, dj)]
+        policies.append(rng.integers(0, 1 << T, size=n).astype(np.uint32))          # an unbalanced one
+        K = len(policies)
+        N = 6007
+        me = int(rng.integers(0, n))
+        alive = int(rng.integers(0, 1 << n)) | (1 << me)
+        src = rng.integers(0, n, N).astype(np.uint8)
+        avail = rng.integers(0, 1 << T, N).astype(np.uint32)
+        pidx = rng.integers(0, K, N).astype(np.uint8)
+        targets, excl = ctx.gossip_plan(me, n, d, torch.from_numpy(src).to(DEV), _t(avail), torch.from_numpy(pidx).to(DEV),
+                                        [list(map(int, q)) for q in policies], alive)
+        torch.cuda.synchronize()
+        targets = targets.cpu().numpy().view(np.uint32); excl = excl.cpu().numpy().view(np.uint32)
+        for i in range(N):
+            wt, we = oracle.gossip_targets_excl(me, n, d, int(src[i]), int(avail[i]), policies[int(pidx[i])], alive)
+            assert int(targets[i]) == wt, (n, i)
+            for peer in range(n):
+                if (wt >> peer) & 1:
+                    assert int(excl[peer, i]) == int(we[peer])
+                else:
+                    assert int(excl[peer, i]) == 0xFFFFFFFF       # untouched
