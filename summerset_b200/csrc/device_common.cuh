@@ -38,6 +38,18 @@ __device__ __forceinline__ void stg128_cs(void *p, const uint4 &v) {
                  : "memory");
 }
 
+// 128-bit store with a run-time cache operator (tuning knob for stores that land in a peer GPU's memory):
+// 0 = .cs (streaming), 1 = default write-back, 2 = .cg, 3 = .wt
+__device__ __forceinline__ void stg128_mode(void *p, const uint4 &v, uint32_t mode) {
+    if (mode == 0u) { stg128_cs(p, v); return; }
+    if (mode == 1u)
+        asm volatile("st.global.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+    else if (mode == 2u)
+        asm volatile("st.global.cg.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+    else
+        asm volatile("st.global.wt.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+
 // keep the first nvalid (0..16) bytes of v, zero the rest
 __device__ __forceinline__ uint4 keep_bytes(uint4 v, int nvalid) {
     if (nvalid >= 16) return v;

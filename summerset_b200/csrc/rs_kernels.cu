@@ -157,6 +157,7 @@ struct Enc32Row {
     uint32_t s1, s2;          // (L & 15), (2L & 15): misalignment of shards 1 and 2
     uint32_t emit_data;
     uint32_t chunk;           // 0: codewords g = blockIdx.x + i*gridDim.x ; else CTA b owns [b*chunk, (b+1)*chunk)
+    uint32_t st_mode;         // cache operator of the plane stores in replicate mode (tuning)
     const uint64_t *planes;   // fused tally (nullptr: none); G == n
     uint32_t R, threshold;
     uint64_t *committed;
@@ -205,7 +206,7 @@ template <bool EMIT, bool MASKED>
 __device__ __forceinline__ void rs32_row_column(const uint8_t *__restrict__ src, uint8_t *const (&out)[5],
                                                 uint32_t k, uint32_t o1, uint32_t o2,
                                                 uint32_t s0, uint32_t s1, uint32_t s2, int nva, int nvb, int nvc,
-                                                int onv) {
+                                                int onv, uint32_t st_mode = 0u) {
     // `src` is the 16-byte-aligned address at or below the payload (payload = src + s0); o1/o2 are aligned
     // offsets from src.  Loads first (pairs adjacent so the second one hits the sectors the first just
     // brought into L1), then the byte funnels.
@@ -237,12 +238,15 @@ __device__ __forceinline__ void rs32_row_column(const uint8_t *__restrict__ src,
         p0 = keep_bytes(p0, onv);
         p1 = keep_bytes(p1, onv);
     }
-    dev::stg128_cs(out[3] + k, p0);
-    dev::stg128_cs(out[4] + k, p1);
-    if (EMIT) {   // data shards into their planes too: the pack-for-send of subset_copy (rscoding.rs:255-293)
-        dev::stg128_cs(out[0] + k, MASKED ? keep_bytes(a, onv) : a);
-        dev::stg128_cs(out[1] + k, MASKED ? keep_bytes(b, onv) : b);
-        dev::stg128_cs(out[2] + k, MASKED ? keep_bytes(c, onv) : c);
+    if (EMIT) {   // all five planes (possibly peer memory): data shards too -- the pack-for-send of subset_copy
+        dev::stg128_mode(out[3] + k, p0, st_mode);
+        dev::stg128_mode(out[4] + k, p1, st_mode);
+        dev::stg128_mode(out[0] + k, MASKED ? keep_bytes(a, onv) : a, st_mode);
+        dev::stg128_mode(out[1] + k, MASKED ? keep_bytes(b, onv) : b, st_mode);
+        dev::stg128_mode(out[2] + k, MASKED ? keep_bytes(c, onv) : c, st_mode);
+    } else {
+        dev::stg128_cs(out[3] + k, p0);
+        dev::stg128_cs(out[4] + k, p1);
     }
 }
 
@@ -286,7 +290,7 @@ __global__ void __launch_bounds__(MAXT, MINB) rs32_encode_row_kernel(const __gri
             uint8_t *const out[5] = {EMIT ? P.plane[0] + so : nullptr, EMIT ? P.plane[1] + so : nullptr,
                                      EMIT ? P.plane[2] + so : nullptr, P.plane[3] + so, P.plane[4] + so};
             rs32_row_column<EMIT, false>(P.data + static_cast<uint64_t>(g) * P.data_stride, out, k, o1, o2, 0u, s1, s2,
-                                         16, 16, 16, 16);
+                                         16, 16, 16, 16, P.st_mode);
         }
     } else {
 #pragma unroll 1
@@ -295,7 +299,7 @@ __global__ void __launch_bounds__(MAXT, MINB) rs32_encode_row_kernel(const __gri
             uint8_t *const out[5] = {EMIT ? P.plane[0] + so : nullptr, EMIT ? P.plane[1] + so : nullptr,
                                      EMIT ? P.plane[2] + so : nullptr, P.plane[3] + so, P.plane[4] + so};
             rs32_row_column<EMIT, true>(P.data + static_cast<uint64_t>(g) * P.data_stride, out, k, o1, o2, 0u, s1, s2,
-                                        nva, nvb, nvc, onv);
+                                        nva, nvb, nvc, onv, P.st_mode);
         }
     }
 }
@@ -926,6 +930,7 @@ int launch_rs_encode(ss_rs_coder *coder, const EncGeom &g, const TallyArgs *tall
             uint64_t ctas = static_cast<uint64_t>(ctx->sm_count) * per_sm * waves;
             if (ctas > g.n) ctas = g.n;
             Rw.chunk = 0;
+            Rw.st_mode = static_cast<uint32_t>((coder->variant >> 8) & 3);
             if (vchunk) { Rw.chunk = static_cast<uint32_t>((g.n + ctas - 1) / ctas); ctas = (g.n + Rw.chunk - 1) / Rw.chunk; }
             const uint32_t grid = static_cast<uint32_t>(ctas);
             // register budget variants (tuning knob ss_rs_set_variant): 0/2 = 40 regs, 3 = 32 regs, 4 = unconstrained

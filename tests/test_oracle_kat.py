@@ -205,3 +205,21 @@ def test_batch_matches_single_and_simd(oracle):
             for j in range(p):
                 assert (par0[j, g, :L] == cw[d + j]).all()
                 assert (par0[j, g, L:] == 0).all()
+
+
+def test_oracle_reproduces_committed_golden_fixtures(oracle):
+    """tests/golden/*.npz were generated by tests/golden/make_golden.py from this oracle; any drift of the oracle
+    (or of the seeded workload generators) shows up here on the CPU, before a GPU is involved."""
+    from pathlib import Path
+    z = np.load(Path(__file__).parent / "golden" / "rs_golden.npz")
+    keys = [k[5:] for k in z.files if k.startswith("data_")]
+    assert len(keys) >= 6
+    for key in keys:
+        d, p, data_len = (int(x) for x in key.split("_"))
+        assert (oracle.rs_encode_uniform(d, p, z["data_" + key], data_len) == z["parity_" + key]).all(), key
+    t = np.load(Path(__file__).parent / "golden" / "tally_golden.npz")
+    c, bar = oracle.tally_planes(t["planes"], int(t["threshold"]))
+    assert (c == t["committed"]).all() and (bar == t["commit_bar"]).all()
+    nc = oracle.raft_scan_batch(t["raft_match"], t["raft_last_commit"], t["raft_log_end"], t["raft_curr_term"],
+                                t["raft_terms"], int(t["raft_threshold"]))
+    assert (nc == t["raft_new_commit"]).all()
