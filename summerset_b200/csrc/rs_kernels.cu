@@ -250,6 +250,46 @@ __device__ __forceinline__ void rs32_row_column(const uint8_t *__restrict__ src,
     }
 }
 
+// two unmasked columns (k and k + 512 bytes) of one codeword with all ten loads in flight before any compute:
+// doubles the memory-level parallelism of a warp that walks a long codeword alone (ragged geometry)
+__device__ __forceinline__ void rs32_row_pair(const uint8_t *__restrict__ src, uint8_t *out3, uint8_t *out4, uint32_t k,
+                                              uint32_t o1, uint32_t o2, uint32_t s0, uint32_t s1, uint32_t s2) {
+    const uint32_t D2 = 512u;
+    const uint4 a0 = dev::ldg128(src + k), A0 = dev::ldg128(src + k + D2);
+    uint4 a1 = a0, A1 = A0;
+    if (s0 != 0u) { a1 = dev::ldg128(src + k + 16u); A1 = dev::ldg128(src + k + D2 + 16u); }
+    const uint4 b0 = dev::ldg128(src + o1), B0 = dev::ldg128(src + o1 + D2);
+    uint4 b1 = b0, B1 = B0;
+    if (s1 != 0u) { b1 = dev::ldg128(src + o1 + 16u); B1 = dev::ldg128(src + o1 + D2 + 16u); }
+    const uint4 c0 = dev::ldg128(src + o2), C0 = dev::ldg128(src + o2 + D2);
+    uint4 c1 = c0, C1 = C0;
+    if (s2 != 0u) { c1 = dev::ldg128(src + o2 + 16u); C1 = dev::ldg128(src + o2 + D2 + 16u); }
+    {
+        const uint4 a = s0 != 0u ? funnel16(a0, a1, s0) : a0;
+        const uint4 b = s1 != 0u ? funnel16(b0, b1, s1) : b0;
+        const uint4 c = s2 != 0u ? funnel16(c0, c1, s2) : c0;
+        uint4 p0, p1;
+        rs32_word_fast(a.x, b.x, c.x, p0.x, p1.x);
+        rs32_word_fast(a.y, b.y, c.y, p0.y, p1.y);
+        rs32_word_fast(a.z, b.z, c.z, p0.z, p1.z);
+        rs32_word_fast(a.w, b.w, c.w, p0.w, p1.w);
+        dev::stg128_cs(out3 + k, p0);
+        dev::stg128_cs(out4 + k, p1);
+    }
+    {
+        const uint4 a = s0 != 0u ? funnel16(A0, A1, s0) : A0;
+        const uint4 b = s1 != 0u ? funnel16(B0, B1, s1) : B0;
+        const uint4 c = s2 != 0u ? funnel16(C0, C1, s2) : C0;
+        uint4 p0, p1;
+        rs32_word_fast(a.x, b.x, c.x, p0.x, p1.x);
+        rs32_word_fast(a.y, b.y, c.y, p0.y, p1.y);
+        rs32_word_fast(a.z, b.z, c.z, p0.z, p1.z);
+        rs32_word_fast(a.w, b.w, c.w, p0.w, p1.w);
+        dev::stg128_cs(out3 + k + D2, p0);
+        dev::stg128_cs(out4 + k + D2, p1);
+    }
+}
+
 template <bool EMIT, int MAXT, int MINB>
 __global__ void __launch_bounds__(MAXT, MINB) rs32_encode_row_kernel(const __grid_constant__ Enc32Row P) {
     const uint32_t v = threadIdx.x;
@@ -315,7 +355,7 @@ struct EncRagged {
     uint32_t padded;
 };
 
-__global__ void __launch_bounds__(kThreads, 4) rs32_encode_ragged_kernel(const __grid_constant__ EncRagged P) {
+__global__ void __launch_bounds__(kThreads, 3) rs32_encode_ragged_kernel(const __grid_constant__ EncRagged P) {
     // a warp per codeword; the byte-funnel parameters are per-codeword, hence warp-uniform
     const uint32_t lane = threadIdx.x & 31u;
     const uint64_t warp = (static_cast<uint64_t>(blockIdx.x) * kThreads + threadIdx.x) >> 5;
@@ -344,7 +384,13 @@ __global__ void __launch_bounds__(kThreads, 4) rs32_encode_ragged_kernel(const _
         const uint8_t *src = pay - s0;
         const uint32_t s1 = (s0 + L) & 15u, s2 = (s0 + 2u * L) & 15u;
         const uint32_t fast_cols = len >= 2u * L ? (((len - 2u * L) < L ? (len - 2u * L) : L) / 16u) : 0u;
-        for (uint32_t v0 = 0; v0 < vpc; v0 += 32u) {
+        uint32_t v0 = 0;
+        // long codewords: two columns per lane per iteration while both are interior
+        for (; v0 + 64u <= fast_cols; v0 += 64u) {
+            const uint32_t k = (v0 + lane) * 16u;
+            rs32_row_pair(src, out, out + P.plane_stride, k, s0 + L + k - s1, s0 + 2u * L + k - s2, s0, s1, s2);
+        }
+        for (; v0 < vpc; v0 += 32u) {
             const uint32_t v = v0 + lane;
             if (v >= vpc) break;
             const uint32_t k = v * 16u;
