@@ -841,7 +841,42 @@ struct CwDistribute {
     uint64_t n;
 };
 
-__global__ void __launch_bounds__(kThreads, 4) rs32_crossword_distribute_kernel(const __grid_constant__ CwDistribute P) {
+// raw aligned vectors covering one unmasked column of the three data shards
+struct Raw6 { uint4 a0, a1, b0, b1, c0, c1; };
+__device__ __forceinline__ void rs32_issue_loads(const uint8_t *__restrict__ src, uint32_t k, uint32_t o1, uint32_t o2,
+                                                 uint32_t s0, uint32_t s1, uint32_t s2, Raw6 &r) {
+    r.a0 = dev::ldg128(src + k);
+    r.a1 = r.a0;
+    if (s0 != 0u) r.a1 = dev::ldg128(src + k + 16u);
+    r.b0 = dev::ldg128(src + o1);
+    r.b1 = r.b0;
+    if (s1 != 0u) r.b1 = dev::ldg128(src + o1 + 16u);
+    r.c0 = dev::ldg128(src + o2);
+    r.c1 = r.c0;
+    if (s2 != 0u) r.c1 = dev::ldg128(src + o2 + 16u);
+}
+__device__ __forceinline__ void rs32_shards_from_raw(const Raw6 &r, uint32_t s0, uint32_t s1, uint32_t s2, uint4 (&sh)[5]) {
+    sh[0] = s0 != 0u ? funnel16(r.a0, r.a1, s0) : r.a0;
+    sh[1] = s1 != 0u ? funnel16(r.b0, r.b1, s1) : r.b0;
+    sh[2] = s2 != 0u ? funnel16(r.c0, r.c1, s2) : r.c0;
+    rs32_word_fast(sh[0].x, sh[1].x, sh[2].x, sh[3].x, sh[4].x);
+    rs32_word_fast(sh[0].y, sh[1].y, sh[2].y, sh[3].y, sh[4].y);
+    rs32_word_fast(sh[0].z, sh[1].z, sh[2].z, sh[3].z, sh[4].z);
+    rs32_word_fast(sh[0].w, sh[1].w, sh[2].w, sh[3].w, sh[4].w);
+}
+// replica r, slot kk holds shard (r + kk) mod 5
+__device__ __forceinline__ void distribute_store(const CwDistribute &P, uint64_t ro, uint32_t k, uint32_t Lpad, uint32_t spr,
+                                                 const uint4 (&sh)[5]) {
+#pragma unroll
+    for (int r = 0; r < 5; ++r) {
+        uint8_t *dst = P.rep[r] + ro + k;
+#pragma unroll
+        for (int kk = 0; kk < 3; ++kk)
+            if (static_cast<uint32_t>(kk) < spr) dev::stg128_cs(dst + static_cast<uint64_t>(kk) * Lpad, sh[(r + kk) % 5]);
+    }
+}
+
+__global__ void __launch_bounds__(kThreads, 3) rs32_crossword_distribute_kernel(const __grid_constant__ CwDistribute P) {
     const uint32_t lane = threadIdx.x & 31u;
     const uint64_t warp = (static_cast<uint64_t>(blockIdx.x) * kThreads + threadIdx.x) >> 5;
     const uint64_t nwarps = (static_cast<uint64_t>(gridDim.x) * kThreads) >> 5;
@@ -858,42 +893,57 @@ __global__ void __launch_bounds__(kThreads, 4) rs32_crossword_distribute_kernel(
         const uint32_t s0 = static_cast<uint32_t>(reinterpret_cast<uintptr_t>(pay)) & 15u;
         const uint8_t *src = pay - s0;
         const uint32_t s1 = (s0 + L) & 15u, s2 = (s0 + 2u * L) & 15u;
-        for (uint32_t v = lane; v < vpc; v += 32u) {
-            const uint32_t k = v * 16u;
-            const int nva = clamp16(static_cast<int64_t>(len) - k);
-            const int nvb = clamp16(static_cast<int64_t>(len) - L - k);
-            const int nvc = clamp16(static_cast<int64_t>(len) - 2ll * L - k);
-            const int onv = clamp16(static_cast<int64_t>(L) - k);
-            const uint32_t o1 = s0 + L + k - s1, o2 = s0 + 2u * L + k - s2;
-            // loads + funnels + masks (the masked column path: ragged tails are everywhere in this workload)
-            const uint4 a0 = dev::ldg128(src + k);
-            uint4 a1 = a0;
-            if (s0 != 0u && static_cast<int>(s0) + nva > 16) a1 = dev::ldg128(src + k + 16u);
-            uint4 b0 = make_uint4(0u, 0u, 0u, 0u), c0 = make_uint4(0u, 0u, 0u, 0u);
-            if (nvb > 0) b0 = dev::ldg128(src + o1);
-            uint4 b1 = b0;
-            if (s1 != 0u && static_cast<int>(s1) + nvb > 16) b1 = dev::ldg128(src + o1 + 16u);
-            if (nvc > 0) c0 = dev::ldg128(src + o2);
-            uint4 c1 = c0;
-            if (s2 != 0u && static_cast<int>(s2) + nvc > 16) c1 = dev::ldg128(src + o2 + 16u);
+        const uint32_t fast_cols = len >= 2u * L ? (((len - 2u * L) < L ? (len - 2u * L) : L) / 16u) : 0u;
+        uint32_t v0 = 0;
+        // interior columns, two per lane per iteration: all loads in flight before any compute
+        for (; v0 + 64u <= fast_cols; v0 += 64u) {
+            const uint32_t k = (v0 + lane) * 16u, k2 = k + 512u;
+            Raw6 r1, r2;
+            rs32_issue_loads(src, k, s0 + L + k - s1, s0 + 2u * L + k - s2, s0, s1, s2, r1);
+            rs32_issue_loads(src, k2, s0 + L + k2 - s1, s0 + 2u * L + k2 - s2, s0, s1, s2, r2);
             uint4 sh[5];
-            sh[0] = keep_bytes(s0 != 0u ? funnel16(a0, a1, s0) : a0, nva < onv ? nva : onv);
-            sh[1] = keep_bytes(s1 != 0u ? funnel16(b0, b1, s1) : b0, nvb < onv ? nvb : onv);
-            sh[2] = keep_bytes(s2 != 0u ? funnel16(c0, c1, s2) : c0, nvc < onv ? nvc : onv);
-            rs32_word_fast(sh[0].x, sh[1].x, sh[2].x, sh[3].x, sh[4].x);
-            rs32_word_fast(sh[0].y, sh[1].y, sh[2].y, sh[3].y, sh[4].y);
-            rs32_word_fast(sh[0].z, sh[1].z, sh[2].z, sh[3].z, sh[4].z);
-            rs32_word_fast(sh[0].w, sh[1].w, sh[2].w, sh[3].w, sh[4].w);
-            sh[3] = keep_bytes(sh[3], onv);
-            sh[4] = keep_bytes(sh[4], onv);
-            // replica r, slot kk holds shard (r + kk) mod 5
-#pragma unroll
-            for (int r = 0; r < 5; ++r) {
-                uint8_t *dst = P.rep[r] + ro + k;
-#pragma unroll
-                for (int kk = 0; kk < 3; ++kk)
-                    if (static_cast<uint32_t>(kk) < spr) dev::stg128_cs(dst + static_cast<uint64_t>(kk) * Lpad, sh[(r + kk) % 5]);
+            rs32_shards_from_raw(r1, s0, s1, s2, sh);
+            distribute_store(P, ro, k, Lpad, spr, sh);
+            rs32_shards_from_raw(r2, s0, s1, s2, sh);
+            distribute_store(P, ro, k2, Lpad, spr, sh);
+        }
+        for (; v0 < vpc; v0 += 32u) {
+            const uint32_t v = v0 + lane;
+            if (v >= vpc) break;
+            const uint32_t k = v * 16u;
+            const uint32_t o1 = s0 + L + k - s1, o2 = s0 + 2u * L + k - s2;
+            uint4 sh[5];
+            if (v0 + 32u <= fast_cols) {
+                Raw6 r1;
+                rs32_issue_loads(src, k, o1, o2, s0, s1, s2, r1);
+                rs32_shards_from_raw(r1, s0, s1, s2, sh);
+            } else {
+                // masked column: zero-padded payload tail / partial last vector; windows in the padding are not read
+                const int nva = clamp16(static_cast<int64_t>(len) - k);
+                const int nvb = clamp16(static_cast<int64_t>(len) - L - k);
+                const int nvc = clamp16(static_cast<int64_t>(len) - 2ll * L - k);
+                const int onv = clamp16(static_cast<int64_t>(L) - k);
+                const uint4 a0 = dev::ldg128(src + k);
+                uint4 a1 = a0;
+                if (s0 != 0u && static_cast<int>(s0) + nva > 16) a1 = dev::ldg128(src + k + 16u);
+                uint4 b0 = make_uint4(0u, 0u, 0u, 0u), c0 = make_uint4(0u, 0u, 0u, 0u);
+                if (nvb > 0) b0 = dev::ldg128(src + o1);
+                uint4 b1 = b0;
+                if (s1 != 0u && static_cast<int>(s1) + nvb > 16) b1 = dev::ldg128(src + o1 + 16u);
+                if (nvc > 0) c0 = dev::ldg128(src + o2);
+                uint4 c1 = c0;
+                if (s2 != 0u && static_cast<int>(s2) + nvc > 16) c1 = dev::ldg128(src + o2 + 16u);
+                sh[0] = keep_bytes(s0 != 0u ? funnel16(a0, a1, s0) : a0, nva < onv ? nva : onv);
+                sh[1] = keep_bytes(s1 != 0u ? funnel16(b0, b1, s1) : b0, nvb < onv ? nvb : onv);
+                sh[2] = keep_bytes(s2 != 0u ? funnel16(c0, c1, s2) : c0, nvc < onv ? nvc : onv);
+                rs32_word_fast(sh[0].x, sh[1].x, sh[2].x, sh[3].x, sh[4].x);
+                rs32_word_fast(sh[0].y, sh[1].y, sh[2].y, sh[3].y, sh[4].y);
+                rs32_word_fast(sh[0].z, sh[1].z, sh[2].z, sh[3].z, sh[4].z);
+                rs32_word_fast(sh[0].w, sh[1].w, sh[2].w, sh[3].w, sh[4].w);
+                sh[3] = keep_bytes(sh[3], onv);
+                sh[4] = keep_bytes(sh[4], onv);
             }
+            distribute_store(P, ro, k, Lpad, spr, sh);
         }
     }
 }
