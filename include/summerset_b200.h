@@ -87,6 +87,9 @@ int ss_dev_alloc(ss_ctx *ctx, size_t bytes, void **dptr);
 int ss_dev_free(ss_ctx *ctx, void *dptr);
 int ss_dev_memset(ss_ctx *ctx, void *dptr, int value, size_t bytes);      /* async */
 int ss_host_alloc(ss_ctx *ctx, size_t bytes, void **hptr);                /* pinned */
+/* write-combined pinned memory: for buffers the CPU only WRITES and the GPU reads (payload staging); faster H2D on
+ * some hosts, very slow for CPU reads */
+int ss_host_alloc_wc(ss_ctx *ctx, size_t bytes, void **hptr);
 int ss_host_free(ss_ctx *ctx, void *hptr);
 int ss_copy_h2d(ss_ctx *ctx, void *dst_dev, const void *src_host, size_t bytes); /* async */
 int ss_copy_d2h(ss_ctx *ctx, void *dst_host, const void *src_dev, size_t bytes); /* async */

@@ -50,6 +50,7 @@ SIGNATURES = {
     "ss_dev_free": (_i, [_vp, _vp]),
     "ss_dev_memset": (_i, [_vp, _vp, _i, _sz]),
     "ss_host_alloc": (_i, [_vp, _sz, C.POINTER(_vp)]),
+    "ss_host_alloc_wc": (_i, [_vp, _sz, C.POINTER(_vp)]),
     "ss_host_free": (_i, [_vp, _vp]),
     "ss_copy_h2d": (_i, [_vp, _vp, _vp, _sz]),
     "ss_copy_d2h": (_i, [_vp, _vp, _vp, _sz]),

@@ -5,6 +5,7 @@
 // All arithmetic on shard bytes and vote masks happens in the kernels (rs_kernels.cu,
 // tally_kernels.cu).  There is no CPU fallback anywhere in this file.
 #include <cstdarg>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <new>
@@ -327,6 +328,12 @@ int ss_host_alloc(ss_ctx *ctx, size_t bytes, void **hptr) {
     SS_TRY(ctx_bind(ctx));
     if (hptr == nullptr) return set_error(SS_ERR_INVALID_ARG, "null out pointer");
     SS_CUDA(cudaHostAlloc(hptr, bytes ? bytes : 1, cudaHostAllocDefault));
+    return SS_OK;
+}
+int ss_host_alloc_wc(ss_ctx *ctx, size_t bytes, void **hptr) {
+    SS_TRY(ctx_bind(ctx));
+    if (hptr == nullptr) return set_error(SS_ERR_INVALID_ARG, "null out pointer");
+    SS_CUDA(cudaHostAlloc(hptr, bytes ? bytes : 1, cudaHostAllocWriteCombined));
     return SS_OK;
 }
 int ss_host_free(ss_ctx *ctx, void *hptr) {
@@ -664,8 +671,10 @@ int ss_rs_encode_uniform(ss_rs_coder *c, const uint8_t *data, uint64_t data_stri
     const int d = c->d, p = c->p;
     const uint64_t L = (uint64_t(data_len) + d - 1) / d, ds = (L + 15) & ~uint64_t(15);
     if (data_stride < data_len || shard_stride < L) return set_error(SS_ERR_INVALID_ARG, "stride shorter than element");
-    // chunk: ~64 MiB of payload
-    uint64_t C = (64ull << 20) / data_stride;
+    // chunk: 16 MiB of payload measured best (profiles/r01_pcie_probe.txt); SS_E2E_CHUNK_MB overrides, for tuning
+    uint64_t chunk_mb = 16;
+    if (const char *e = getenv("SS_E2E_CHUNK_MB")) { const long v = atol(e); if (v >= 1 && v <= 4096) chunk_mb = static_cast<uint64_t>(v); }
+    uint64_t C = (chunk_mb << 20) / data_stride;
     if (C < 1) C = 1;
     if (C > n) C = n;
     const uint64_t in_stride_dev = (data_stride + 15) & ~uint64_t(15);
