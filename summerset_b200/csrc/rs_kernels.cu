@@ -158,6 +158,7 @@ struct Enc32Row {
     uint32_t emit_data;
     uint32_t chunk;           // 0: codewords g = blockIdx.x + i*gridDim.x ; else CTA b owns [b*chunk, (b+1)*chunk)
     uint32_t st_mode;         // cache operator of the plane stores in replicate mode (tuning)
+    uint32_t rotate;          // 1: rotate the warp -> column-block assignment per codeword (default)
     const uint64_t *planes;   // fused tally (nullptr: none); G == n
     uint32_t R, threshold;
     uint64_t *committed;
@@ -292,54 +293,51 @@ __device__ __forceinline__ void rs32_row_pair(const uint8_t *__restrict__ src, u
 
 template <bool EMIT, int MAXT, int MINB>
 __global__ void __launch_bounds__(MAXT, MINB) rs32_encode_row_kernel(const __grid_constant__ Enc32Row P) {
-    const uint32_t v = threadIdx.x;
-    const uint32_t k = v * 16u;
+    const uint32_t lane = threadIdx.x & 31u, wid = threadIdx.x >> 5, nblk = blockDim.x >> 5;
     const uint32_t s1 = P.s1, s2 = P.s2;
-    // aligned in-codeword offsets of the vectors that cover shard 1 / shard 2 at column v
-    const uint32_t o1 = P.L + k - s1, o2 = 2u * P.L + k - s2;
-    const bool is_col = v < P.vpc;
-    // warp-uniform: does this warp contain a column that needs masking?
-    const uint32_t warp_first = v & ~31u;
-    const bool warp_masked = warp_first + 32u > P.fast_cols;
     auto clamp16 = [](int64_t r) { return r > 16 ? 16 : (r < 0 ? 0 : static_cast<int>(r)); };
-    const int nva = clamp16(static_cast<int64_t>(P.len) - k);
-    const int nvb = clamp16(static_cast<int64_t>(P.len) - P.L - k);
-    const int nvc = clamp16(static_cast<int64_t>(P.len) - 2ll * P.L - k);
-    const int onv = clamp16(static_cast<int64_t>(P.L) - k);
 
     // ---- fused tally: this CTA's contiguous slice of groups, coalesced (one pass, before the encode loop) ----
     if (P.planes != nullptr) {
         const uint32_t per = (P.n + gridDim.x - 1) / gridDim.x;
         const uint32_t lo = blockIdx.x * per;
         const uint32_t hi = lo + per < P.n ? lo + per : P.n;
-        for (uint32_t g = lo + v; g < hi; g += blockDim.x) {
+        for (uint32_t g = lo + threadIdx.x; g < hi; g += blockDim.x) {
             const uint64_t w = dev::tally_word(P.planes, P.R, P.n, g, P.threshold);
             P.committed[g] = w;
             if (P.commit_bar != nullptr) P.commit_bar[g] = dev::commit_prefix(w);
         }
     }
-    if (!is_col) return;
 
+    // The CTA's warps work on the same codeword, each on one 32-column block.  The block that holds the codeword's
+    // last column runs the (longer) masked variant; with a fixed warp->block assignment that warp is the CTA's
+    // critical path and the other warps idle at the end (measured: 10 % of the whole kernel).  So the assignment
+    // ROTATES: on its i-th codeword warp w takes block (w + i) mod nblk, and every warp does every block type
+    // equally often.
     const uint32_t g_begin = P.chunk ? blockIdx.x * P.chunk : blockIdx.x;
     const uint32_t g_step = P.chunk ? 1u : gridDim.x;
     const uint32_t g_end = P.chunk ? (g_begin + P.chunk < P.n ? g_begin + P.chunk : P.n) : P.n;
-    if (!warp_masked) {
+    uint32_t wb = wid;
 #pragma unroll 1
-        for (uint32_t g = g_begin; g < g_end; g += g_step) {
-            const uint64_t so = static_cast<uint64_t>(g) * P.shard_stride;
-            uint8_t *const out[5] = {EMIT ? P.plane[0] + so : nullptr, EMIT ? P.plane[1] + so : nullptr,
-                                     EMIT ? P.plane[2] + so : nullptr, P.plane[3] + so, P.plane[4] + so};
-            rs32_row_column<EMIT, false>(P.data + static_cast<uint64_t>(g) * P.data_stride, out, k, o1, o2, 0u, s1, s2,
-                                         16, 16, 16, 16, P.st_mode);
-        }
-    } else {
-#pragma unroll 1
-        for (uint32_t g = g_begin; g < g_end; g += g_step) {
-            const uint64_t so = static_cast<uint64_t>(g) * P.shard_stride;
-            uint8_t *const out[5] = {EMIT ? P.plane[0] + so : nullptr, EMIT ? P.plane[1] + so : nullptr,
-                                     EMIT ? P.plane[2] + so : nullptr, P.plane[3] + so, P.plane[4] + so};
-            rs32_row_column<EMIT, true>(P.data + static_cast<uint64_t>(g) * P.data_stride, out, k, o1, o2, 0u, s1, s2,
-                                        nva, nvb, nvc, onv, P.st_mode);
+    for (uint32_t g = g_begin; g < g_end; g += g_step) {
+        const uint32_t v = wb * 32u + lane;
+        const uint32_t k = v * 16u;
+        const bool masked = wb * 32u + 32u > P.fast_cols;           // warp-uniform
+        if (P.rotate) wb = (wb + 1u == nblk) ? 0u : wb + 1u;
+        if (v >= P.vpc) continue;
+        // aligned in-codeword offsets of the vectors that cover shard 1 / shard 2 at column v
+        const uint32_t o1 = P.L + k - s1, o2 = 2u * P.L + k - s2;
+        const uint64_t so = static_cast<uint64_t>(g) * P.shard_stride;
+        uint8_t *const out[5] = {EMIT ? P.plane[0] + so : nullptr, EMIT ? P.plane[1] + so : nullptr,
+                                 EMIT ? P.plane[2] + so : nullptr, P.plane[3] + so, P.plane[4] + so};
+        const uint8_t *src = P.data + static_cast<uint64_t>(g) * P.data_stride;
+        if (!masked) {
+            rs32_row_column<EMIT, false>(src, out, k, o1, o2, 0u, s1, s2, 16, 16, 16, 16, P.st_mode);
+        } else {
+            rs32_row_column<EMIT, true>(src, out, k, o1, o2, 0u, s1, s2, clamp16(static_cast<int64_t>(P.len) - k),
+                                        clamp16(static_cast<int64_t>(P.len) - P.L - k),
+                                        clamp16(static_cast<int64_t>(P.len) - 2ll * P.L - k),
+                                        clamp16(static_cast<int64_t>(P.L) - k), P.st_mode);
         }
     }
 }
@@ -1021,26 +1019,27 @@ int launch_rs_encode(ss_rs_coder *coder, const EncGeom &g, const TallyArgs *tall
             // resident CTAs per SM (2048 threads, 32 CTAs) x a few waves; every CTA strides over codewords
             uint32_t per_sm = 2048u / threads; if (per_sm > 32u) per_sm = 32u;
             const int vr = coder->variant & 15, vchunk = (coder->variant >> 4) & 1, vw = (coder->variant >> 5) & 7;
-            static const uint64_t kWaves[8] = {16, 1, 2, 4, 64, 256, 1u << 20, 8};   // [0] = default, rest: tuning
+            static const uint64_t kWaves[8] = {64, 1, 32, 4, 16, 256, 128, 8};   // [0] = default, rest: tuning
             const uint64_t waves = kWaves[vw];
             uint64_t ctas = static_cast<uint64_t>(ctx->sm_count) * per_sm * waves;
             if (ctas > g.n) ctas = g.n;
             Rw.chunk = 0;
             Rw.st_mode = static_cast<uint32_t>((coder->variant >> 8) & 3);
+            Rw.rotate = ((coder->variant >> 10) & 1) ? 0u : 1u;
             if (vchunk) { Rw.chunk = static_cast<uint32_t>((g.n + ctas - 1) / ctas); ctas = (g.n + Rw.chunk - 1) / Rw.chunk; }
             const uint32_t grid = static_cast<uint32_t>(ctas);
             // register budget variants (tuning knob ss_rs_set_variant): 0/2 = 40 regs, 3 = 32 regs, 4 = unconstrained
-            // Register budget: 56/thread (9 CTAs of <= 128 threads per SM) measured best on B200 -- more
-            // occupancy (40 or 32 registers) spills, fewer resident CTAs (64+) loses latency hiding
-            // (profiles/r01_row_kernel_sweep.txt).  The other budgets stay selectable for tuning.
+            // Register budget: 40/thread (12 CTAs of <= 128 threads per SM; the kernel needs ~47 unconstrained and fits
+            // 40 without spilling) and 64 waves measured best on B200 (profiles/r01_row_kernel_sweep.txt).  The other
+            // budgets stay selectable for tuning.
             if (threads > 128) {
                 if (Rw.emit_data) rs32_encode_row_kernel<true, 256, 4><<<grid, threads, 0, st>>>(Rw);
                 else rs32_encode_row_kernel<false, 256, 4><<<grid, threads, 0, st>>>(Rw);
             } else if (Rw.emit_data) rs32_encode_row_kernel<true, 128, 8><<<grid, threads, 0, st>>>(Rw);
             else if (vr == 3) rs32_encode_row_kernel<false, 128, 16><<<grid, threads, 0, st>>>(Rw);   // 32 regs
-            else if (vr == 2) rs32_encode_row_kernel<false, 128, 12><<<grid, threads, 0, st>>>(Rw);   // 40 regs
-            else if (vr == 6) rs32_encode_row_kernel<false, 128, 8><<<grid, threads, 0, st>>>(Rw);    // 64 regs
-            else rs32_encode_row_kernel<false, 128, 9><<<grid, threads, 0, st>>>(Rw);                 // 56 regs
+            else if (vr == 6) rs32_encode_row_kernel<false, 128, 8><<<grid, threads, 0, st>>>(Rw);    // 64 regs cap
+            else if (vr == 7) rs32_encode_row_kernel<false, 128, 9><<<grid, threads, 0, st>>>(Rw);    // 56 regs cap
+            else rs32_encode_row_kernel<false, 128, 12><<<grid, threads, 0, st>>>(Rw);                // 40 regs
             coder->last_kernel = Rw.planes ? "rs32_encode_row_kernel+tally" : "rs32_encode_row_kernel";
             SS_CUDA(cudaGetLastError());
             ctx->launches++;
