@@ -461,6 +461,11 @@ def run_ours(args):
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
             "parity_check": check_note,
         }
+        if world > 1 and args.workload == "cfg3":
+            line["scaling_note"] = ("N=1 simulates all 5 replicas of a group on one GPU (no exchange: the shard planes are the "
+                                    "follower logs). At N>1 replica r of a group led from rank h lives on rank (h+r)%N and the encode "
+                                    "kernel stores its shard there over NVLink, so the step becomes NVLink-bound (roofline.comm); the "
+                                    "same kernel without the remote stores takes roofline.local_only_kernel_ms on every N.")
         line.update(extra)
         print(json.dumps(line))
     if world > 1:

@@ -322,7 +322,14 @@ int ss_gossip_plan_dev(ss_ctx *ctx, uint32_t me, uint32_t population, uint32_t d
                        uint32_t n_policies, uint32_t peer_alive, uint64_t n_instances, uint32_t *targets, uint32_t *excl);
 
 /* ---- tuning / introspection (bench + tests) ------------------------------------------------ */
-/* selects the encode kernel variant: 0 = auto, 1 = direct-LDG, 2 = bulk-copy (TMA) ring */
+/* Tuning knob for experiments (profiles/r01_row_kernel_sweep.txt); 0 = the measured-best defaults.
+ *   bits 0-3  kernel choice / register budget: 1 = flat one-column-per-thread RS(3,2) kernel instead of the row kernel,
+ *             5 = bit-plane generic kernels instead of the Horner ones, 8 = global-table Horner reconstruct instead of the
+ *             shared-memory small-code kernel; 3 / 6 / 7 = 32 / 64 / 56-register builds of the row kernel (default 40)
+ *   bit 4     row kernel: contiguous chunk of codewords per CTA instead of grid-stride
+ *   bits 5-7  row kernel waves of CTAs per resident set: {64 (default), 1, 32, 4, 16, 256, 128, 8}
+ *   bits 8-9  cache operator of the plane stores in replicate mode: .cs (default), write-back, .cg, .wt
+ *   bit 10    row kernel: fixed instead of rotating warp -> column-block assignment */
 int ss_rs_set_variant(ss_rs_coder *coder, int variant);
 /* name of the kernel the last batch call on this coder launched (static string) */
 const char *ss_rs_last_kernel(const ss_rs_coder *coder);
