@@ -9,22 +9,26 @@
 // (rspaxos/request.rs:72-77, crossword/request.rs:82-87, rspaxos/durability.rs:146-159).
 //
 // This is HBM-bound byte work: no tensor cores.  Design points:
-//   * a thread owns one 16-byte "column" of a codeword: it reads the 16 bytes at the same offset
-//     of each of the d source shards (128-bit loads; shards of a contiguous split are generally
-//     misaligned w.r.t. 16 bytes, handled with two aligned loads + a byte funnel shift whose
-//     second load is an L1 hit on the neighbour lane's data) and writes 16 bytes of each output
-//     shard with one 128-bit streaming store;
-//   * GF multiplication is done on four packed field elements per 32-bit register with
-//     prmt/lop3/shift only -- no table, no shared-memory gathers:
-//       - RS(3,2), the code of every 5-replica RSPaxos/Crossword/CRaft deployment, is specialised:
-//         parity0 = a^b^c, parity1 = 0f*a ^ 08*b ^ 06*c evaluated by Horner's rule in x
-//         ( ((a^b)*x ^ (a^c))*x ^ (a^c))*x ^ a ): three packed xtime steps per word;
-//       - every other (d,p) and every reconstruction runs the generic kernel: each source word is
-//         expanded into its 8 bit-planes (byte masks via prmt sign replication) and accumulated
-//         into each output as mask_k & splat(c*2^k); the splats come from a small per-program
-//         coefficient table (one program per erasure pattern, built on the host at coder creation);
-//   * uniform geometry (all codewords the same length) maps threads to columns with a flat index,
-//     so no lane idles on codeword tails; ragged geometry gives each warp whole codewords.
+//   * a thread owns 16-byte "columns" of a codeword: it reads the 16 bytes at the same offset of each of the d source
+//     shards (128-bit loads; the shards of a contiguous split are generally misaligned w.r.t. 16 bytes: two aligned
+//     loads + a byte funnel shift, the second load being an L1 hit on the neighbour lane's sectors) and writes 16
+//     bytes of each output shard with one 128-bit streaming store;
+//   * GF multiplication works on four packed field elements per 32-bit register with prmt / lop3 / imad only -- no
+//     table, no shared-memory gathers.  Every product is a Horner evaluation in x over the coefficient bits:
+//       - RS(3,2), the code of every 5-replica RSPaxos / Crossword / CRaft deployment, is specialised with its
+//         coefficients folded in: parity0 = a^b^c, parity1 = (((a^b)*x ^ (a^c))*x ^ (a^c))*x ^ a;
+//       - other codes with d <= 8 and all reconstructions use run-time coefficient programs (one per erasure
+//         pattern, built on the host at coder creation): per bit level one packed xtime of the accumulator and one
+//         lop3 per source.  d > 8 falls back to the bit-plane form (sources expanded into byte masks).
+//   * kernels, by geometry:
+//       rs32_encode_row_kernel            uniform codewords up to 256 columns, 16-byte-aligned stride: a CTA walks
+//                                         codewords, thread = column, kernel-uniform funnel, masked tail handled by
+//                                         whichever warp has the last column block this iteration (rotating), the
+//                                         fused tally as a coalesced prologue, optional stores into peer GPUs
+//       rs32_encode_uniform_kernel        any uniform geometry: flat thread <-> column index, general masked loads
+//       rs32_encode_ragged_kernel         ragged batches: a warp per codeword, two columns per lane on long ones
+//       rs32_crossword_distribute_kernel  ragged encode + per-replica shard placement (config 4)
+//       horner_* / generic_*              other codes; rs_reconstruct_small_kernel / horner_reconstruct_kernel
 #include <cstring>
 
 #include "device_common.cuh"
