@@ -45,6 +45,7 @@ def parse_args():
     ap.add_argument("--workload", default="cfg3", choices=["cfg3", "cfg2", "cfg5", "cfg3b", "cfg4"])
     ap.add_argument("--groups", type=int, default=G_PER_GPU, help="groups per GPU")
     ap.add_argument("--variant", type=int, default=0, help="encode kernel variant (tuning)")
+    ap.add_argument("--replicas", type=int, default=5, help="cfg3 variant: population n (RS(majority, n-majority), f=(n//2)//2)")
     ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"], help="N>1: how shard planes reach the simulated peers")
     ap.add_argument("--no-tally", action="store_true", help="tuning: time the encode alone")
     ap.add_argument("--no-e2e", action="store_true")
@@ -203,7 +204,7 @@ def run_reference(args):
 
 def config_dict(args, world):
     L = (DATA_LEN + D - 1) // D
-    return {"workload": {"cfg3": "cfg3: RSPaxos (3,5) fused RS(3,2) encode + quorum tally (4 of 5), 2^20 groups x 4096 B "
+    return {"workload": {"cfg3": f"cfg3: RSPaxos ({D},{R}) fused RS({D},{P}) encode + quorum tally ({THRESH_RSPAXOS} of {R}), 2^20 groups x 4096 B "
                                  "request batch + 64-slot ack window per GPU",
                          "cfg2": "cfg2: MultiPaxos 5-replica quorum tally (3 of 5), 2^20 groups x 64 slots per GPU",
                          "cfg5": "cfg5: Raft 7-replica match-index commit scan, 2^22 groups, 64-slot term window"}[args.workload],
@@ -750,7 +751,14 @@ def run_cfg4(args, ctx, rs, dev, world, rank, peak, peak_src):
 
 
 def main():
+    global D, P, R, THRESH_RSPAXOS, THRESH_MULTIPAXOS
     args = parse_args()
+    if args.replicas != 5:      # scripts/local_cluster.py:41-50 defaults: fault_tolerance = (n//2)//2
+        R = args.replicas
+        D = R // 2 + 1
+        P = R - D
+        THRESH_MULTIPAXOS = D
+        THRESH_RSPAXOS = D + (R // 2) // 2
     if args.impl == "reference":
         run_reference(args)
     else:
