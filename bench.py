@@ -138,7 +138,9 @@ class ClockSampler:
 def cpu_arm(steps: int, warmup: int, sample_cw: int, workload: str):
     from oracle import pyoracle as oracle
     from summerset_b200 import workloads as wl
-    threads = oracle.max_threads()
+    # hardware threads this process may run on -- NOT omp_get_max_threads(): torchrun exports OMP_NUM_THREADS=1
+    hw_threads = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    threads = hw_threads
     mode = 1 if oracle.have_avx2() else 0
     L = oracle.cw_shard_len(DATA_LEN, D)
     ds = (L + 15) // 16 * 16
@@ -158,7 +160,7 @@ def cpu_arm(steps: int, warmup: int, sample_cw: int, workload: str):
     # threads for this memory-bound loop, so the thread count is calibrated (best of max, max/2, max/4) and stated.
     step()
     best = None
-    for cand in sorted({oracle.max_threads(), max(1, oracle.max_threads() // 2), max(1, oracle.max_threads() // 4)}):
+    for cand in sorted({hw_threads, max(1, hw_threads // 2), max(1, hw_threads // 4)}):
         threads = cand
         t0 = time.perf_counter(); step(); dtc = time.perf_counter() - t0
         if best is None or dtc < best[0]:
