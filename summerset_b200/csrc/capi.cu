@@ -413,6 +413,19 @@ int ss_rs_coder_create(ss_ctx *ctx, int d, int p, ss_rs_coder **out) {
         build_encode_program(M, d, p, buf.data());
         cudaError_t e = cudaMalloc(&c->enc_prog, buf.size());
         if (e == cudaSuccess) e = cudaMemcpy(c->enc_prog, buf.data(), buf.size(), cudaMemcpyHostToDevice);
+        c->static_code = ssb::match_static_code(d, p, c->matrix.data());
+        if (e == cudaSuccess && d <= 8) {
+            std::vector<uint32_t> t8(size_t(p) * 8 * 8, 0u);
+            for (int j = 0; j < p; ++j) {
+                int top = 0;
+                for (int i = 0; i < d; ++i)
+                    for (int k = 0; k < 8; ++k)
+                        if ((M.at(d + j, i) >> k) & 1) { t8[(size_t(j) * 8 + k) * 8 + i] = 0xffffffffu; if (k > top) top = k; }
+                c->enc_top[j] = static_cast<uint8_t>(top);
+            }
+            e = cudaMalloc(&c->enc_hmT8, t8.size() * 4);
+            if (e == cudaSuccess) e = cudaMemcpy(c->enc_hmT8, t8.data(), t8.size() * 4, cudaMemcpyHostToDevice);
+        }
         if (e != cudaSuccess) { ss_rs_coder_destroy(c); return cuda_error(e, "upload encode program", __FILE__, __LINE__); }
     }
     if (c->dec_ok) {
@@ -463,6 +476,7 @@ int ss_rs_coder_destroy(ss_rs_coder *c) {
         cudaStreamSynchronize(c->ctx->stream);
     }
     if (c->enc_prog) cudaFree(c->enc_prog);
+    if (c->enc_hmT8) cudaFree(c->enc_hmT8);
     if (c->dec_progs) cudaFree(c->dec_progs);
     if (c->dec_progs_data) cudaFree(c->dec_progs_data);
     if (c->fast_progs) cudaFree(c->fast_progs);

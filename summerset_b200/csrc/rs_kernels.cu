@@ -788,6 +788,210 @@ horner_encode_ragged_kernel(const __grid_constant__ EncRagged E, const uint32_t 
     }
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// Generic "row" encode kernel for any code with d <= 8 (RS(2,1), RS(4,3), RS(5,4), RS(6,4) ...): the structure of
+// rs32_encode_row_kernel -- a CTA walks codewords, thread = column, kernel-uniform byte funnels, rotating block
+// assignment, coalesced tally prologue -- with the parity rows evaluated by run-time Horner programs.
+// hmT8[(j*8 + k)*8 + i] = all-ones if bit k of coefficient M[d+j][i] is set.
+// ------------------------------------------------------------------------------------------------
+struct EncRowGen {
+    const uint8_t *data;
+    uint64_t data_stride;
+    uint8_t *parity;
+    uint64_t plane_stride, shard_stride;
+    uint32_t n, len, L, vpc, fast_cols;
+    uint32_t d, p;
+    const uint32_t *hmT8;
+    uint8_t top[kMaxP];
+    const uint64_t *planes;   // fused tally (nullptr: none); G == n
+    uint32_t R, threshold;
+    uint64_t *committed;
+    uint32_t *commit_bar;
+};
+
+// The codes Summerset's protocols actually build are ReedSolomon::new(majority, population - majority)
+// (rspaxos/mod.rs:597-609, crossword/mod.rs:742-750): population 3 -> RS(2,1), 5 -> RS(3,2), 7 -> RS(4,3), 9 -> RS(5,4)
+// (4 -> RS(3,1), 6 -> RS(4,2)).  For those the parity rows are compile-time constants, so the Horner evaluation is
+// fully unrolled and only the set coefficient bits cost an instruction.  The coder only selects a static code when its
+// run-time matrix (built by gf256.hpp exactly as the crate builds it) equals the table below byte for byte.
+enum : int { kCodeGeneric = -1, kCode21 = 0, kCode43 = 1, kCode54 = 2, kCode42 = 3, kCode31 = 4, kNumStaticCodes = 5 };
+__host__ __device__ constexpr int static_code_d(int code) {
+    return code == kCode21 ? 2 : code == kCode43 ? 4 : code == kCode54 ? 5 : code == kCode42 ? 4 : code == kCode31 ? 3 : 0;
+}
+__host__ __device__ constexpr int static_code_p(int code) {
+    return code == kCode21 ? 1 : code == kCode43 ? 3 : code == kCode54 ? 4 : code == kCode42 ? 2 : code == kCode31 ? 1 : 0;
+}
+__host__ __device__ constexpr uint32_t static_code_coef(int code, int j, int i) {
+    if (code == kCode21) return i == 0 ? 0x03u : 0x02u;
+    if (code == kCode31) return 0x01u;
+    if (code == kCode43 || code == kCode42) {
+        switch (j * 4 + i) {
+            case 0: return 0x1bu; case 1: return 0x1cu; case 2: return 0x12u; case 3: return 0x14u;
+            case 4: return 0x1cu; case 5: return 0x1bu; case 6: return 0x14u; case 7: return 0x12u;
+            case 8: return 0x12u; case 9: return 0x14u; case 10: return 0x1bu; default: return 0x1cu;
+        }
+    }
+    switch (j * 5 + i) {   // kCode54
+        case 0: return 0x07u; case 1: return 0x07u; case 2: return 0x06u; case 3: return 0x06u; case 4: return 0x01u;
+        case 5: return 0x09u; case 6: return 0x08u; case 7: return 0x09u; case 8: return 0x08u; case 9: return 0x01u;
+        case 10: return 0x0fu; case 11: return 0x0eu; case 12: return 0x0eu; case 13: return 0x0fu; case 14: return 0x01u;
+        case 15: return 0x02u; case 16: return 0x7du; case 17: return 0x95u; case 18: return 0xfdu; default: return 0x16u;
+    }
+}
+__host__ __device__ constexpr int static_code_top(int code, int j) {
+    uint32_t any = 0;
+    for (int i = 0; i < static_code_d(code); ++i) any |= static_code_coef(code, j, i);
+    int top = 0;
+    for (int k = 0; k < 8; ++k)
+        if ((any >> k) & 1u) top = k;
+    return top;
+}
+
+// multiply four packed field elements by x.  XT == 0: prmt sign mask (3 alu-pipe + 1 fma-pipe instruction);
+// XT == 1: the reduction term comes from a high multiply, (x & 0x80..) * 0x1d >> 7, and the carries are removed by a
+// multiply-add (1 alu-pipe + 3 fma-pipe; the closing XOR folds into the LOP3 of the next accumulate).
+template <int XT>
+__device__ __forceinline__ uint32_t xtime_word(uint32_t x) {
+    if constexpr (XT == 0) {
+        return ((x * 2u) & 0xfefefefeu) ^ (msb_mask(x) & 0x1d1d1d1du);
+    } else {
+        const uint32_t h = x & 0x80808080u;
+        const uint32_t r = __umulhi(h, 0x3a000000u);        // (h * 0x1d) >> 7: 0x1d in every byte whose top bit was set
+        uint32_t t;
+        asm("mad.lo.u32 %0, %1, 0xfffffffe, %2;" : "=r"(t) : "r"(h), "r"(x + x));   // 2x - 2h: carried-out bits removed
+        return t ^ r;
+    }
+}
+
+// the d source vectors of column k of one codeword, funnelled to shard alignment and masked to the payload
+template <int D, bool MASKED>
+__device__ __forceinline__ int row_load_column(const EncRowGen &P, const uint8_t *__restrict__ src, uint32_t k, uint4 (&x)[D]) {
+    auto clamp16 = [](int64_t r) { return r > 16 ? 16 : (r < 0 ? 0 : static_cast<int>(r)); };
+    const int d = static_cast<int>(P.d);
+    uint4 lo[D], hi[D];
+#pragma unroll
+    for (int i = 0; i < D; ++i) {
+        lo[i] = make_uint4(0u, 0u, 0u, 0u);
+        hi[i] = lo[i];
+        if (i < d) {
+            const uint32_t pos = static_cast<uint32_t>(i) * P.L + k;
+            const uint32_t s = (static_cast<uint32_t>(i) * P.L) & 15u;      // kernel-uniform (k is a multiple of 16)
+            const int nv = MASKED ? clamp16(static_cast<int64_t>(P.len) - pos) : 16;
+            if (!MASKED || nv > 0) lo[i] = dev::ldg128(src + pos - s);
+            hi[i] = lo[i];
+            if (s != 0u && (!MASKED || static_cast<int>(s) + nv > 16)) hi[i] = dev::ldg128(src + pos - s + 16u);
+        }
+    }
+    const int onv = MASKED ? clamp16(static_cast<int64_t>(P.L) - k) : 16;
+#pragma unroll
+    for (int i = 0; i < D; ++i) {
+        x[i] = lo[i];
+        if (i < d) {
+            const uint32_t s = (static_cast<uint32_t>(i) * P.L) & 15u;
+            if (s != 0u) x[i] = funnel16(lo[i], hi[i], s);
+            if (MASKED) {
+                const int nv = clamp16(static_cast<int64_t>(P.len) - (static_cast<uint32_t>(i) * P.L + k));
+                x[i] = keep_bytes(x[i], nv < onv ? nv : onv);
+            }
+        }
+    }
+    return onv;
+}
+
+template <int D, int CODE, int XT, bool MASKED>
+__device__ __forceinline__ void horner_row_column(const EncRowGen &P, const uint8_t *__restrict__ src, uint8_t *__restrict__ out,
+                                                  uint32_t k) {
+    uint4 x[D];
+    const int onv = row_load_column<D, MASKED>(P, src, k, x);
+    if constexpr (CODE != kCodeGeneric) {
+        static_assert(D == static_code_d(CODE), "static code width");
+#pragma unroll
+        for (int j = 0; j < static_code_p(CODE); ++j) {
+            const int top = static_code_top(CODE, j);
+            uint4 acc = make_uint4(0u, 0u, 0u, 0u);
+#pragma unroll
+            for (int kk = 7; kk >= 0; --kk) {
+                if (kk > top) continue;
+                if (kk != top) {
+                    acc.x = xtime_word<XT>(acc.x); acc.y = xtime_word<XT>(acc.y);
+                    acc.z = xtime_word<XT>(acc.z); acc.w = xtime_word<XT>(acc.w);
+                }
+#pragma unroll
+                for (int i = 0; i < D; ++i)
+                    if ((static_code_coef(CODE, j, i) >> kk) & 1u) {
+                        acc.x ^= x[i].x; acc.y ^= x[i].y; acc.z ^= x[i].z; acc.w ^= x[i].w;
+                    }
+            }
+            if (MASKED) acc = keep_bytes(acc, onv);
+            dev::stg128_cs(out + static_cast<uint64_t>(j) * P.plane_stride + k, acc);
+        }
+    } else {
+        for (uint32_t j = 0; j < P.p; ++j) {
+            const uint4 *hm = reinterpret_cast<const uint4 *>(P.hmT8 + j * 64u);
+            uint4 acc = make_uint4(0u, 0u, 0u, 0u);
+            const int top = P.top[j];
+            for (int kk = top; kk >= 0; --kk) {
+                const uint4 m0 = __ldg(hm + kk * 2);
+                const uint4 m1 = D > 4 ? __ldg(hm + kk * 2 + 1) : make_uint4(0u, 0u, 0u, 0u);
+                const uint32_t mk[8] = {m0.x, m0.y, m0.z, m0.w, m1.x, m1.y, m1.z, m1.w};
+                if (kk != top) {
+                    acc.x = xtime_word<0>(acc.x); acc.y = xtime_word<0>(acc.y);
+                    acc.z = xtime_word<0>(acc.z); acc.w = xtime_word<0>(acc.w);
+                }
+#pragma unroll
+                for (int i = 0; i < D; ++i) {
+                    acc.x ^= x[i].x & mk[i];
+                    acc.y ^= x[i].y & mk[i];
+                    acc.z ^= x[i].z & mk[i];
+                    acc.w ^= x[i].w & mk[i];
+                }
+            }
+            if (MASKED) acc = keep_bytes(acc, onv);
+            dev::stg128_cs(out + static_cast<uint64_t>(j) * P.plane_stride + k, acc);
+        }
+    }
+}
+
+template <int D, int CODE, int XT, int MAXT, int MINB>
+__global__ void __launch_bounds__(MAXT, MINB) horner_encode_row_kernel(const __grid_constant__ EncRowGen P) {
+    const uint32_t lane = threadIdx.x & 31u, wid = threadIdx.x >> 5, nblk = blockDim.x >> 5;
+    if (P.planes != nullptr) {
+        const uint32_t per = (P.n + gridDim.x - 1) / gridDim.x;
+        const uint32_t lo = blockIdx.x * per;
+        const uint32_t hi = lo + per < P.n ? lo + per : P.n;
+        for (uint32_t g = lo + threadIdx.x; g < hi; g += blockDim.x) {
+            const uint64_t w = dev::tally_word(P.planes, P.R, P.n, g, P.threshold);
+            P.committed[g] = w;
+            if (P.commit_bar != nullptr) P.commit_bar[g] = dev::commit_prefix(w);
+        }
+    }
+    uint32_t wb = wid;
+#pragma unroll 1
+    for (uint32_t g = blockIdx.x; g < P.n; g += gridDim.x) {
+        const uint32_t v = wb * 32u + lane;
+        const bool masked = wb * 32u + 32u > P.fast_cols;           // warp-uniform
+        wb = (wb + 1u == nblk) ? 0u : wb + 1u;                       // rotate the warp -> block assignment
+        if (v >= P.vpc) continue;
+        const uint8_t *src = P.data + static_cast<uint64_t>(g) * P.data_stride;
+        uint8_t *out = P.parity + static_cast<uint64_t>(g) * P.shard_stride;
+        if (!masked) horner_row_column<D, CODE, XT, false>(P, src, out, v * 16u);
+        else horner_row_column<D, CODE, XT, true>(P, src, out, v * 16u);
+    }
+}
+
+int match_static_code(int d, int p, const uint8_t *matrix) {
+    for (int c = 0; c < kNumStaticCodes; ++c) {
+        if (static_code_d(c) != d || static_code_p(c) != p) continue;
+        bool same = true;
+        for (int j = 0; j < p && same; ++j)
+            for (int i = 0; i < d; ++i)
+                if (matrix[static_cast<size_t>(d + j) * d + i] != static_code_coef(c, j, i)) { same = false; break; }
+        if (same) return c;
+    }
+    return -1;
+}
+
 // smallest instantiated register capacity >= d (0: use the bit-plane kernels)
 template <typename F>
 static int dispatch_d(int d, F &&f) {
@@ -1045,6 +1249,69 @@ int launch_rs_encode(ss_rs_coder *coder, const EncGeom &g, const TallyArgs *tall
             else if (vr == 7) rs32_encode_row_kernel<false, 128, 9><<<grid, threads, 0, st>>>(Rw);    // 56 regs cap
             else rs32_encode_row_kernel<false, 128, 12><<<grid, threads, 0, st>>>(Rw);                // 40 regs
             coder->last_kernel = Rw.planes ? "rs32_encode_row_kernel+tally" : "rs32_encode_row_kernel";
+            SS_CUDA(cudaGetLastError());
+            ctx->launches++;
+            return SS_OK;
+        }
+
+        // ---- generic row kernel: any code with d <= 8, aligned uniform geometry, codewords up to 256 columns ----
+        if (!use_rs32 && d <= 8 && coder->enc_hmT8 != nullptr && (coder->variant & 15) != 5 && (coder->variant & 15) != 1 &&
+            padded && !(g.flags & SS_RS_EMIT_DATA) && vpc >= 1 && vpc <= 256 && g.n <= 0xffffffffull &&
+            ((reinterpret_cast<uintptr_t>(g.data) | g.data_stride) & 15u) == 0u &&
+            (tally == nullptr || tally->planes == nullptr || tally->G == g.n)) {
+            EncRowGen Rg;
+            Rg.data = g.data; Rg.data_stride = g.data_stride; Rg.parity = g.parity; Rg.plane_stride = g.plane_stride;
+            Rg.shard_stride = g.shard_stride; Rg.n = static_cast<uint32_t>(g.n); Rg.len = len; Rg.L = L; Rg.vpc = vpc;
+            // columns whose every source window lies inside the payload and whose output vector is complete
+            const uint64_t last_shard_bytes = static_cast<uint64_t>(len) >= static_cast<uint64_t>(d - 1) * L
+                                                  ? static_cast<uint64_t>(len) - static_cast<uint64_t>(d - 1) * L : 0;
+            Rg.fast_cols = static_cast<uint32_t>((last_shard_bytes < L ? last_shard_bytes : L) / 16u);
+            Rg.d = static_cast<uint32_t>(d); Rg.p = static_cast<uint32_t>(p);
+            Rg.hmT8 = static_cast<const uint32_t *>(coder->enc_hmT8);
+            for (int j = 0; j < kMaxP; ++j) Rg.top[j] = coder->enc_top[j];
+            Rg.planes = nullptr; Rg.R = 0; Rg.threshold = 0; Rg.committed = nullptr; Rg.commit_bar = nullptr;
+            if (tally != nullptr && tally->planes != nullptr) {
+                Rg.planes = tally->planes; Rg.R = tally->R; Rg.threshold = tally->threshold;
+                Rg.committed = tally->committed; Rg.commit_bar = tally->commit_bar;
+            }
+            const uint32_t threads = (vpc + 31u) & ~31u;
+            uint32_t per_sm = 2048u / threads; if (per_sm > 32u) per_sm = 32u;
+            uint64_t ctas = static_cast<uint64_t>(ctx->sm_count) * per_sm * 64ull;
+            if (ctas > g.n) ctas = g.n;
+            const uint32_t grid = static_cast<uint32_t>(ctas);
+            const int sc = ((coder->variant >> 11) & 1) ? kCodeGeneric : coder->static_code;   // bit 11: run-time masks
+            const int xt = (coder->variant >> 12) & 1;                                          // bit 12: multiply-based xtime
+            // register budget (variant bits 0-3): threads <= 128: 0 = 12 CTAs/SM (40 regs), 2 = 10 (48), 3 = 8 (64), 4 = 6 (80)
+            const int vb = coder->variant & 15;
+            auto go = [&](auto DC, auto CC, auto XC) {
+                constexpr int kD = decltype(DC)::value, kC = decltype(CC)::value, kX = decltype(XC)::value;
+                if (threads > 128) horner_encode_row_kernel<kD, kC, kX, 256, 3><<<grid, threads, 0, st>>>(Rg);
+                else if (vb == 2) horner_encode_row_kernel<kD, kC, kX, 128, 10><<<grid, threads, 0, st>>>(Rg);
+                else if (vb == 3) horner_encode_row_kernel<kD, kC, kX, 128, 8><<<grid, threads, 0, st>>>(Rg);
+                else if (vb == 4) horner_encode_row_kernel<kD, kC, kX, 128, 6><<<grid, threads, 0, st>>>(Rg);
+                else horner_encode_row_kernel<kD, kC, kX, 128, 12><<<grid, threads, 0, st>>>(Rg);
+            };
+            auto go_static = [&](auto CC) {
+                constexpr int C = decltype(CC)::value;
+                if (xt) go(std::integral_constant<int, static_code_d(C)>{}, CC, std::integral_constant<int, 1>{});
+                else go(std::integral_constant<int, static_code_d(C)>{}, CC, std::integral_constant<int, 0>{});
+            };
+            switch (sc) {
+                case kCode21: go_static(std::integral_constant<int, kCode21>{}); break;
+                case kCode43: go_static(std::integral_constant<int, kCode43>{}); break;
+                case kCode54: go_static(std::integral_constant<int, kCode54>{}); break;
+                case kCode42: go_static(std::integral_constant<int, kCode42>{}); break;
+                case kCode31: go_static(std::integral_constant<int, kCode31>{}); break;
+                default:
+                    SS_TRY(dispatch_d(d, [&](auto DC) {
+                        go(DC, std::integral_constant<int, kCodeGeneric>{}, std::integral_constant<int, 0>{});
+                        return SS_OK;
+                    }));
+            }
+            if (sc != kCodeGeneric)
+                coder->last_kernel = Rg.planes ? "horner_encode_row_kernel<static code>+tally" : "horner_encode_row_kernel<static code>";
+            else
+                coder->last_kernel = Rg.planes ? "horner_encode_row_kernel+tally" : "horner_encode_row_kernel";
             SS_CUDA(cudaGetLastError());
             ctx->launches++;
             return SS_OK;

@@ -91,6 +91,9 @@ struct ss_rs_coder {
     const char *last_kernel = "none";
     // device tables
     void *enc_prog = nullptr;         // ProgHeader + splats for encode
+    void *enc_hmT8 = nullptr;         // d <= 8: encode masks transposed, hmT8[(j*8 + k)*8 + i] (row kernel)
+    uint8_t enc_top[ssb::kMaxP] = {};
+    int static_code = -1;             // index of the compile-time specialised cluster code equal to this matrix, or -1      // Horner start bit of every parity row
     void *dec_progs = nullptr;        // one program per present-pattern (2^(d+p) of them), or null
     void *dec_progs_data = nullptr;   // same, data_only flavour
     void *fast_progs = nullptr;       // d <= 4: compact programs (FastProgHeader + hmT rows), all patterns
@@ -133,6 +136,8 @@ struct TallyArgs {              // optional fused tally
 };
 
 int launch_rs_encode(ss_rs_coder *coder, const EncGeom &g, const TallyArgs *tally);
+// index of the compile-time specialised code whose parity rows equal matrix[(d..d+p) x d], or -1
+int match_static_code(int d, int p, const uint8_t *matrix);
 int launch_rs_reconstruct(ss_rs_coder *coder, uint8_t *shards, uint64_t plane_stride,
                           const uint64_t *off, const uint32_t *data_len, const uint32_t *present,
                           uint64_t n, int data_only, int32_t *status, uint32_t flags);

@@ -368,6 +368,46 @@ def test_accept_step_fused(ctx, oracle):
     assert (bar.cpu().numpy().view(np.uint32) == b_want).all()
 
 
+@pytest.mark.parametrize("d,p,data_len,n", [(4, 3, 4096, 3000), (5, 4, 4096, 2000), (2, 1, 777, 1000), (6, 4, 4090, 500),
+                                            (8, 8, 1, 100), (4, 3, 100, 400000), (7, 2, 16 * 7 * 3, 900), (4, 2, 5000, 300), (3, 1, 3333, 300),
+                                            (5, 4, 64, 1000), (2, 1, 4096, 1000)])
+def test_generic_row_kernel_fused_step(ctx, oracle, d, p, data_len, n):
+    """the d <= 8 Horner row kernel: fused step with the tally, grid-stride wrap (n > resident CTAs x waves), ragged tails"""
+    rs = ReedSolomon(ctx, d, p)
+    data = wl.payload_uniform(n, data_len, seed_extra=d * 31 + p)
+    R = d + p
+    planes = wl.cfg2_planes(n, R, 0.8, seed_extra=d)
+    L, ds, ps = rs.parity_layout(data_len, n)
+    par = torch.full((p, n, ds), 0x5a, dtype=torch.uint8, device=DEV)
+    committed = torch.empty(n, dtype=torch.int64, device=DEV)
+    bar = torch.empty(n, dtype=torch.int32, device=DEV)
+    thr = R // 2 + 1
+    before = ctx.launches
+    rs.accept_step_fused(torch.from_numpy(data).to(DEV), data_len, par, torch.from_numpy(planes.view(np.int64)).to(DEV),
+                         thr, committed, bar)
+    torch.cuda.synchronize()
+    assert ctx.launches == before + 1
+    static = (d, p) in [(2, 1), (4, 3), (5, 4), (4, 2), (3, 1)]      # population 3/7/9/6/4 cluster codes
+    assert rs.last_kernel() == ("horner_encode_row_kernel<static code>+tally" if static else "horner_encode_row_kernel+tally")
+    want = oracle.rs_encode_uniform(d, p, data, data_len)
+    assert (par.cpu().numpy() == want).all()
+    for v in (1 << 11, 1 << 12):                  # run-time mask flavour; multiply-based xtime flavour
+        rs.set_variant(v)
+        par3 = rs.encode_uniform(torch.from_numpy(data).to(DEV), data_len)
+        torch.cuda.synchronize()
+        assert rs.last_kernel() == ("horner_encode_row_kernel" if v == 1 << 11 or not static else "horner_encode_row_kernel<static code>")
+        assert (par3.cpu().numpy() == want).all(), v
+    c_want, b_want = oracle.tally_planes(planes, thr)
+    assert (committed.cpu().numpy().view(np.uint64) == c_want).all()
+    assert (bar.cpu().numpy().view(np.uint32) == b_want).all()
+    # the flat kernel (variant 1) gives the same bytes
+    rs.set_variant(1)
+    par2 = rs.encode_uniform(torch.from_numpy(data).to(DEV), data_len)
+    torch.cuda.synchronize()
+    assert rs.last_kernel().startswith("horner_encode_uniform")
+    assert torch.equal(par2, par)
+
+
 def test_encode_uniform_host_buffers(ctx, oracle):
     for d, p, data_len, n in [(3, 2, 4096, 40000), (4, 3, 1000, 5000)]:
         rs = ReedSolomon(ctx, d, p)
