@@ -216,15 +216,17 @@ __device__ __forceinline__ void rs32_row_column(const uint8_t *__restrict__ src,
     // offsets from src.  Loads first (pairs adjacent so the second one hits the sectors the first just
     // brought into L1), then the byte funnels.
     const uint4 a0 = dev::ldg128(src + k);
-    uint4 a1 = a0;
+    // the second-load registers start as zeros, never as a copy of the first load: a copy would be issued right
+    // behind the load and stall every later load of this column until that one has landed
+    uint4 a1 = make_uint4(0u, 0u, 0u, 0u);
     if (s0 != 0u && (!MASKED || static_cast<int>(s0) + nva > 16)) a1 = dev::ldg128(src + k + 16u);
     uint4 b0 = make_uint4(0u, 0u, 0u, 0u);
     if (!MASKED || nvb > 0) b0 = dev::ldg128(src + o1);   // a window entirely in the zero padding is never read
-    uint4 b1 = b0;
+    uint4 b1 = make_uint4(0u, 0u, 0u, 0u);
     if (s1 != 0u && (!MASKED || static_cast<int>(s1) + nvb > 16)) b1 = dev::ldg128(src + o1 + 16u);
     uint4 c0 = make_uint4(0u, 0u, 0u, 0u);
     if (!MASKED || nvc > 0) c0 = dev::ldg128(src + o2);
-    uint4 c1 = c0;
+    uint4 c1 = make_uint4(0u, 0u, 0u, 0u);
     if (s2 != 0u && (!MASKED || static_cast<int>(s2) + nvc > 16)) c1 = dev::ldg128(src + o2 + 16u);
     uint4 a = s0 != 0u ? funnel16(a0, a1, s0) : a0;
     uint4 b = s1 != 0u ? funnel16(b0, b1, s1) : b0;
@@ -261,13 +263,13 @@ __device__ __forceinline__ void rs32_row_pair(const uint8_t *__restrict__ src, u
                                               uint32_t o1, uint32_t o2, uint32_t s0, uint32_t s1, uint32_t s2) {
     const uint32_t D2 = 512u;
     const uint4 a0 = dev::ldg128(src + k), A0 = dev::ldg128(src + k + D2);
-    uint4 a1 = a0, A1 = A0;
+    uint4 a1 = make_uint4(0u, 0u, 0u, 0u), A1 = a1;      // zeros, not copies of the loads (see rs32_row_column)
     if (s0 != 0u) { a1 = dev::ldg128(src + k + 16u); A1 = dev::ldg128(src + k + D2 + 16u); }
     const uint4 b0 = dev::ldg128(src + o1), B0 = dev::ldg128(src + o1 + D2);
-    uint4 b1 = b0, B1 = B0;
+    uint4 b1 = make_uint4(0u, 0u, 0u, 0u), B1 = b1;
     if (s1 != 0u) { b1 = dev::ldg128(src + o1 + 16u); B1 = dev::ldg128(src + o1 + D2 + 16u); }
     const uint4 c0 = dev::ldg128(src + o2), C0 = dev::ldg128(src + o2 + D2);
-    uint4 c1 = c0, C1 = C0;
+    uint4 c1 = make_uint4(0u, 0u, 0u, 0u), C1 = c1;
     if (s2 != 0u) { c1 = dev::ldg128(src + o2 + 16u); C1 = dev::ldg128(src + o2 + D2 + 16u); }
     {
         const uint4 a = s0 != 0u ? funnel16(a0, a1, s0) : a0;
@@ -802,6 +804,7 @@ struct EncRowGen {
     uint64_t plane_stride, shard_stride;
     uint32_t n, len, L, vpc, fast_cols;
     uint32_t d, p;
+    uint32_t pack_m, tail_ctas, ntail;   // packed kernel: codewords per CTA pass, CTAs that do tail columns, tail columns per codeword
     const uint32_t *hmT8;
     uint8_t top[kMaxP];
     const uint64_t *planes;   // fused tally (nullptr: none); G == n
@@ -865,10 +868,10 @@ __device__ __forceinline__ uint32_t xtime_word(uint32_t x) {
 }
 
 // the d source vectors of column k of one codeword, funnelled to shard alignment and masked to the payload
-template <int D, bool MASKED>
+template <int D, bool MASKED, bool EXACT>
 __device__ __forceinline__ int row_load_column(const EncRowGen &P, const uint8_t *__restrict__ src, uint32_t k, uint4 (&x)[D]) {
     auto clamp16 = [](int64_t r) { return r > 16 ? 16 : (r < 0 ? 0 : static_cast<int>(r)); };
-    const int d = static_cast<int>(P.d);
+    const int d = EXACT ? D : static_cast<int>(P.d);            // EXACT: the code's width is the template's
     uint4 lo[D], hi[D];
 #pragma unroll
     for (int i = 0; i < D; ++i) {
@@ -879,7 +882,7 @@ __device__ __forceinline__ int row_load_column(const EncRowGen &P, const uint8_t
             const uint32_t s = (static_cast<uint32_t>(i) * P.L) & 15u;      // kernel-uniform (k is a multiple of 16)
             const int nv = MASKED ? clamp16(static_cast<int64_t>(P.len) - pos) : 16;
             if (!MASKED || nv > 0) lo[i] = dev::ldg128(src + pos - s);
-            hi[i] = lo[i];
+            // hi stays zero when unused: copying lo here would make every later load wait for this one to land
             if (s != 0u && (!MASKED || static_cast<int>(s) + nv > 16)) hi[i] = dev::ldg128(src + pos - s + 16u);
         }
     }
@@ -899,11 +902,9 @@ __device__ __forceinline__ int row_load_column(const EncRowGen &P, const uint8_t
     return onv;
 }
 
+// the p parity vectors of one column from its d source vectors x[], stored at out + j*plane_stride + k
 template <int D, int CODE, int XT, bool MASKED>
-__device__ __forceinline__ void horner_row_column(const EncRowGen &P, const uint8_t *__restrict__ src, uint8_t *__restrict__ out,
-                                                  uint32_t k) {
-    uint4 x[D];
-    const int onv = row_load_column<D, MASKED>(P, src, k, x);
+__device__ __forceinline__ void parity_rows(const EncRowGen &P, const uint4 (&x)[D], int onv, uint8_t *__restrict__ out, uint32_t k) {
     if constexpr (CODE != kCodeGeneric) {
         static_assert(D == static_code_d(CODE), "static code width");
 #pragma unroll
@@ -953,6 +954,57 @@ __device__ __forceinline__ void horner_row_column(const EncRowGen &P, const uint
     }
 }
 
+template <int D, int CODE, int XT, bool MASKED>
+__device__ __forceinline__ void horner_row_column(const EncRowGen &P, const uint8_t *__restrict__ src, uint8_t *__restrict__ out,
+                                                  uint32_t k) {
+    uint4 x[D];
+    const int onv = row_load_column<D, MASKED, CODE != kCodeGeneric>(P, src, k, x);
+    parity_rows<D, CODE, XT, MASKED>(P, x, onv, out, k);
+}
+
+// Split load for the software-pipelined packed kernel (complete columns only): issue the aligned 128-bit loads of one
+// column into raw registers, and later funnel them to shard alignment.  Shard 0 always starts 16-byte aligned; with
+// ALIGNED (shard_len % 16 == 0) every shard does and no second load exists.
+template <int D, bool ALIGNED>
+struct RawColumn {
+    uint4 lo[D];
+    uint4 hi[ALIGNED ? 1 : D];
+};
+template <int D, bool ALIGNED, bool EXACT>
+__device__ __forceinline__ void raw_issue(const EncRowGen &P, const uint8_t *__restrict__ src, uint32_t k, RawColumn<D, ALIGNED> &r) {
+    const int d = EXACT ? D : static_cast<int>(P.d);
+#pragma unroll
+    for (int i = 0; i < D; ++i) {
+        if (i < d) {
+            const uint32_t pos = static_cast<uint32_t>(i) * P.L + k;
+            const uint32_t s = ALIGNED ? 0u : (static_cast<uint32_t>(i) * P.L) & 15u;
+            r.lo[i] = dev::ldg128(src + pos - s);
+            if constexpr (!ALIGNED) {
+                if (i > 0) {
+                    r.hi[i] = make_uint4(0u, 0u, 0u, 0u);       // never a copy of lo: that would wait for the load
+                    if (s != 0u) r.hi[i] = dev::ldg128(src + pos - s + 16u);
+                }
+            }
+        } else {
+            r.lo[i] = make_uint4(0u, 0u, 0u, 0u);
+        }
+    }
+}
+template <int D, bool ALIGNED, bool EXACT>
+__device__ __forceinline__ void raw_finish(const EncRowGen &P, const RawColumn<D, ALIGNED> &r, uint4 (&x)[D]) {
+    const int d = EXACT ? D : static_cast<int>(P.d);
+#pragma unroll
+    for (int i = 0; i < D; ++i) {
+        x[i] = r.lo[i];
+        if constexpr (!ALIGNED) {
+            if (i > 0 && i < d) {
+                const uint32_t s = (static_cast<uint32_t>(i) * P.L) & 15u;
+                if (s != 0u) x[i] = funnel16(r.lo[i], r.hi[i], s);
+            }
+        }
+    }
+}
+
 template <int D, int CODE, int XT, int MAXT, int MINB>
 __global__ void __launch_bounds__(MAXT, MINB) horner_encode_row_kernel(const __grid_constant__ EncRowGen P) {
     const uint32_t lane = threadIdx.x & 31u, wid = threadIdx.x >> 5, nblk = blockDim.x >> 5;
@@ -977,6 +1029,68 @@ __global__ void __launch_bounds__(MAXT, MINB) horner_encode_row_kernel(const __g
         uint8_t *out = P.parity + static_cast<uint64_t>(g) * P.shard_stride;
         if (!masked) horner_row_column<D, CODE, XT, false>(P, src, out, v * 16u);
         else horner_row_column<D, CODE, XT, true>(P, src, out, v * 16u);
+    }
+}
+
+// Packed flavour of the row kernel, for shard lengths whose column count is not a multiple of 32.  The complete
+// columns (every source window inside the payload, full 16-byte output) of pack_m consecutive codewords are laid side by
+// side over the CTA's threads with a FIXED thread -> (codeword, column) map -- one division per thread for the whole
+// kernel -- so nearly every lane does unmasked work (RS(5,4) on 4 KB: 5 x 51 columns on 256 threads instead of 52 on 64).
+// The incomplete columns (normally one per codeword) go to the first tail_ctas CTAs, one column per thread, masked.
+// resident 256-thread CTAs per SM for the packed kernel: the pipelined main loop holds one column being computed
+// (4D registers) and the next one in flight (4D aligned, 8D-4 otherwise)
+template <int D, bool ALIGNED, bool PIPE>
+constexpr int packed_min_blocks() {
+    if (!PIPE) return D <= 3 ? 6 : D <= 5 ? 5 : D <= 6 ? 4 : 3;          // 40 / 48 / 64 / 80 registers
+    constexpr int need = 4 * D + (ALIGNED ? 4 * D : 8 * D - 4) + 22;
+    constexpr int b = 65536 / (256 * need);
+    return b > 6 ? 6 : (b < 1 ? 1 : b);
+}
+
+template <int D, int CODE, int XT, bool ALIGNED, bool PIPE>
+__global__ void __launch_bounds__(256, packed_min_blocks<D, ALIGNED, PIPE>()) horner_encode_packed_kernel(const __grid_constant__ EncRowGen P) {
+    if (P.planes != nullptr) {
+        const uint32_t per = (P.n + gridDim.x - 1) / gridDim.x;
+        const uint32_t lo = blockIdx.x * per;
+        const uint32_t hi = lo + per < P.n ? lo + per : P.n;
+        for (uint32_t g = lo + threadIdx.x; g < hi; g += blockDim.x) {
+            const uint64_t w = dev::tally_word(P.planes, P.R, P.n, g, P.threshold);
+            P.committed[g] = w;
+            if (P.commit_bar != nullptr) P.commit_bar[g] = dev::commit_prefix(w);
+        }
+    }
+    if (blockIdx.x < P.tail_ctas) {
+        const uint64_t item = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+        const uint64_t g = P.ntail == 1u ? item : item / P.ntail;
+        if (g >= P.n) return;
+        const uint32_t col = P.fast_cols + static_cast<uint32_t>(item - g * P.ntail);
+        horner_row_column<D, CODE, XT, true>(P, P.data + g * P.data_stride, P.parity + g * P.shard_stride, col * 16u);
+        return;
+    }
+    const uint32_t cg = threadIdx.x / P.fast_cols;               // fast_cols >= 1 whenever main CTAs exist
+    const uint32_t k = (threadIdx.x - cg * P.fast_cols) * 16u;
+    if (cg >= P.pack_m) return;
+    const uint64_t step = static_cast<uint64_t>(gridDim.x - P.tail_ctas) * P.pack_m;
+    uint64_t g = static_cast<uint64_t>(blockIdx.x - P.tail_ctas) * P.pack_m + cg;
+    if (g >= P.n) return;
+    if constexpr (!PIPE) {
+#pragma unroll 1
+        for (; g < P.n; g += step)
+            horner_row_column<D, CODE, XT, false>(P, P.data + g * P.data_stride, P.parity + g * P.shard_stride, k);
+        return;
+    }
+    // software pipeline: the loads of this thread's next column are in flight while the current one is computed
+    RawColumn<D, ALIGNED> raw;
+    raw_issue<D, ALIGNED, CODE != kCodeGeneric>(P, P.data + g * P.data_stride, k, raw);
+#pragma unroll 1
+    while (true) {
+        uint4 x[D];
+        raw_finish<D, ALIGNED, CODE != kCodeGeneric>(P, raw, x);
+        const uint64_t gn = g + step;
+        if (gn < P.n) raw_issue<D, ALIGNED, CODE != kCodeGeneric>(P, P.data + gn * P.data_stride, k, raw);
+        parity_rows<D, CODE, XT, false>(P, x, 16, P.parity + g * P.shard_stride, k);
+        if (gn >= P.n) break;
+        g = gn;
     }
 }
 
@@ -1052,13 +1166,13 @@ struct Raw6 { uint4 a0, a1, b0, b1, c0, c1; };
 __device__ __forceinline__ void rs32_issue_loads(const uint8_t *__restrict__ src, uint32_t k, uint32_t o1, uint32_t o2,
                                                  uint32_t s0, uint32_t s1, uint32_t s2, Raw6 &r) {
     r.a0 = dev::ldg128(src + k);
-    r.a1 = r.a0;
+    r.a1 = make_uint4(0u, 0u, 0u, 0u);       // zeros, not copies of the loads (see rs32_row_column)
     if (s0 != 0u) r.a1 = dev::ldg128(src + k + 16u);
     r.b0 = dev::ldg128(src + o1);
-    r.b1 = r.b0;
+    r.b1 = make_uint4(0u, 0u, 0u, 0u);
     if (s1 != 0u) r.b1 = dev::ldg128(src + o1 + 16u);
     r.c0 = dev::ldg128(src + o2);
-    r.c1 = r.c0;
+    r.c1 = make_uint4(0u, 0u, 0u, 0u);
     if (s2 != 0u) r.c1 = dev::ldg128(src + o2 + 16u);
 }
 __device__ __forceinline__ void rs32_shards_from_raw(const Raw6 &r, uint32_t s0, uint32_t s1, uint32_t s2, uint4 (&sh)[5]) {
@@ -1130,14 +1244,14 @@ __global__ void __launch_bounds__(kThreads, 3) rs32_crossword_distribute_kernel(
                 const int nvc = clamp16(static_cast<int64_t>(len) - 2ll * L - k);
                 const int onv = clamp16(static_cast<int64_t>(L) - k);
                 const uint4 a0 = dev::ldg128(src + k);
-                uint4 a1 = a0;
+                uint4 a1 = make_uint4(0u, 0u, 0u, 0u);
                 if (s0 != 0u && static_cast<int>(s0) + nva > 16) a1 = dev::ldg128(src + k + 16u);
                 uint4 b0 = make_uint4(0u, 0u, 0u, 0u), c0 = make_uint4(0u, 0u, 0u, 0u);
                 if (nvb > 0) b0 = dev::ldg128(src + o1);
-                uint4 b1 = b0;
+                uint4 b1 = make_uint4(0u, 0u, 0u, 0u);
                 if (s1 != 0u && static_cast<int>(s1) + nvb > 16) b1 = dev::ldg128(src + o1 + 16u);
                 if (nvc > 0) c0 = dev::ldg128(src + o2);
-                uint4 c1 = c0;
+                uint4 c1 = make_uint4(0u, 0u, 0u, 0u);
                 if (s2 != 0u && static_cast<int>(s2) + nvc > 16) c1 = dev::ldg128(src + o2 + 16u);
                 sh[0] = keep_bytes(s0 != 0u ? funnel16(a0, a1, s0) : a0, nva < onv ? nva : onv);
                 sh[1] = keep_bytes(s1 != 0u ? funnel16(b0, b1, s1) : b0, nvb < onv ? nvb : onv);
@@ -1274,17 +1388,92 @@ int launch_rs_encode(ss_rs_coder *coder, const EncGeom &g, const TallyArgs *tall
                 Rg.planes = tally->planes; Rg.R = tally->R; Rg.threshold = tally->threshold;
                 Rg.committed = tally->committed; Rg.commit_bar = tally->commit_bar;
             }
-            const uint32_t threads = (vpc + 31u) & ~31u;
+            const int sc = ((coder->variant >> 11) & 1) ? kCodeGeneric : coder->static_code;   // bit 11: run-time masks
+            const int xt = (coder->variant >> 12) & 1;                                          // bit 12: multiply-based xtime
+            // Packed flavour when the one-codeword-per-pass layout would idle or mask a good part of the lanes
+            // (bit 13 forces it off, bit 14 forces it on).
+            const uint32_t fc = Rg.fast_cols;
+            const uint32_t row_threads = (vpc + 31u) & ~31u;
+            bool packed = fc != vpc || row_threads != vpc;
+            if ((coder->variant >> 13) & 1) packed = false;
+            if ((coder->variant >> 14) & 1) packed = true;
+            // software-pipelined main loop: always when every shard is 16-byte aligned; bit 15 selects it for unaligned too
+            const bool pipe = (L & 15u) == 0u || ((coder->variant >> 15) & 1);
+            if (packed) {
+                // threads: the multiple of 32 (<= 256) that wastes the fewest lanes; ties go to the larger CTA
+                uint32_t T = 256, m = fc ? 256u / fc : 0u;
+                if (fc) {
+                    double best = -1.0;
+                    for (uint32_t t = 256; t >= 64; t -= 32) {
+                        const uint32_t mm = t / fc;
+                        const double eff = static_cast<double>(mm * fc) / t;
+                        if (eff > best + 1e-9) { best = eff; T = t; m = mm; }
+                    }
+                }
+                Rg.pack_m = m;
+                Rg.ntail = vpc - fc;
+                const uint64_t tail_items = g.n * Rg.ntail;
+                const uint64_t tail_ctas = (tail_items + T - 1) / T;
+                uint64_t main_ctas = 0;
+                if (m) {
+                    const uint32_t dcap = d <= 2 ? 2 : d == 3 ? 3 : d == 4 ? 4 : d <= 6 ? 6 : 8;      // dispatch_d's capacity
+                    const uint32_t dt = sc != kCodeGeneric ? static_cast<uint32_t>(d) : dcap;
+                    const uint32_t reg_need = 4u * dt + ((L & 15u) == 0u ? 4u * dt : 8u * dt - 4u) + 22u;
+                    uint32_t rb = 65536u / (256u * reg_need); rb = rb > 6u ? 6u : (rb < 1u ? 1u : rb);
+                    if (!pipe) rb = dt <= 3 ? 6u : dt <= 5 ? 5u : dt <= 6 ? 4u : 3u;
+                    const uint32_t resident_threads = 256u * rb;
+                    main_ctas = static_cast<uint64_t>(ctx->sm_count) * (resident_threads / T) * 64ull;
+                    const uint64_t need = (g.n + m - 1) / m;
+                    if (main_ctas > need) main_ctas = need;
+                }
+                if (tail_ctas + main_ctas <= 0x7fffffffull) {
+                    Rg.tail_ctas = static_cast<uint32_t>(tail_ctas);
+                    const uint32_t grid = static_cast<uint32_t>(tail_ctas + main_ctas);
+                    auto gop = [&](auto DC, auto CC, auto XC) {
+                        constexpr int kD = decltype(DC)::value, kC = decltype(CC)::value, kX = decltype(XC)::value;
+                        if ((L & 15u) == 0u) horner_encode_packed_kernel<kD, kC, kX, true, true><<<grid, T, 0, st>>>(Rg);
+                        else if (pipe) horner_encode_packed_kernel<kD, kC, kX, false, true><<<grid, T, 0, st>>>(Rg);
+                        else horner_encode_packed_kernel<kD, kC, kX, false, false><<<grid, T, 0, st>>>(Rg);
+                    };
+                    auto gop_static = [&](auto CC) {
+                        constexpr int C = decltype(CC)::value;
+                        if (xt) gop(std::integral_constant<int, static_code_d(C)>{}, CC, std::integral_constant<int, 1>{});
+                        else gop(std::integral_constant<int, static_code_d(C)>{}, CC, std::integral_constant<int, 0>{});
+                    };
+                    switch (sc) {
+                        case kCode21: gop_static(std::integral_constant<int, kCode21>{}); break;
+                        case kCode43: gop_static(std::integral_constant<int, kCode43>{}); break;
+                        case kCode54: gop_static(std::integral_constant<int, kCode54>{}); break;
+                        case kCode42: gop_static(std::integral_constant<int, kCode42>{}); break;
+                        case kCode31: gop_static(std::integral_constant<int, kCode31>{}); break;
+                        default:
+                            SS_TRY(dispatch_d(d, [&](auto DC) {
+                                gop(DC, std::integral_constant<int, kCodeGeneric>{}, std::integral_constant<int, 0>{});
+                                return SS_OK;
+                            }));
+                    }
+                    if (sc != kCodeGeneric)
+                        coder->last_kernel = Rg.planes ? "horner_encode_packed_kernel<static code>+tally" : "horner_encode_packed_kernel<static code>";
+                    else
+                        coder->last_kernel = Rg.planes ? "horner_encode_packed_kernel+tally" : "horner_encode_packed_kernel";
+                    SS_CUDA(cudaGetLastError());
+                    ctx->launches++;
+                    return SS_OK;
+                }
+            }
+            Rg.pack_m = 0; Rg.tail_ctas = 0; Rg.ntail = 0;
+            const uint32_t threads = row_threads;
             uint32_t per_sm = 2048u / threads; if (per_sm > 32u) per_sm = 32u;
             uint64_t ctas = static_cast<uint64_t>(ctx->sm_count) * per_sm * 64ull;
             if (ctas > g.n) ctas = g.n;
             const uint32_t grid = static_cast<uint32_t>(ctas);
-            const int sc = ((coder->variant >> 11) & 1) ? kCodeGeneric : coder->static_code;   // bit 11: run-time masks
-            const int xt = (coder->variant >> 12) & 1;                                          // bit 12: multiply-based xtime
             // register budget (variant bits 0-3): threads <= 128: 0 = 12 CTAs/SM (40 regs), 2 = 10 (48), 3 = 8 (64), 4 = 6 (80)
-            const int vb = coder->variant & 15;
+            const int vbits = coder->variant & 15;
             auto go = [&](auto DC, auto CC, auto XC) {
                 constexpr int kD = decltype(DC)::value, kC = decltype(CC)::value, kX = decltype(XC)::value;
+                // default budget by width: spill-free at 40 registers up to d = 4, 48 for 5, 64 for 6, 80 beyond
+                const int vdef = kD <= 4 ? 0 : kD == 5 ? 2 : kD == 6 ? 3 : 4;
+                const int vb = vbits ? vbits : vdef;
                 if (threads > 128) horner_encode_row_kernel<kD, kC, kX, 256, 3><<<grid, threads, 0, st>>>(Rg);
                 else if (vb == 2) horner_encode_row_kernel<kD, kC, kX, 128, 10><<<grid, threads, 0, st>>>(Rg);
                 else if (vb == 3) horner_encode_row_kernel<kD, kC, kX, 128, 8><<<grid, threads, 0, st>>>(Rg);

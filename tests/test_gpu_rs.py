@@ -388,14 +388,22 @@ def test_generic_row_kernel_fused_step(ctx, oracle, d, p, data_len, n):
     torch.cuda.synchronize()
     assert ctx.launches == before + 1
     static = (d, p) in [(2, 1), (4, 3), (5, 4), (4, 2), (3, 1)]      # population 3/7/9/6/4 cluster codes
-    assert rs.last_kernel() == ("horner_encode_row_kernel<static code>+tally" if static else "horner_encode_row_kernel+tally")
+    tag = "<static code>" if static else ""
+    vpc = -(-L // 16)
+    last = max(0, data_len - (d - 1) * L)
+    packed = (min(L, last) // 16 != vpc) or vpc % 32 != 0          # some lanes would idle or be masked: packed layout
+    assert rs.last_kernel() == ("horner_encode_packed_kernel" if packed else "horner_encode_row_kernel") + tag + "+tally"
     want = oracle.rs_encode_uniform(d, p, data, data_len)
     assert (par.cpu().numpy() == want).all()
-    for v in (1 << 11, 1 << 12):                  # run-time mask flavour; multiply-based xtime flavour
+    # run-time masks; multiply-based xtime; forced one-codeword-per-pass layout; forced packed layout
+    for v in (1 << 11, 1 << 12, 1 << 13, 1 << 14, (1 << 14) | (1 << 11), (1 << 13) | (1 << 12)):
         rs.set_variant(v)
         par3 = rs.encode_uniform(torch.from_numpy(data).to(DEV), data_len)
         torch.cuda.synchronize()
-        assert rs.last_kernel() == ("horner_encode_row_kernel" if v == 1 << 11 or not static else "horner_encode_row_kernel<static code>")
+        is_packed = (packed or (v >> 14) & 1) and not (v >> 13) & 1
+        is_static = static and not (v >> 11) & 1
+        assert rs.last_kernel() == ("horner_encode_packed_kernel" if is_packed else "horner_encode_row_kernel") + \
+            ("<static code>" if is_static else ""), (v, rs.last_kernel())
         assert (par3.cpu().numpy() == want).all(), v
     c_want, b_want = oracle.tally_planes(planes, thr)
     assert (committed.cpu().numpy().view(np.uint64) == c_want).all()
