@@ -409,7 +409,8 @@ def run_ours(args):
         unit = "GB/s"
     achieved = alg * n / (kernel_ms * 1e-3) / 1e9
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": profile_traffic(args.workload), "kernel": rs.last_kernel() if args.workload != "cfg2" else "tally_planes_kernel",
+                "traffic": profile_traffic(args.workload if R == 5 else f"{args.workload}_r{R}"),
+                "kernel": rs.last_kernel() if args.workload != "cfg2" else "tally_planes_kernel",
                 "kernel_ms": kernel_ms, "algorithmic_bytes_per_launch": alg * n, "peak_source": peak_src + " (burst figure; kernel timed alone)"}
     if world > 1 and args.workload == "cfg3":
         # the same fused kernel WITHOUT the replicate stores (parity to local HBM only): per-GPU compute is flat in N

@@ -329,7 +329,13 @@ int ss_gossip_plan_dev(ss_ctx *ctx, uint32_t me, uint32_t population, uint32_t d
  *   bit 4     row kernel: contiguous chunk of codewords per CTA instead of grid-stride
  *   bits 5-7  row kernel waves of CTAs per resident set: {64 (default), 1, 32, 4, 16, 256, 128, 8}
  *   bits 8-9  cache operator of the plane stores in replicate mode: .cs (default), write-back, .cg, .wt
- *   bit 10    row kernel: fixed instead of rotating warp -> column-block assignment */
+ *   bit 10    row kernel: fixed instead of rotating warp -> column-block assignment
+ *   d <= 8 codes other than RS(3,2) (horner_encode_row_kernel / horner_encode_packed_kernel):
+ *   bits 0-3  1 = flat kernel; 2 / 3 / 4 = 48 / 64 / 80-register builds of the row layout (default by width)
+ *   bit 11    run-time coefficient masks even when the matrix is one of the compile-time cluster codes
+ *   bit 12    multiply-based xtime (reduction term from a high multiply) instead of the prmt sign mask
+ *   bit 13    never / bit 14 always use the packed layout (m codewords side by side per CTA, tail columns apart)
+ *   bit 15    software-pipelined packed loop also for shards that are not 16-byte aligned */
 int ss_rs_set_variant(ss_rs_coder *coder, int variant);
 /* name of the kernel the last batch call on this coder launched (static string) */
 const char *ss_rs_last_kernel(const ss_rs_coder *coder);
