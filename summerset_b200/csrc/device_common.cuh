@@ -67,18 +67,34 @@ __device__ __forceinline__ uint4 keep_bytes(uint4 v, int nvalid) {
 // index >= nvalid come back as zero and are never dereferenced beyond the aligned 16-byte block
 // that holds the last valid byte.  nvalid <= 0 returns zeros without touching memory.
 // Two aligned 128-bit loads + a byte funnel shift; neighbouring lanes hit the same sectors in L1.
-__device__ __forceinline__ uint4 load16(const uint8_t *p, int nvalid) {
-    if (nvalid <= 0) return make_uint4(0u, 0u, 0u, 0u);
+//
+// Split in two so that a thread that needs several vectors can ISSUE all their loads before it TOUCHES any of the
+// data: a warp issues in order, so the first instruction that reads a load's destination stalls everything behind
+// it -- including the next vector's loads -- until that load has landed.
+struct Raw16 {
+    uint4 lo, hi;
+    uint32_t s;
+};
+__device__ __forceinline__ Raw16 raw16_issue(const uint8_t *p, int nvalid) {
+    Raw16 r;
+    r.lo = make_uint4(0u, 0u, 0u, 0u);
+    r.hi = r.lo;
+    r.s = 0u;
+    if (nvalid <= 0) return r;
     const uintptr_t a = reinterpret_cast<uintptr_t>(p);
-    const uint32_t s = static_cast<uint32_t>(a) & 15u;
-    const uint4 *q = reinterpret_cast<const uint4 *>(a - s);
-    const uint4 lo = ldg128(q);
+    r.s = static_cast<uint32_t>(a) & 15u;
+    const uint4 *q = reinterpret_cast<const uint4 *>(a - r.s);
+    r.lo = ldg128(q);
+    if (r.s != 0u && static_cast<int>(16u - r.s) < nvalid) r.hi = ldg128(q + 1);
+    return r;
+}
+__device__ __forceinline__ uint4 raw16_finish(const Raw16 &r, int nvalid) {
+    const uint4 &lo = r.lo, &hi = r.hi;
+    const uint32_t s = r.s;
     uint4 o;
     if (s == 0u) {
         o = lo;
     } else {
-        uint4 hi = make_uint4(0u, 0u, 0u, 0u);
-        if (static_cast<int>(16u - s) < nvalid) hi = ldg128(q + 1);
         const uint32_t sel = 0x3210u + 0x1111u * (s & 3u);
         switch (s >> 2) {
             case 0:
@@ -101,6 +117,7 @@ __device__ __forceinline__ uint4 load16(const uint8_t *p, int nvalid) {
     }
     return keep_bytes(o, nvalid);
 }
+__device__ __forceinline__ uint4 load16(const uint8_t *p, int nvalid) { return raw16_finish(raw16_issue(p, nvalid), nvalid); }
 
 // Store the first nvalid (1..16) bytes of v at p.  padded: p is 16-byte aligned with 16 bytes of
 // capacity, and the bytes past nvalid are written as zeros (one 128-bit store).  Otherwise exact.

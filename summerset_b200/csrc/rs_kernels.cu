@@ -63,9 +63,13 @@ __device__ __forceinline__ void rs32_column(const uint8_t *src, uint32_t len, ui
                                             uint8_t *out, uint64_t plane_stride, bool padded, bool emit_data) {
     const int64_t rem = static_cast<int64_t>(len) - static_cast<int64_t>(k);
     auto nv = [](int64_t r) { return r > 16 ? 16 : (r < 0 ? 0 : static_cast<int>(r)); };
-    const uint4 a = load16(src + k, nv(rem));
-    const uint4 b = load16(src + static_cast<uint64_t>(L) + k, nv(rem - L));
-    const uint4 c = load16(src + 2ull * L + k, nv(rem - 2ll * L));
+    // all loads issued before any of the data is touched
+    const dev::Raw16 ra = dev::raw16_issue(src + k, nv(rem));
+    const dev::Raw16 rb = dev::raw16_issue(src + static_cast<uint64_t>(L) + k, nv(rem - L));
+    const dev::Raw16 rc = dev::raw16_issue(src + 2ull * L + k, nv(rem - 2ll * L));
+    const uint4 a = dev::raw16_finish(ra, nv(rem));
+    const uint4 b = dev::raw16_finish(rb, nv(rem - L));
+    const uint4 c = dev::raw16_finish(rc, nv(rem - 2ll * L));
     uint4 p0, p1;
     rs32_word(a.x, b.x, c.x, p0.x, p1.x);
     rs32_word(a.y, b.y, c.y, p0.y, p1.y);
@@ -603,7 +607,7 @@ __device__ __forceinline__ uint4 horner_row_t(const uint4 (&x)[D], const uint4 *
 }
 
 template <int D>
-__global__ void __launch_bounds__(kThreads, 4) horner_reconstruct_kernel(const __grid_constant__ DecArgs A) {
+__global__ void __launch_bounds__(kThreads, D <= 4 ? 4 : 2) horner_reconstruct_kernel(const __grid_constant__ DecArgs A) {
     const uint32_t lane = threadIdx.x & 31u;
     const uint64_t warp = (static_cast<uint64_t>(blockIdx.x) * kThreads + threadIdx.x) >> 5;
     const uint64_t nwarps = (static_cast<uint64_t>(gridDim.x) * kThreads) >> 5;
@@ -636,15 +640,20 @@ __global__ void __launch_bounds__(kThreads, 4) horner_reconstruct_kernel(const _
             const uint32_t k = v * 16u;
             const int nv = static_cast<int>(L - k) > 16 ? 16 : static_cast<int>(L - k);
             uint4 x[D];
+            dev::Raw16 raw[D];
+            // every source load of the column is issued before any loaded byte is touched
 #pragma unroll
             for (int i = 0; i < D; ++i) {
-                x[i] = make_uint4(0u, 0u, 0u, 0u);
+                raw[i].lo = make_uint4(0u, 0u, 0u, 0u); raw[i].hi = raw[i].lo; raw[i].s = 0u;
                 if (i < d) {
                     const uint8_t *sp = base + static_cast<uint64_t>(hdr->src[i]) * A.plane_stride + k;
                     // padded layout: every shard slot is 16-byte aligned -> one aligned 128-bit load
-                    x[i] = A.padded != 0u ? keep_bytes(dev::ldg128(sp), nv) : load16(sp, nv);
+                    if (A.padded != 0u) raw[i].lo = dev::ldg128(sp);
+                    else raw[i] = dev::raw16_issue(sp, nv);
                 }
             }
+#pragma unroll
+            for (int i = 0; i < D; ++i) x[i] = dev::raw16_finish(raw[i], nv);
             for (int j = 0; j < n_out; ++j) {
                 const uint4 acc = horner_row<D>(x, d, hmask + j * d * 8, hdr->top[j]);
                 store16(base + static_cast<uint64_t>(hdr->dst[j]) * A.plane_stride + k, acc, nv, A.padded != 0u);
@@ -711,10 +720,26 @@ __global__ void __launch_bounds__(kThreads, 4) rs_reconstruct_small_kernel(const
             const uint32_t k = v * 16u;
             const int nv = static_cast<int>(L - k) > 16 ? 16 : static_cast<int>(L - k);
             uint4 x[D];
+            if (padded) {
+                // every source load of the column is issued before any loaded byte is touched
 #pragma unroll
-            for (int i = 0; i < D; ++i) {
-                x[i] = make_uint4(0u, 0u, 0u, 0u);
-                if (i < d) x[i] = padded ? keep_bytes(dev::ldg128(sp[i] + k), nv) : load16(sp[i] + k, nv);
+                for (int i = 0; i < D; ++i) {
+                    x[i] = make_uint4(0u, 0u, 0u, 0u);
+                    if (i < d) x[i] = dev::ldg128(sp[i] + k);
+                }
+                if (nv < 16) {
+#pragma unroll
+                    for (int i = 0; i < D; ++i) x[i] = keep_bytes(x[i], nv);
+                }
+            } else {
+                dev::Raw16 raw[D];
+#pragma unroll
+                for (int i = 0; i < D; ++i) {
+                    raw[i].lo = make_uint4(0u, 0u, 0u, 0u); raw[i].hi = raw[i].lo; raw[i].s = 0u;
+                    if (i < d) raw[i] = dev::raw16_issue(sp[i] + k, nv);
+                }
+#pragma unroll
+                for (int i = 0; i < D; ++i) x[i] = dev::raw16_finish(raw[i], nv);
             }
             const uint4 y0 = horner_row_t<D, SMEM>(x, hmT, top0);
             store16(dp0 + k, y0, nv, padded);
@@ -739,12 +764,22 @@ __device__ __forceinline__ void horner_payload_column(const uint8_t *src, uint32
     const ProgHeader *hdr = reinterpret_cast<const ProgHeader *>(prog);
     const uint32_t *hmask = prog + sizeof(ProgHeader) / 4 + p * d * 8;
     uint4 x[D];
+    dev::Raw16 raw[D];
+    // every source load of the column is issued before any loaded byte is touched
 #pragma unroll
     for (int i = 0; i < D; ++i) {
+        raw[i].lo = make_uint4(0u, 0u, 0u, 0u); raw[i].hi = raw[i].lo; raw[i].s = 0u;
         if (i < d) {
             const int64_t pos = static_cast<int64_t>(i) * L + k;
             const int64_t rem = static_cast<int64_t>(len) - pos;
-            x[i] = load16(src + pos, rem > 16 ? 16 : (rem < 0 ? 0 : static_cast<int>(rem)));
+            raw[i] = dev::raw16_issue(src + pos, rem > 16 ? 16 : (rem < 0 ? 0 : static_cast<int>(rem)));
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < D; ++i) {
+        if (i < d) {
+            const int64_t rem = static_cast<int64_t>(len) - (static_cast<int64_t>(i) * L + k);
+            x[i] = dev::raw16_finish(raw[i], rem > 16 ? 16 : (rem < 0 ? 0 : static_cast<int>(rem)));
             if (emit_data) store16(out - static_cast<uint64_t>(d - i) * plane_stride + k, x[i], onv, padded);
         } else {
             x[i] = make_uint4(0u, 0u, 0u, 0u);
