@@ -335,7 +335,8 @@ int ss_gossip_plan_dev(ss_ctx *ctx, uint32_t me, uint32_t population, uint32_t d
  *   bit 11    run-time coefficient masks even when the matrix is one of the compile-time cluster codes
  *   bit 12    multiply-based xtime (reduction term from a high multiply) instead of the prmt sign mask
  *   bit 13    never / bit 14 always use the packed layout (m codewords side by side per CTA, tail columns apart)
- *   bit 15    software-pipelined packed loop also for shards that are not 16-byte aligned */
+ *   bit 15    software-pipelined packed loop also for shards that are not 16-byte aligned
+ *   bit 16    small-code reconstruct kernel: two columns per lane and pass (80 registers) instead of one (64) */
 int ss_rs_set_variant(ss_rs_coder *coder, int variant);
 /* name of the kernel the last batch call on this coder launched (static string) */
 const char *ss_rs_last_kernel(const ss_rs_coder *coder);

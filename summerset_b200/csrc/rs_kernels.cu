@@ -668,8 +668,8 @@ __global__ void __launch_bounds__(kThreads, D <= 4 ? 4 : 2) horner_reconstruct_k
 // staged in shared memory (no dependent global look-ups between a codeword's metadata and its shard loads),
 // Horner rows from one 128-bit mask word per bit level, XOR chain for the second of two missing data shards.
 // ------------------------------------------------------------------------------------------------
-template <int D, bool SMEM>
-__global__ void __launch_bounds__(kThreads, 4) rs_reconstruct_small_kernel(const __grid_constant__ DecArgs A) {
+template <int D, bool SMEM, bool PADDED, bool PAIR>
+__global__ void __launch_bounds__(kThreads, PAIR ? 3 : 4) rs_reconstruct_small_kernel(const __grid_constant__ DecArgs A) {
     extern __shared__ uint4 s_prog[];
     const uint8_t *table = A.fast_progs;
     if (SMEM) {
@@ -682,7 +682,7 @@ __global__ void __launch_bounds__(kThreads, 4) rs_reconstruct_small_kernel(const
     const uint64_t warp = (static_cast<uint64_t>(blockIdx.x) * kThreads + threadIdx.x) >> 5;
     const uint64_t nwarps = (static_cast<uint64_t>(gridDim.x) * kThreads) >> 5;
     const int d = A.d;
-    const bool padded = A.padded != 0u;
+    constexpr bool padded = PADDED;
     uint32_t nx_len = 0, nx_pat = 0; uint64_t nx_off = 0;
     if (warp < A.n) { nx_len = __ldg(A.data_len + warp); nx_pat = __ldg(A.present + warp); nx_off = __ldg(A.off + warp); }
     for (uint64_t g = warp; g < A.n; g += nwarps) {
@@ -716,31 +716,8 @@ __global__ void __launch_bounds__(kThreads, 4) rs_reconstruct_small_kernel(const
         const bool chain1 = hdr->chain1 != 0;
         uint8_t *dp0 = base + static_cast<uint64_t>(hdr->dst[0]) * A.plane_stride;
         uint8_t *dp1 = base + static_cast<uint64_t>(hdr->dst[1]) * A.plane_stride;
-        for (uint32_t v = lane; v < vpc; v += 32u) {
-            const uint32_t k = v * 16u;
-            const int nv = static_cast<int>(L - k) > 16 ? 16 : static_cast<int>(L - k);
-            uint4 x[D];
-            if (padded) {
-                // every source load of the column is issued before any loaded byte is touched
-#pragma unroll
-                for (int i = 0; i < D; ++i) {
-                    x[i] = make_uint4(0u, 0u, 0u, 0u);
-                    if (i < d) x[i] = dev::ldg128(sp[i] + k);
-                }
-                if (nv < 16) {
-#pragma unroll
-                    for (int i = 0; i < D; ++i) x[i] = keep_bytes(x[i], nv);
-                }
-            } else {
-                dev::Raw16 raw[D];
-#pragma unroll
-                for (int i = 0; i < D; ++i) {
-                    raw[i].lo = make_uint4(0u, 0u, 0u, 0u); raw[i].hi = raw[i].lo; raw[i].s = 0u;
-                    if (i < d) raw[i] = dev::raw16_issue(sp[i] + k, nv);
-                }
-#pragma unroll
-                for (int i = 0; i < D; ++i) x[i] = dev::raw16_finish(raw[i], nv);
-            }
+        // one column: Horner rows of the missing shards from the d source vectors
+        auto emit = [&](const uint4 (&x)[D], uint32_t k, int nv) {
             const uint4 y0 = horner_row_t<D, SMEM>(x, hmT, top0);
             store16(dp0 + k, y0, nv, padded);
             if (n_out > 1) {
@@ -751,6 +728,64 @@ __global__ void __launch_bounds__(kThreads, 4) rs_reconstruct_small_kernel(const
             for (int j = 2; j < n_out; ++j)
                 store16(base + static_cast<uint64_t>(hdr->dst[j]) * A.plane_stride + k,
                         horner_row_t<D, SMEM>(x, hmT + j * 8, hdr->top[j]), nv, padded);
+        };
+        if constexpr (PADDED && PAIR) {
+            // Two columns (v and v + 32) per lane and pass: all 2d source loads are issued before any loaded byte is
+            // touched, so a warp that walks its codeword alone keeps twice the bytes in flight.
+            for (uint32_t v = lane; v < vpc; v += 64u) {
+                const uint32_t k0 = v * 16u, k1 = k0 + 512u;
+                const bool two = v + 32u < vpc;
+                const int nv0 = static_cast<int>(L - k0) > 16 ? 16 : static_cast<int>(L - k0);
+                const int nv1 = two ? (static_cast<int>(L - k1) > 16 ? 16 : static_cast<int>(L - k1)) : 0;
+                uint4 x[D], y[D];
+#pragma unroll
+                for (int i = 0; i < D; ++i) {
+                    x[i] = make_uint4(0u, 0u, 0u, 0u);
+                    y[i] = x[i];
+                    if (i < d) {
+                        x[i] = dev::ldg128(sp[i] + k0);
+                        if (two) y[i] = dev::ldg128(sp[i] + k1);
+                    }
+                }
+                if (nv0 < 16) {
+#pragma unroll
+                    for (int i = 0; i < D; ++i) x[i] = keep_bytes(x[i], nv0);
+                }
+                if (two && nv1 < 16) {
+#pragma unroll
+                    for (int i = 0; i < D; ++i) y[i] = keep_bytes(y[i], nv1);
+                }
+                emit(x, k0, nv0);
+                if (two) emit(y, k1, nv1);
+            }
+        } else {
+            for (uint32_t v = lane; v < vpc; v += 32u) {
+                const uint32_t k = v * 16u;
+                const int nv = static_cast<int>(L - k) > 16 ? 16 : static_cast<int>(L - k);
+                uint4 x[D];
+                // every source load of the column is issued before any loaded byte is touched
+                if constexpr (PADDED) {
+#pragma unroll
+                    for (int i = 0; i < D; ++i) {
+                        x[i] = make_uint4(0u, 0u, 0u, 0u);
+                        if (i < d) x[i] = dev::ldg128(sp[i] + k);
+                    }
+                    if (nv < 16) {
+#pragma unroll
+                        for (int i = 0; i < D; ++i) x[i] = keep_bytes(x[i], nv);
+                    }
+                } else {
+                    dev::Raw16 raw[D];
+#pragma unroll
+                    for (int i = 0; i < D; ++i) {
+                        raw[i].lo = make_uint4(0u, 0u, 0u, 0u); raw[i].hi = raw[i].lo; raw[i].s = 0u;
+                        if (i < d) raw[i] = dev::raw16_issue(sp[i] + k, nv);
+                    }
+#pragma unroll
+                    for (int i = 0; i < D; ++i) x[i] = dev::raw16_finish(raw[i], nv);
+                }
+                emit(x, k, nv);
+            }
         }
     }
 }
@@ -1656,8 +1691,13 @@ int launch_rs_reconstruct(ss_rs_coder *coder, uint8_t *shards, uint64_t plane_st
         const size_t sb = smem ? A.fast_bytes : 0;
 #define SS_SMALL(DD)                                                                                       \
         do {                                                                                                   \
-            if (smem) rs_reconstruct_small_kernel<DD, true><<<grid, kThreads, sb, ctx->stream>>>(A);           \
-            else rs_reconstruct_small_kernel<DD, false><<<grid, kThreads, 0, ctx->stream>>>(A);                \
+            const bool pair = A.padded && ((coder->variant >> 16) & 1);    /* bit 16: two columns per lane and pass */      \
+            if (smem && pair) rs_reconstruct_small_kernel<DD, true, true, true><<<grid, kThreads, sb, ctx->stream>>>(A);         \
+            else if (smem && A.padded) rs_reconstruct_small_kernel<DD, true, true, false><<<grid, kThreads, sb, ctx->stream>>>(A); \
+            else if (smem) rs_reconstruct_small_kernel<DD, true, false, false><<<grid, kThreads, sb, ctx->stream>>>(A);          \
+            else if (pair) rs_reconstruct_small_kernel<DD, false, true, true><<<grid, kThreads, 0, ctx->stream>>>(A);            \
+            else if (A.padded) rs_reconstruct_small_kernel<DD, false, true, false><<<grid, kThreads, 0, ctx->stream>>>(A);       \
+            else rs_reconstruct_small_kernel<DD, false, false, false><<<grid, kThreads, 0, ctx->stream>>>(A);                    \
         } while (0)
         if (coder->d <= 2) SS_SMALL(2);
         else if (coder->d == 3) SS_SMALL(3);

@@ -275,9 +275,22 @@ def _planes_from(oracle, d, p, data, data_len):
 @pytest.mark.parametrize("d,p", [(3, 2), (4, 3), (5, 4), (2, 1), (6, 4)])
 @pytest.mark.parametrize("data_only", [True, False])
 def test_reconstruct_every_pattern(ctx, oracle, d, p, data_only):
+    _check_reconstruct_every_pattern(ctx, oracle, d, p, data_only, 1000 + d, 0)
+
+
+@pytest.mark.parametrize("d,p,data_len", [(3, 2, 4096), (3, 2, 9001), (4, 3, 4096), (2, 1, 3000), (3, 2, 16 * 3 * 64)])
+@pytest.mark.parametrize("variant", [0, 1 << 16])
+def test_reconstruct_long_codewords(ctx, oracle, d, p, data_len, variant):
+    """codewords of more than 32 / 64 columns: the small-code kernel's one-column passes and (bit 16) its paired-column
+    passes, full and partial second columns"""
+    _check_reconstruct_every_pattern(ctx, oracle, d, p, False, data_len, variant)
+    _check_reconstruct_every_pattern(ctx, oracle, d, p, True, data_len, variant)
+
+
+def _check_reconstruct_every_pattern(ctx, oracle, d, p, data_only, data_len, variant):
     rs = ReedSolomon(ctx, d, p)
+    rs.set_variant(variant)
     t = d + p
-    data_len = 1000 + d
     pats = list(range(1 << t))
     n = len(pats)
     data = wl.payload_uniform(n, data_len, seed_extra=77 + d)
