@@ -204,7 +204,7 @@ def run_reference(args):
         "e2e": {"value": value, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    print(json.dumps(line), flush=True)
 
 
 def config_dict(args, world):
@@ -474,7 +474,7 @@ def run_ours(args):
                                     "kernel stores its shard there over NVLink, so the step becomes NVLink-bound (roofline.comm); the "
                                     "same kernel without the remote stores takes roofline.local_only_kernel_ms on every N.")
         line.update(extra)
-        print(json.dumps(line))
+        print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -759,6 +759,13 @@ def run_cfg4(args, ctx, rs, dev, world, rank, peak, peak_src):
 def main():
     global D, P, R, THRESH_RSPAXOS, THRESH_MULTIPAXOS
     args = parse_args()
+    # The contract is ONE JSON line on stdout.  Native libraries print there too (NCCL writes "NCCL version ..." to fd 1
+    # when the first communicator comes up), so fd 1 is pointed at stderr for the whole run and Python's sys.stdout
+    # keeps a private duplicate of the real stdout for the result line.
+    sys.stdout.flush()
+    real_stdout = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+    sys.stdout = real_stdout
     if args.replicas != 5:      # scripts/local_cluster.py:41-50 defaults: fault_tolerance = (n//2)//2
         R = args.replicas
         D = R // 2 + 1
