@@ -333,7 +333,6 @@ int ss_gossip_plan_dev(ss_ctx *ctx, uint32_t me, uint32_t population, uint32_t d
  *   d <= 8 codes other than RS(3,2) (horner_encode_row_kernel / horner_encode_packed_kernel):
  *   bits 0-3  1 = flat kernel; 2 / 3 / 4 = 48 / 64 / 80-register builds of the row layout (default by width)
  *   bit 11    run-time coefficient masks even when the matrix is one of the compile-time cluster codes
- *   bit 12    multiply-based xtime (reduction term from a high multiply) instead of the prmt sign mask
  *   bit 13    never / bit 14 always use the packed layout (m codewords side by side per CTA, tail columns apart)
  *   bit 15    software-pipelined packed loop also for shards that are not 16-byte aligned
  *   bit 16    small-code reconstruct kernel: two columns per lane and pass (80 registers) instead of one (64) */

@@ -921,21 +921,10 @@ __host__ __device__ constexpr int static_code_top(int code, int j) {
     return top;
 }
 
-// multiply four packed field elements by x.  XT == 0: prmt sign mask (3 alu-pipe + 1 fma-pipe instruction);
-// XT == 1: the reduction term comes from a high multiply, (x & 0x80..) * 0x1d >> 7, and the carries are removed by a
-// multiply-add (1 alu-pipe + 3 fma-pipe; the closing XOR folds into the LOP3 of the next accumulate).
-template <int XT>
-__device__ __forceinline__ uint32_t xtime_word(uint32_t x) {
-    if constexpr (XT == 0) {
-        return ((x * 2u) & 0xfefefefeu) ^ (msb_mask(x) & 0x1d1d1d1du);
-    } else {
-        const uint32_t h = x & 0x80808080u;
-        const uint32_t r = __umulhi(h, 0x3a000000u);        // (h * 0x1d) >> 7: 0x1d in every byte whose top bit was set
-        uint32_t t;
-        asm("mad.lo.u32 %0, %1, 0xfffffffe, %2;" : "=r"(t) : "r"(h), "r"(x + x));   // 2x - 2h: carried-out bits removed
-        return t ^ r;
-    }
-}
+// multiply four packed field elements by x: shift on the FMA pipe, prmt sign mask + two lop3 on the ALU pipe.
+// (A flavour that took the reduction term from a high multiply -- 1 ALU + 3 FMA-pipe instructions -- measured the
+// same on B200 and was dropped: profiles/r01_cluster_codes_sweep.txt, variant 4096.)
+__device__ __forceinline__ uint32_t xtime_word(uint32_t x) { return ((x * 2u) & 0xfefefefeu) ^ (msb_mask(x) & 0x1d1d1d1du); }
 
 // the d source vectors of column k of one codeword, funnelled to shard alignment and masked to the payload
 template <int D, bool MASKED, bool EXACT>
@@ -973,7 +962,7 @@ __device__ __forceinline__ int row_load_column(const EncRowGen &P, const uint8_t
 }
 
 // the p parity vectors of one column from its d source vectors x[], stored at out + j*plane_stride + k
-template <int D, int CODE, int XT, bool MASKED>
+template <int D, int CODE, bool MASKED>
 __device__ __forceinline__ void parity_rows(const EncRowGen &P, const uint4 (&x)[D], int onv, uint8_t *__restrict__ out, uint32_t k) {
     if constexpr (CODE != kCodeGeneric) {
         static_assert(D == static_code_d(CODE), "static code width");
@@ -985,8 +974,8 @@ __device__ __forceinline__ void parity_rows(const EncRowGen &P, const uint4 (&x)
             for (int kk = 7; kk >= 0; --kk) {
                 if (kk > top) continue;
                 if (kk != top) {
-                    acc.x = xtime_word<XT>(acc.x); acc.y = xtime_word<XT>(acc.y);
-                    acc.z = xtime_word<XT>(acc.z); acc.w = xtime_word<XT>(acc.w);
+                    acc.x = xtime_word(acc.x); acc.y = xtime_word(acc.y);
+                    acc.z = xtime_word(acc.z); acc.w = xtime_word(acc.w);
                 }
 #pragma unroll
                 for (int i = 0; i < D; ++i)
@@ -1007,8 +996,8 @@ __device__ __forceinline__ void parity_rows(const EncRowGen &P, const uint4 (&x)
                 const uint4 m1 = D > 4 ? __ldg(hm + kk * 2 + 1) : make_uint4(0u, 0u, 0u, 0u);
                 const uint32_t mk[8] = {m0.x, m0.y, m0.z, m0.w, m1.x, m1.y, m1.z, m1.w};
                 if (kk != top) {
-                    acc.x = xtime_word<0>(acc.x); acc.y = xtime_word<0>(acc.y);
-                    acc.z = xtime_word<0>(acc.z); acc.w = xtime_word<0>(acc.w);
+                    acc.x = xtime_word(acc.x); acc.y = xtime_word(acc.y);
+                    acc.z = xtime_word(acc.z); acc.w = xtime_word(acc.w);
                 }
 #pragma unroll
                 for (int i = 0; i < D; ++i) {
@@ -1024,12 +1013,12 @@ __device__ __forceinline__ void parity_rows(const EncRowGen &P, const uint4 (&x)
     }
 }
 
-template <int D, int CODE, int XT, bool MASKED>
+template <int D, int CODE, bool MASKED>
 __device__ __forceinline__ void horner_row_column(const EncRowGen &P, const uint8_t *__restrict__ src, uint8_t *__restrict__ out,
                                                   uint32_t k) {
     uint4 x[D];
     const int onv = row_load_column<D, MASKED, CODE != kCodeGeneric>(P, src, k, x);
-    parity_rows<D, CODE, XT, MASKED>(P, x, onv, out, k);
+    parity_rows<D, CODE, MASKED>(P, x, onv, out, k);
 }
 
 // Split load for the software-pipelined packed kernel (complete columns only): issue the aligned 128-bit loads of one
@@ -1075,7 +1064,7 @@ __device__ __forceinline__ void raw_finish(const EncRowGen &P, const RawColumn<D
     }
 }
 
-template <int D, int CODE, int XT, int MAXT, int MINB>
+template <int D, int CODE, int MAXT, int MINB>
 __global__ void __launch_bounds__(MAXT, MINB) horner_encode_row_kernel(const __grid_constant__ EncRowGen P) {
     const uint32_t lane = threadIdx.x & 31u, wid = threadIdx.x >> 5, nblk = blockDim.x >> 5;
     if (P.planes != nullptr) {
@@ -1097,8 +1086,8 @@ __global__ void __launch_bounds__(MAXT, MINB) horner_encode_row_kernel(const __g
         if (v >= P.vpc) continue;
         const uint8_t *src = P.data + static_cast<uint64_t>(g) * P.data_stride;
         uint8_t *out = P.parity + static_cast<uint64_t>(g) * P.shard_stride;
-        if (!masked) horner_row_column<D, CODE, XT, false>(P, src, out, v * 16u);
-        else horner_row_column<D, CODE, XT, true>(P, src, out, v * 16u);
+        if (!masked) horner_row_column<D, CODE, false>(P, src, out, v * 16u);
+        else horner_row_column<D, CODE, true>(P, src, out, v * 16u);
     }
 }
 
@@ -1117,7 +1106,7 @@ constexpr int packed_min_blocks() {
     return b > 6 ? 6 : (b < 1 ? 1 : b);
 }
 
-template <int D, int CODE, int XT, bool ALIGNED, bool PIPE>
+template <int D, int CODE, bool ALIGNED, bool PIPE>
 __global__ void __launch_bounds__(256, packed_min_blocks<D, ALIGNED, PIPE>()) horner_encode_packed_kernel(const __grid_constant__ EncRowGen P) {
     if (P.planes != nullptr) {
         const uint32_t per = (P.n + gridDim.x - 1) / gridDim.x;
@@ -1134,7 +1123,7 @@ __global__ void __launch_bounds__(256, packed_min_blocks<D, ALIGNED, PIPE>()) ho
         const uint64_t g = P.ntail == 1u ? item : item / P.ntail;
         if (g >= P.n) return;
         const uint32_t col = P.fast_cols + static_cast<uint32_t>(item - g * P.ntail);
-        horner_row_column<D, CODE, XT, true>(P, P.data + g * P.data_stride, P.parity + g * P.shard_stride, col * 16u);
+        horner_row_column<D, CODE, true>(P, P.data + g * P.data_stride, P.parity + g * P.shard_stride, col * 16u);
         return;
     }
     const uint32_t cg = threadIdx.x / P.fast_cols;               // fast_cols >= 1 whenever main CTAs exist
@@ -1146,7 +1135,7 @@ __global__ void __launch_bounds__(256, packed_min_blocks<D, ALIGNED, PIPE>()) ho
     if constexpr (!PIPE) {
 #pragma unroll 1
         for (; g < P.n; g += step)
-            horner_row_column<D, CODE, XT, false>(P, P.data + g * P.data_stride, P.parity + g * P.shard_stride, k);
+            horner_row_column<D, CODE, false>(P, P.data + g * P.data_stride, P.parity + g * P.shard_stride, k);
         return;
     }
     // software pipeline: the loads of this thread's next column are in flight while the current one is computed
@@ -1158,7 +1147,7 @@ __global__ void __launch_bounds__(256, packed_min_blocks<D, ALIGNED, PIPE>()) ho
         raw_finish<D, ALIGNED, CODE != kCodeGeneric>(P, raw, x);
         const uint64_t gn = g + step;
         if (gn < P.n) raw_issue<D, ALIGNED, CODE != kCodeGeneric>(P, P.data + gn * P.data_stride, k, raw);
-        parity_rows<D, CODE, XT, false>(P, x, 16, P.parity + g * P.shard_stride, k);
+        parity_rows<D, CODE, false>(P, x, 16, P.parity + g * P.shard_stride, k);
         if (gn >= P.n) break;
         g = gn;
     }
@@ -1459,7 +1448,6 @@ int launch_rs_encode(ss_rs_coder *coder, const EncGeom &g, const TallyArgs *tall
                 Rg.committed = tally->committed; Rg.commit_bar = tally->commit_bar;
             }
             const int sc = ((coder->variant >> 11) & 1) ? kCodeGeneric : coder->static_code;   // bit 11: run-time masks
-            const int xt = (coder->variant >> 12) & 1;                                          // bit 12: multiply-based xtime
             // Packed flavour when the one-codeword-per-pass layout would idle or mask a good part of the lanes
             // (bit 13 forces it off, bit 14 forces it on).
             const uint32_t fc = Rg.fast_cols;
@@ -1499,16 +1487,15 @@ int launch_rs_encode(ss_rs_coder *coder, const EncGeom &g, const TallyArgs *tall
                 if (tail_ctas + main_ctas <= 0x7fffffffull) {
                     Rg.tail_ctas = static_cast<uint32_t>(tail_ctas);
                     const uint32_t grid = static_cast<uint32_t>(tail_ctas + main_ctas);
-                    auto gop = [&](auto DC, auto CC, auto XC) {
-                        constexpr int kD = decltype(DC)::value, kC = decltype(CC)::value, kX = decltype(XC)::value;
-                        if ((L & 15u) == 0u) horner_encode_packed_kernel<kD, kC, kX, true, true><<<grid, T, 0, st>>>(Rg);
-                        else if (pipe) horner_encode_packed_kernel<kD, kC, kX, false, true><<<grid, T, 0, st>>>(Rg);
-                        else horner_encode_packed_kernel<kD, kC, kX, false, false><<<grid, T, 0, st>>>(Rg);
+                    auto gop = [&](auto DC, auto CC) {
+                        constexpr int kD = decltype(DC)::value, kC = decltype(CC)::value;
+                        if ((L & 15u) == 0u) horner_encode_packed_kernel<kD, kC, true, true><<<grid, T, 0, st>>>(Rg);
+                        else if (pipe) horner_encode_packed_kernel<kD, kC, false, true><<<grid, T, 0, st>>>(Rg);
+                        else horner_encode_packed_kernel<kD, kC, false, false><<<grid, T, 0, st>>>(Rg);
                     };
                     auto gop_static = [&](auto CC) {
                         constexpr int C = decltype(CC)::value;
-                        if (xt) gop(std::integral_constant<int, static_code_d(C)>{}, CC, std::integral_constant<int, 1>{});
-                        else gop(std::integral_constant<int, static_code_d(C)>{}, CC, std::integral_constant<int, 0>{});
+                        gop(std::integral_constant<int, static_code_d(C)>{}, CC);
                     };
                     switch (sc) {
                         case kCode21: gop_static(std::integral_constant<int, kCode21>{}); break;
@@ -1518,7 +1505,7 @@ int launch_rs_encode(ss_rs_coder *coder, const EncGeom &g, const TallyArgs *tall
                         case kCode31: gop_static(std::integral_constant<int, kCode31>{}); break;
                         default:
                             SS_TRY(dispatch_d(d, [&](auto DC) {
-                                gop(DC, std::integral_constant<int, kCodeGeneric>{}, std::integral_constant<int, 0>{});
+                                gop(DC, std::integral_constant<int, kCodeGeneric>{});
                                 return SS_OK;
                             }));
                     }
@@ -1539,21 +1526,20 @@ int launch_rs_encode(ss_rs_coder *coder, const EncGeom &g, const TallyArgs *tall
             const uint32_t grid = static_cast<uint32_t>(ctas);
             // register budget (variant bits 0-3): threads <= 128: 0 = 12 CTAs/SM (40 regs), 2 = 10 (48), 3 = 8 (64), 4 = 6 (80)
             const int vbits = coder->variant & 15;
-            auto go = [&](auto DC, auto CC, auto XC) {
-                constexpr int kD = decltype(DC)::value, kC = decltype(CC)::value, kX = decltype(XC)::value;
+            auto go = [&](auto DC, auto CC) {
+                constexpr int kD = decltype(DC)::value, kC = decltype(CC)::value;
                 // default budget by width: spill-free at 40 registers up to d = 4, 48 for 5, 64 for 6, 80 beyond
                 const int vdef = kD <= 4 ? 0 : kD == 5 ? 2 : kD == 6 ? 3 : 4;
                 const int vb = vbits ? vbits : vdef;
-                if (threads > 128) horner_encode_row_kernel<kD, kC, kX, 256, 3><<<grid, threads, 0, st>>>(Rg);
-                else if (vb == 2) horner_encode_row_kernel<kD, kC, kX, 128, 10><<<grid, threads, 0, st>>>(Rg);
-                else if (vb == 3) horner_encode_row_kernel<kD, kC, kX, 128, 8><<<grid, threads, 0, st>>>(Rg);
-                else if (vb == 4) horner_encode_row_kernel<kD, kC, kX, 128, 6><<<grid, threads, 0, st>>>(Rg);
-                else horner_encode_row_kernel<kD, kC, kX, 128, 12><<<grid, threads, 0, st>>>(Rg);
+                if (threads > 128) horner_encode_row_kernel<kD, kC, 256, 3><<<grid, threads, 0, st>>>(Rg);
+                else if (vb == 2) horner_encode_row_kernel<kD, kC, 128, 10><<<grid, threads, 0, st>>>(Rg);
+                else if (vb == 3) horner_encode_row_kernel<kD, kC, 128, 8><<<grid, threads, 0, st>>>(Rg);
+                else if (vb == 4) horner_encode_row_kernel<kD, kC, 128, 6><<<grid, threads, 0, st>>>(Rg);
+                else horner_encode_row_kernel<kD, kC, 128, 12><<<grid, threads, 0, st>>>(Rg);
             };
             auto go_static = [&](auto CC) {
                 constexpr int C = decltype(CC)::value;
-                if (xt) go(std::integral_constant<int, static_code_d(C)>{}, CC, std::integral_constant<int, 1>{});
-                else go(std::integral_constant<int, static_code_d(C)>{}, CC, std::integral_constant<int, 0>{});
+                go(std::integral_constant<int, static_code_d(C)>{}, CC);
             };
             switch (sc) {
                 case kCode21: go_static(std::integral_constant<int, kCode21>{}); break;
@@ -1563,7 +1549,7 @@ int launch_rs_encode(ss_rs_coder *coder, const EncGeom &g, const TallyArgs *tall
                 case kCode31: go_static(std::integral_constant<int, kCode31>{}); break;
                 default:
                     SS_TRY(dispatch_d(d, [&](auto DC) {
-                        go(DC, std::integral_constant<int, kCodeGeneric>{}, std::integral_constant<int, 0>{});
+                        go(DC, std::integral_constant<int, kCodeGeneric>{});
                         return SS_OK;
                     }));
             }

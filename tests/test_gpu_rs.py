@@ -408,8 +408,8 @@ def test_generic_row_kernel_fused_step(ctx, oracle, d, p, data_len, n):
     assert rs.last_kernel() == ("horner_encode_packed_kernel" if packed else "horner_encode_row_kernel") + tag + "+tally"
     want = oracle.rs_encode_uniform(d, p, data, data_len)
     assert (par.cpu().numpy() == want).all()
-    # run-time masks; multiply-based xtime; forced one-codeword-per-pass layout; forced packed layout
-    for v in (1 << 11, 1 << 12, 1 << 13, 1 << 14, (1 << 14) | (1 << 11), (1 << 13) | (1 << 12)):
+    # run-time masks; forced one-codeword-per-pass layout; forced packed layout; pipelined packed loop
+    for v in (1 << 11, 1 << 13, 1 << 14, (1 << 14) | (1 << 11), (1 << 14) | (1 << 15), (1 << 13) | (1 << 11)):
         rs.set_variant(v)
         par3 = rs.encode_uniform(torch.from_numpy(data).to(DEV), data_len)
         torch.cuda.synchronize()
