@@ -671,7 +671,8 @@ def run_cfg4(args, ctx, rs, dev, world, rank, peak, peak_src):
     dlen = torch.from_numpy(lens.astype(np.int32)).to(dev)
     masks = torch.randint(0, 32, (n,), dtype=torch.uint8, device=dev, generator=gen) | 1     # leader always acks
     pidx = torch.from_numpy((spr - 1).astype(np.uint8)).to(dev)
-    policies = [list(map(int, oracle.cw_brr_assignment(5, 5, s))) for s in (1, 2, 3)]
+    from summerset_b200.api import crossword_brr_assignment
+    policies = [crossword_brr_assignment(5, 5, s) for s in (1, 2, 3)]
 
     # replica logs for the distribute step: replica r of my groups lives on rank (rank + r) % world
     import torch.distributed as dist

@@ -231,6 +231,20 @@ def craft_threshold(majority: int, fault_tolerance: int, full_copy_mode: bool) -
     return majority if full_copy_mode else majority + fault_tolerance
 
 
+def crossword_brr_assignment(population: int, total_shards: int, shards_per_replica: int) -> list:
+    """Balanced round-robin shard assignment policy of Crossword (crossword/mod.rs:866-888): replica r is assigned
+    shards ((r*dj)..(r*dj+spr)).map(|i| i % T) with dj = T / n; returned as one bitmask of shard indices per replica.
+    Host-side policy table handed to ss_tally_crossword_dev / ss_crossword_distribute_dev (nothing here touches data)."""
+    dj = total_shards // population
+    out = []
+    for r in range(population):
+        m = 0
+        for i in range(r * dj, r * dj + shards_per_replica):
+            m |= 1 << (i % total_shards)
+        out.append(m)
+    return out
+
+
 class DevBuffer:
     """A raw device allocation from ss_dev_alloc (or a peer GPU's buffer opened through CUDA IPC).
     Exposes __cuda_array_interface__ so `torch.as_tensor(buf, device=...)` views it without a copy."""

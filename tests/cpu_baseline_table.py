@@ -4,7 +4,7 @@ host cores -- scalar MUL_TABLE loops (the crate's default) and AVX2 vpshufb nibb
 enables, scripts/utils/file.py:33), on 1 thread (the reference runs encode + tally inline on one event-loop
 thread per replica) and on all threads.  Baseline only; never a fallback.  Writes a text table to stdout.
 
-  python tools/cpu_baseline_table.py [--quick]
+  python tests/cpu_baseline_table.py [--quick]
 """
 from __future__ import annotations
 

@@ -157,3 +157,11 @@ def test_rscodeword_p0_and_null_paths_need_no_coder():
     cw = RSCodeword.from_data(DATA, 3, 2)
     with pytest.raises(SummersetError, match="None"):
         cw.compute_parity(None)
+
+
+def test_crossword_brr_assignment_matches_oracle(oracle):
+    """host-side policy helper (crossword/mod.rs:866-888) against the oracle restatement"""
+    from summerset_b200.api import crossword_brr_assignment
+    for n, T in [(5, 5), (3, 3), (7, 7), (5, 10), (9, 9), (4, 8)]:
+        for spr in range(1, T + 1):
+            assert [int(x) for x in oracle.cw_brr_assignment(n, T, spr)] == crossword_brr_assignment(n, T, spr)
