@@ -16,7 +16,9 @@ from summerset_b200 import workloads as wl  # noqa: E402
 
 out = Path(__file__).resolve().parent
 arrs = {}
-for d, p, dl, n in [(3, 2, 4096, 5), (3, 2, 18, 3), (3, 2, 1, 2), (4, 3, 1000, 4), (5, 4, 257, 4), (6, 4, 100, 3)]:
+for d, p, dl, n in [(3, 2, 4096, 5), (3, 2, 18, 3), (3, 2, 1, 2), (4, 3, 1000, 4), (5, 4, 257, 4), (6, 4, 100, 3),
+                    # the cluster codes (population 3 / 7 / 9 / 6 / 4) at the benchmark payload size
+                    (2, 1, 4096, 3), (4, 3, 4096, 3), (5, 4, 4096, 3), (4, 2, 4096, 2), (3, 1, 4096, 2)]:
     data = wl.payload_uniform(n, dl, seed_extra=1000 + d)
     arrs[f"data_{d}_{p}_{dl}"] = data
     arrs[f"parity_{d}_{p}_{dl}"] = oracle.rs_encode_uniform(d, p, data, dl)
