@@ -66,3 +66,15 @@ def test_plain_c_client_on_gpu():
     r = subprocess.run([str(DEMO)], capture_output=True, text=True, timeout=120)
     assert r.returncode == 0, r.stdout + r.stderr
     assert "bit-exact" in r.stdout and "verify after encode: ok" in r.stdout and "-> -10" in r.stdout
+
+
+def test_static_code_tables_match_crate_construction(tmp_path):
+    """tests/cpp/test_static_codes.cpp: compile-time parity rows of the cluster codes == gf256.hpp's coding matrix
+    (host-only, no GPU, no CUDA)."""
+    gxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
+    exe = tmp_path / "test_static_codes"
+    subprocess.run([gxx, "-std=c++17", "-O1", "-Wall", str(ROOT / "tests" / "cpp" / "test_static_codes.cpp"), "-o", str(exe)],
+                   check=True)
+    r = subprocess.run([str(exe)], capture_output=True, text=True, timeout=60)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "0 failure(s)" in r.stdout
