@@ -1493,7 +1493,7 @@ int launch_rs_encode(ss_rs_coder *coder, const EncGeom &g, const TallyArgs *tall
                 constexpr int kD = decltype(DC)::value, kC = decltype(CC)::value;
                 // default budget by width: spill-free at 40 registers up to d = 4, 48 for 5, 64 for 6, 80 beyond
                 const int vdef = kD <= 4 ? 0 : kD == 5 ? 2 : kD == 6 ? 3 : 4;
-                const int vb = vbits ? vbits : vdef;
+                const int vb = (vbits >= 2 && vbits <= 4) ? vbits : vdef;      // other values select other kernels' knobs
                 if (threads > 128) horner_encode_row_kernel<kD, kC, 256, 3><<<grid, threads, 0, st>>>(Rg);
                 else if (vb == 2) horner_encode_row_kernel<kD, kC, 128, 10><<<grid, threads, 0, st>>>(Rg);
                 else if (vb == 3) horner_encode_row_kernel<kD, kC, 128, 8><<<grid, threads, 0, st>>>(Rg);
