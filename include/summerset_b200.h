@@ -65,8 +65,9 @@ typedef struct ss_ctx ss_ctx;           /* device + stream + scratch */
 typedef struct ss_rs_coder ss_rs_coder; /* replaces reed_solomon_erasure::galois_8::ReedSolomon */
 
 int ss_version(void);
-/* Text of the most recent error in this process (copied under a lock; not thread-local).
- * Maps to SummersetError::msg (src/utils/error.rs:6-14). */
+/* Text of the most recent error raised on the CALLING thread (one buffer per OS thread; the pointer stays valid until
+ * the next failing call on that thread).  Read it right after the failing call, before yielding: two replicas driven
+ * from two tokio worker threads never see each other's text.  Maps to SummersetError::msg (src/utils/error.rs:6-14). */
 const char *ss_last_error(void);
 const char *ss_strerror(int code);
 
@@ -75,6 +76,8 @@ const char *ss_strerror(int code);
 int ss_ctx_create(int device, ss_ctx **out);
 /* Same, but launches on a caller-owned cudaStream_t (e.g. torch's current stream). */
 int ss_ctx_create_on_stream(int device, void *cuda_stream, ss_ctx **out);
+/* Coders / engines created on a context keep it alive: destroying the context before them only marks it closed and the
+ * last handle's destroy call frees it (either order is safe). */
 int ss_ctx_destroy(ss_ctx *ctx);
 int ss_ctx_sync(ss_ctx *ctx);               /* cudaStreamSynchronize on the context's stream */
 void *ss_ctx_stream(ss_ctx *ctx);           /* the cudaStream_t */
@@ -235,11 +238,14 @@ int ss_tally_crossword_dev(ss_ctx *ctx, const void *masks, uint32_t mask_bytes,
  * entries last_commit+1 .. log_end-1 of group g have terms terms[g*window + (slot-last_commit-1)]
  * (log_end - last_commit - 1 <= window).  new_commit[g] = the LAST slot in that range with
  * term == curr_term and 1 + #{p: match[p] >= slot} >= threshold, else last_commit[g].
- * threshold = quorum_cnt (Raft), majority+f or majority (CRaft full-copy). */
+ * threshold = quorum_cnt (Raft), majority+f or majority (CRaft full-copy).
+ * window_overflow (device u32, may be NULL): incremented once per group whose candidate range exceeds `window`
+ * entries (precondition violated); for such a group new_commit is a lower bound of the reference's result (candidates
+ * beyond the window cannot be examined) and the host should rescan it with a larger window. */
 int ss_raft_commit_scan_dev(ss_ctx *ctx, const uint32_t *match, uint32_t n_peers, uint64_t n_groups,
                             const uint32_t *last_commit, const uint32_t *log_end,
                             const uint32_t *curr_term, const uint32_t *terms, uint32_t window,
-                            uint32_t threshold, uint32_t *new_commit);
+                            uint32_t threshold, uint32_t *new_commit, uint32_t *window_overflow);
 
 /* k-th largest peer match per group.  k = threshold - 1 gives CRaft's shadow_last_commit
  * (craft/messages.rs:677-690: match slots sorted descending, element [threshold-2], threshold =

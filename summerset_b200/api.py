@@ -157,15 +157,16 @@ class Context:
 
     def raft_commit_scan(self, match: torch.Tensor, last_commit: torch.Tensor, log_end: torch.Tensor,
                          curr_term: torch.Tensor, terms: torch.Tensor, threshold: int,
-                         out: Optional[torch.Tensor] = None) -> torch.Tensor:
-        """match int32 [P, G]; terms int32 [G, W]; everything on the GPU."""
+                         out: Optional[torch.Tensor] = None, window_overflow: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """match int32 [P, G]; terms int32 [G, W]; everything on the GPU.  window_overflow: optional int32 [1] counter of
+        groups whose candidate range exceeded W (their result is a lower bound)."""
         assert match.dtype == torch.int32 and terms.dtype == torch.int32 and match.is_contiguous() and terms.is_contiguous()
         P, G = match.shape
         W = terms.shape[1]
         if out is None:
             out = torch.empty(G, dtype=torch.int32, device=match.device)
         check(self.lib.ss_raft_commit_scan_dev(self.h, _ptr(match), P, G, _ptr(last_commit), _ptr(log_end),
-                                               _ptr(curr_term), _ptr(terms), W, threshold, _ptr(out)))
+                                               _ptr(curr_term), _ptr(terms), W, threshold, _ptr(out), _ptr(window_overflow)))
         return out
 
 
@@ -198,7 +199,7 @@ def _ctx_extras():
         L = shard_len(data_len, d)
         stride = round_up(L + 96 + d + p, 16)
         dev = shard_plane.device
-        out = torch.zeros((n, stride), dtype=torch.uint8, device=dev)
+        out = torch.full((n, stride), 0xA5, dtype=torch.uint8, device=dev)   # the C ABI does not require a zeroed buffer
         off = torch.empty(n, dtype=torch.int64, device=dev)
         ln = torch.empty(n, dtype=torch.int32, device=dev)
         check(self.lib.ss_frame_accept_batch_dev(self.h, _ptr(shard_plane), ss, shard_idx, d, p, data_len, msg_variant,

@@ -7,6 +7,7 @@
 #include <cstdarg>
 #include <cstdlib>
 #include <cstring>
+#include <atomic>
 #include <mutex>
 #include <new>
 
@@ -16,17 +17,15 @@
 namespace ssb {
 
 // ---- errors -----------------------------------------------------------------------------------
-static std::mutex g_err_mu;
-static char g_err[512] = "";
+// One buffer per calling thread: two coders driven from two tokio worker threads never see each other's text, and the
+// pointer ss_last_error() returns stays valid until the next failing call on the same thread.
+static thread_local char g_err[512] = "";
 
 int set_error(int code, const char *fmt, ...) {
-    char buf[512];
     va_list ap;
     va_start(ap, fmt);
-    vsnprintf(buf, sizeof(buf), fmt, ap);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
     va_end(ap);
-    std::lock_guard<std::mutex> lk(g_err_mu);
-    snprintf(g_err, sizeof(g_err), "%s", buf);
     return code;
 }
 
@@ -41,6 +40,7 @@ int cuda_error(cudaError_t e, const char *what, const char *file, int line) {
 
 int ctx_bind(ss_ctx *ctx) {
     if (ctx == nullptr) return set_error(SS_ERR_INVALID_ARG, "null context");
+    if (ctx->closing.load()) return set_error(SS_ERR_INVALID_ARG, "context was destroyed (a handle outlived it)");
     SS_CUDA(cudaSetDevice(ctx->device));
     return SS_OK;
 }
@@ -198,6 +198,36 @@ static int check_shard_args(const ss_rs_coder *c, const void *shards, size_t n_s
     return SS_OK;
 }
 
+// frees everything the context owns; only called once no coder / engine handle refers to it any more
+static void ctx_teardown(ss_ctx *ctx) {
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    if (ctx->pipeline_ready) {
+        cudaStreamSynchronize(ctx->h2d_stream);
+        cudaStreamSynchronize(ctx->d2h_stream);
+        for (int i = 0; i < ss_ctx::kStages; ++i) {
+            cudaEventDestroy(ctx->ev_h2d[i]);
+            cudaEventDestroy(ctx->ev_kernel[i]);
+            cudaEventDestroy(ctx->ev_done[i]);
+        }
+        cudaStreamDestroy(ctx->h2d_stream);
+        cudaStreamDestroy(ctx->d2h_stream);
+    }
+    for (int i = 0; i < ss_ctx::kStages; ++i) {
+        if (ctx->stage_in[i]) cudaFree(ctx->stage_in[i]);
+        if (ctx->stage_out[i]) cudaFree(ctx->stage_out[i]);
+    }
+    if (ctx->scratch) cudaFree(ctx->scratch);
+    if (ctx->owns_stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+void ctx_retain(ss_ctx *ctx) { ctx->live_handles.fetch_add(1); }
+void ctx_release(ss_ctx *ctx) {
+    if (ctx->live_handles.fetch_sub(1) == 1 && ctx->closing.load()) ctx_teardown(ctx);
+}
+
+
 }  // namespace ssb
 
 using namespace ssb;
@@ -273,28 +303,17 @@ int ss_ctx_create_on_stream(int device, void *cuda_stream, ss_ctx **out) {
     return ctx_create_common(device, cuda_stream, true, out);
 }
 
+// Handles created on a context (coders, engines) keep it alive: destroying the context first only marks it closed,
+// and the last handle's destroy call tears it down (either order is safe, e.g. Python garbage collection).
 int ss_ctx_destroy(ss_ctx *ctx) {
     if (ctx == nullptr) return SS_OK;
-    cudaSetDevice(ctx->device);
-    cudaStreamSynchronize(ctx->stream);
-    if (ctx->pipeline_ready) {
-        cudaStreamSynchronize(ctx->h2d_stream);
-        cudaStreamSynchronize(ctx->d2h_stream);
-        for (int i = 0; i < ss_ctx::kStages; ++i) {
-            cudaEventDestroy(ctx->ev_h2d[i]);
-            cudaEventDestroy(ctx->ev_kernel[i]);
-            cudaEventDestroy(ctx->ev_done[i]);
-        }
-        cudaStreamDestroy(ctx->h2d_stream);
-        cudaStreamDestroy(ctx->d2h_stream);
+    if (ctx->live_handles.load() > 0) {
+        cudaSetDevice(ctx->device);
+        cudaStreamSynchronize(ctx->stream);
+        ctx->closing.store(true);
+        return SS_OK;
     }
-    for (int i = 0; i < ss_ctx::kStages; ++i) {
-        if (ctx->stage_in[i]) cudaFree(ctx->stage_in[i]);
-        if (ctx->stage_out[i]) cudaFree(ctx->stage_out[i]);
-    }
-    if (ctx->scratch) cudaFree(ctx->scratch);
-    if (ctx->owns_stream) cudaStreamDestroy(ctx->stream);
-    delete ctx;
+    ctx_teardown(ctx);
     return SS_OK;
 }
 
@@ -395,10 +414,13 @@ int ss_rs_coder_create(ss_ctx *ctx, int d, int p, ss_rs_coder **out) {
     ss_rs_coder *c = new (std::nothrow) ss_rs_coder();
     if (!c) return set_error(SS_ERR_OUT_OF_MEMORY, "host allocation failed");
     c->ctx = ctx; c->d = d; c->p = p;
+    ctx_retain(ctx);
     gf::Matrix M;
+
     try {
         M = gf::coding_matrix(d, p);
     } catch (const std::exception &ex) {
+        ctx_release(ctx);
         delete c;
         return set_error(SS_ERR_INVALID_ARG, "matrix construction failed: %s", ex.what());
     }
@@ -481,6 +503,7 @@ int ss_rs_coder_destroy(ss_rs_coder *c) {
     if (c->dec_progs_data) cudaFree(c->dec_progs_data);
     if (c->fast_progs) cudaFree(c->fast_progs);
     if (c->fast_progs_data) cudaFree(c->fast_progs_data);
+    if (c->ctx) ctx_release(c->ctx);
     delete c;
     return SS_OK;
 }
@@ -579,14 +602,15 @@ int ss_rs_verify(ss_rs_coder *c, const uint8_t *const *shards, size_t n_shards, 
     SS_TRY(check_shard_args(c, shards, n_shards, shard_len));
     if (ok == nullptr) return set_error(SS_ERR_INVALID_ARG, "null ok pointer");
     const int d = c->d, p = c->p;
-    std::vector<std::vector<uint8_t>> par(p, std::vector<uint8_t>(shard_len));
-    std::vector<uint8_t *> tmp(d + p);
-    for (int i = 0; i < d; ++i) tmp[i] = const_cast<uint8_t *>(shards[i]);
-    for (int j = 0; j < p; ++j) tmp[d + j] = par[j].data();
-    SS_TRY(ss_rs_encode(c, tmp.data(), n_shards, shard_len));    // parity recomputed on the GPU
+    // recomputed-parity staging lives in the coder (grow-only): no allocation per call
+    if (c->verify_buf.size() < size_t(p) * shard_len) c->verify_buf.resize(size_t(p) * shard_len);
+    c->verify_ptrs.resize(size_t(d + p));
+    for (int i = 0; i < d; ++i) c->verify_ptrs[i] = const_cast<uint8_t *>(shards[i]);
+    for (int j = 0; j < p; ++j) c->verify_ptrs[d + j] = c->verify_buf.data() + size_t(j) * shard_len;
+    SS_TRY(ss_rs_encode(c, c->verify_ptrs.data(), n_shards, shard_len));    // parity recomputed on the GPU
     *ok = 1;
     for (int j = 0; j < p; ++j)
-        if (memcmp(par[j].data(), shards[d + j], shard_len) != 0) { *ok = 0; break; }
+        if (memcmp(c->verify_ptrs[d + j], shards[d + j], shard_len) != 0) { *ok = 0; break; }
     return SS_OK;
 }
 
@@ -789,13 +813,14 @@ int ss_tally_crossword_dev(ss_ctx *ctx, const void *masks, uint32_t mask_bytes, 
 
 int ss_raft_commit_scan_dev(ss_ctx *ctx, const uint32_t *match, uint32_t n_peers, uint64_t G,
                             const uint32_t *last_commit, const uint32_t *log_end, const uint32_t *curr_term,
-                            const uint32_t *terms, uint32_t window, uint32_t threshold, uint32_t *new_commit) {
+                            const uint32_t *terms, uint32_t window, uint32_t threshold, uint32_t *new_commit,
+                            uint32_t *window_overflow) {
     if (ctx == nullptr) return set_error(SS_ERR_INVALID_ARG, "null context");
     if (G == 0) return SS_OK;
     if ((!match && n_peers) || !last_commit || !log_end || !curr_term || !terms || !new_commit)
         return set_error(SS_ERR_INVALID_ARG, "null buffer");
     return launch_raft_scan(ctx, match, n_peers, G, last_commit, log_end, curr_term, terms, window, threshold,
-                            new_commit);
+                            new_commit, window_overflow);
 }
 
 int ss_crossword_distribute_dev(ss_rs_coder *c, const uint8_t *data, const uint64_t *data_off, const uint32_t *data_len,

@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 
+#include <atomic>
 #include <cstdint>
 #include <cstdio>
 #include <string>
@@ -69,6 +70,9 @@ struct ss_ctx {
     bool owns_stream = false;
     int sm_count = 0;
     uint64_t launches = 0;
+    // coders / engines created on this context hold a reference; ss_ctx_destroy defers the teardown to the last of them
+    std::atomic<int> live_handles{0};
+    std::atomic<bool> closing{false};
     // grow-only device scratch (scan temporaries, LUTs)
     void *scratch = nullptr;
     size_t scratch_bytes = 0;
@@ -102,11 +106,15 @@ struct ss_rs_coder {
     size_t prog_stride = 0;           // bytes per program
     bool batch_ok = false;            // d,p within the batched kernels' limits
     bool dec_ok = false;              // d+p small enough for the per-pattern decode table
+    std::vector<uint8_t> verify_buf;  // ss_rs_verify: recomputed parity (grow-only, reused across calls)
+    std::vector<uint8_t *> verify_ptrs;
 };
 
 namespace ssb {
 
 int ctx_bind(ss_ctx *ctx);                              // cudaSetDevice(ctx->device)
+void ctx_retain(ss_ctx *ctx);                           // a handle (coder, engine) starts referring to ctx
+void ctx_release(ss_ctx *ctx);                          // ... and stops; tears ctx down if it was destroyed meanwhile
 int ctx_scratch(ss_ctx *ctx, size_t bytes, void **out); // grow-only scratch
 
 // ---- kernel launchers (defined in the .cu files) ---------------------------------------------
@@ -155,7 +163,8 @@ int launch_tally_crossword(ss_ctx *ctx, const void *masks, uint32_t mask_bytes, 
                            int balanced, uint64_t *commit_bits);
 int launch_raft_scan(ss_ctx *ctx, const uint32_t *match, uint32_t n_peers, uint64_t G,
                      const uint32_t *last_commit, const uint32_t *log_end, const uint32_t *curr_term,
-                     const uint32_t *terms, uint32_t window, uint32_t threshold, uint32_t *new_commit);
+                     const uint32_t *terms, uint32_t window, uint32_t threshold, uint32_t *new_commit,
+                     uint32_t *window_overflow);
 
 int launch_kth_match(ss_ctx *ctx, const uint32_t *match, uint32_t n_peers, uint64_t G, uint32_t k, uint32_t *out);
 int launch_prepare_merge(ss_ctx *ctx, const uint64_t *vote_bal, const uint32_t *vote_mask, uint32_t R, uint64_t N,

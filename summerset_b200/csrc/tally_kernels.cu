@@ -242,7 +242,7 @@ __global__ void __launch_bounds__(kTallyThreads)
 raft_scan_kernel(const uint32_t *__restrict__ match, uint32_t n_peers, uint64_t G,
                  const uint32_t *__restrict__ last_commit, const uint32_t *__restrict__ log_end,
                  const uint32_t *__restrict__ curr_term, const uint32_t *__restrict__ terms, uint32_t W,
-                 uint32_t threshold, uint32_t *__restrict__ new_commit) {
+                 uint32_t threshold, uint32_t *__restrict__ new_commit, uint32_t *__restrict__ window_overflow) {
     const uint32_t lane = threadIdx.x & 31u;
     const uint64_t warp = (static_cast<uint64_t>(blockIdx.x) * kTallyThreads + threadIdx.x) >> 5;
     const uint64_t nwarps = (static_cast<uint64_t>(gridDim.x) * kTallyThreads) >> 5;
@@ -286,6 +286,9 @@ raft_scan_kernel(const uint32_t *__restrict__ match, uint32_t n_peers, uint64_t 
             if (any && le > 0u) { if (upper > le - 1u) upper = le - 1u; }
             else any = false;
             if (any && upper <= lc) any = false;
+            // precondition log_end - last_commit - 1 <= window violated: candidates beyond the window cannot be
+            // examined, the result is then a LOWER bound of raft/messages.rs:256-275 -- counted so the host can tell
+            if (any && upper - lc > W && window_overflow != nullptr) atomicAdd(window_overflow, 1u);
         }
         uint32_t result = lc;
         // ---- probe: the highest candidate slot usually IS a current-term entry (a leader appends in its own
@@ -419,9 +422,11 @@ __global__ void __launch_bounds__(kTallyThreads) frame_accept_kernel(const __gri
     const uint64_t warp = (static_cast<uint64_t>(blockIdx.x) * kTallyThreads + threadIdx.x) >> 5;
     const uint64_t nwarps = (static_cast<uint64_t>(gridDim.x) * kTallyThreads) >> 5;
     for (uint64_t g = warp; g < A.n; g += nwarps) {
-        // body header: PeerMessage::Msg (0), PeerMsg::Accept, slot, ballot, d, p, data_len, shard_len, #shards,
-        // `shard_idx` Nones, Some tag, shard byte length
-        uint8_t hdr[64];
+        // body header: PeerMessage::Msg (0), PeerMsg::Accept, slot, ballot, d, p, data_len, shard_len, #shards -- the fixed
+        // fields (at most 39 bytes) -- then `shard_idx` None tags, the Some tag and the shard's byte length.  Only the
+        // fixed fields and the Some tag + length go through thread-local arrays; the None runs (up to d+p-1 bytes on
+        // either side of the shard) are written straight into the frame by lane-strided loops.
+        uint8_t hdr[40], some[8];
         int h = 0;
         hdr[h++] = 0;
         h += put_varint(hdr + h, A.msg_variant);
@@ -432,28 +437,32 @@ __global__ void __launch_bounds__(kTallyThreads) frame_accept_kernel(const __gri
         h += put_varint(hdr + h, A.data_len);
         h += put_varint(hdr + h, A.L);
         h += put_varint(hdr + h, A.d + A.p);
-        for (uint32_t j = 0; j < A.shard_idx; ++j) hdr[h++] = 0;
-        hdr[h++] = 1;
-        h += put_varint(hdr + h, A.L);
+        int hs = 0;
+        some[hs++] = 1;
+        hs += put_varint(some + hs, A.L);
+        const uint32_t lead = A.shard_idx;                                // None tags before the shard
         const uint32_t tail = (A.d + A.p - 1u - A.shard_idx) + 1u;       // remaining Nones + data_copy None
-        const uint64_t body = static_cast<uint64_t>(h) + A.L + tail;
-        const uint32_t pre = 8u + static_cast<uint32_t>(h);              // bytes before the shard payload
+        const uint32_t hb = static_cast<uint32_t>(h) + lead + static_cast<uint32_t>(hs);   // body bytes before the shard
+        const uint64_t body = static_cast<uint64_t>(hb) + A.L + tail;
+        const uint32_t pre = 8u + hb;                                    // bytes before the shard payload
         const uint32_t pad = (16u - (pre & 15u)) & 15u;                  // so that the payload is 16-byte aligned
         uint8_t *slot_base = A.out + g * A.frame_stride;
         uint8_t *f = slot_base + pad;
         if (lane == 0u) {
             for (int i = 0; i < 8; ++i) f[i] = static_cast<uint8_t>(body >> (8 * (7 - i)));
             for (int i = 0; i < h; ++i) f[8 + i] = hdr[i];
+            for (int i = 0; i < hs; ++i) f[8u + static_cast<uint32_t>(h) + lead + i] = some[i];
             A.frame_off[g] = g * A.frame_stride + pad;
             A.frame_len[g] = static_cast<uint32_t>(8u + body);
         }
+        for (uint32_t t = lane; t < lead; t += 32u) f[8u + static_cast<uint32_t>(h) + t] = 0;
         uint8_t *pay = f + pre;
         const uint8_t *src = A.plane + g * A.shard_stride;
         const uint32_t full = A.L >> 4;
         for (uint32_t v = lane; v < full; v += 32u) dev::stg128_cs(pay + v * 16u, dev::ldg128(src + v * 16u));
         const uint32_t rem = A.L & 15u;
         if (lane < rem) pay[full * 16u + lane] = src[full * 16u + lane];
-        if (lane < tail) pay[A.L + lane] = 0;
+        for (uint32_t t = lane; t < tail; t += 32u) pay[A.L + t] = 0;
     }
 }
 
@@ -600,7 +609,7 @@ int launch_tally_crossword(ss_ctx *ctx, const void *masks, uint32_t mask_bytes, 
 
 int launch_raft_scan(ss_ctx *ctx, const uint32_t *match, uint32_t n_peers, uint64_t G, const uint32_t *last_commit,
                      const uint32_t *log_end, const uint32_t *curr_term, const uint32_t *terms, uint32_t window,
-                     uint32_t threshold, uint32_t *new_commit) {
+                     uint32_t threshold, uint32_t *new_commit, uint32_t *window_overflow) {
     SS_TRY(ctx_bind(ctx));
     if (n_peers > kRaftMaxPeers) return set_error(SS_ERR_INVALID_ARG, "n_peers must be <= %d, got %u", kRaftMaxPeers, n_peers);
     if (G == 0) return SS_OK;
@@ -610,7 +619,7 @@ int launch_raft_scan(ss_ctx *ctx, const uint32_t *match, uint32_t n_peers, uint6
     if (ctas > cap) ctas = cap;
     const uint32_t grid = static_cast<uint32_t>(ctas);
 #define SS_RAFT_LAUNCH(NP) raft_scan_kernel<NP><<<grid, kTallyThreads, 0, ctx->stream>>>( \
-        match, n_peers, G, last_commit, log_end, curr_term, terms, window, threshold, new_commit)
+        match, n_peers, G, last_commit, log_end, curr_term, terms, window, threshold, new_commit, window_overflow)
     if (n_peers <= 2) SS_RAFT_LAUNCH(2);
     else if (n_peers <= 4) SS_RAFT_LAUNCH(4);
     else if (n_peers <= 6) SS_RAFT_LAUNCH(6);
