@@ -280,16 +280,58 @@ int ss_accept_step_fused_dev(ss_rs_coder *coder, const uint8_t *data, uint64_t d
                              const uint64_t *planes, uint32_t n_replicas, uint32_t threshold,
                              uint64_t *committed, uint32_t *commit_bar);
 
+/* ---- step flags: cross-GPU ordering without host synchronisation ---------------------------------------------
+ * A flag is a u64 step counter in device memory (ss_dev_alloc + ss_dev_memset 0; exported to peers with
+ * ss_ipc_export).  Calls that take an ss_step_sync
+ *   - first wait (on the device, inside the kernel) until every wait_flags[i] >= wait_value -- wait_flags is a device
+ *     array in LOCAL memory that peers write into;
+ *   - after all of the call's stores are visible system-wide, store signal_value to every *signal_flags[i]
+ *     (st.release.sys) -- signal_flags is a HOST array of device pointers into local or peer memory.
+ * This replaces the per-step stream barrier + ack copies a host would otherwise need: a follower's kernel starts when
+ * the leader's shards have landed, the leader's next tally starts when the followers' acks have landed
+ * (rspaxos/request.rs:127-142 -> rspaxos/durability.rs:101-118 -> rspaxos/messages.rs:395-465, with NVLink stores in
+ * place of TransportHub messages).  Waits are bounded (2 s): on time-out bit 0 of ss_ctx_device_status is set and the
+ * kernel proceeds.  n_wait, n_signal <= 32; either part may be empty; a NULL ss_step_sync means no ordering. */
+typedef struct ss_step_sync {
+    const uint64_t *wait_flags;
+    uint32_t n_wait;
+    uint64_t wait_value;
+    uint64_t *const *signal_flags;
+    uint32_t n_signal;
+    uint64_t signal_value;
+} ss_step_sync;
+/* reads (and clears) the context's device status word; synchronises the context's stream */
+#define SS_DEV_STATUS_FLAG_TIMEOUT 1u
+int ss_ctx_device_status(ss_ctx *ctx, uint32_t *status);
+
 /* Fused encode + tally + REPLICATE (the multi-GPU accept step): as ss_accept_step_fused_dev, but shard j of the
  * local groups (data shards included) is written to shard_planes[j] + g*shard_stride, where each shard_planes[j]
  * is a device pointer into LOCAL memory or into a PEER GPU's memory (ss_ipc_open): the encode kernel itself
  * delivers every replica's shard over NVLink -- no pack pass, no separate collective.  shard_planes is a HOST
  * array of d+p pointers; every target slot is 16-byte aligned with capacity round_up(L,16).  RS(3,2) with
- * 16-byte-aligned uniform payloads only (SS_ERR_UNSUPPORTED otherwise). */
+ * 16-byte-aligned uniform payloads only (SS_ERR_UNSUPPORTED otherwise).  sync (may be NULL): the tally waits for
+ * sync->wait_flags (the followers' ack flags) and the followers are signalled when every shard has landed. */
 int ss_accept_step_replicate_dev(ss_rs_coder *coder, const uint8_t *data, uint64_t data_stride, uint32_t data_len,
                                  uint64_t n_groups, uint8_t *const *shard_planes, uint64_t shard_stride,
                                  const uint64_t *planes, uint32_t n_replicas, uint32_t threshold,
-                                 uint64_t *committed, uint32_t *commit_bar);
+                                 uint64_t *committed, uint32_t *commit_bar, const ss_step_sync *sync);
+
+/* Host-buffer form of the fused accept step (the call a host without device-resident state makes): payloads, ack
+ * planes, parity planes, commit words and commit_bar are HOST arrays with the layouts of ss_accept_step_fused_dev;
+ * chunks of groups are uploaded, run through the ONE fused kernel and downloaded with copy and compute overlapped
+ * (three staging buffers on separate copy streams).  Returns when every result is in host memory.  Pinned host
+ * buffers (ss_host_alloc) are needed for the overlap. */
+int ss_accept_step_fused(ss_rs_coder *coder, const uint8_t *data, uint64_t data_stride, uint32_t data_len,
+                         uint64_t n_groups, uint8_t *parity, uint64_t plane_stride, uint64_t shard_stride,
+                         const uint64_t *planes, uint32_t n_replicas, uint32_t threshold, uint64_t *committed,
+                         uint32_t *commit_bar);
+
+/* The simulated followers' side of the step (rspaxos/durability.rs:101-118: log the Accept, reply): once the leaders'
+ * shards have landed (sync->wait_flags), ack plane r -- ack_src[r*n_groups .. +n_groups), this GPU's followers' ack
+ * bits for the groups they follow -- is stored to ack_dst[r] (n_groups words in the leader GPU's memory, local or
+ * peer; a NULL entry is skipped), then the leaders are signalled.  ack_dst is a HOST array of n_replicas pointers. */
+int ss_follower_ack_dev(ss_ctx *ctx, const uint64_t *ack_src, uint64_t *const *ack_dst, uint32_t n_replicas,
+                        uint64_t n_groups, const ss_step_sync *sync);
 
 /* Crossword encode + distribute (BASELINE config 4; crossword/request.rs:82-87,137-185): RS(3,2)-encodes a
  * ragged batch and writes, for every codeword g, the spr[g] shards the balanced round-robin assignment gives

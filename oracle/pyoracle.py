@@ -170,6 +170,17 @@ def rs_reconstruct_batch(d: int, p: int, shards: np.ndarray, plane_stride: int, 
     return status
 
 
+MODE_STATIC = 0x100     # SSOR_MODE_STATIC: contiguous block of codewords per OpenMP thread
+
+
+def first_touch_fill(buf: np.ndarray, n_items: int, item_bytes: int, item_stride: int, seed: int, zero: bool,
+                     threads: int) -> None:
+    """Fill (or zero) buf in the static thread partition the encode loop uses, so pages are placed NUMA-locally."""
+    assert buf.dtype == np.uint8 and buf.flags.c_contiguous and buf.size >= (n_items - 1) * item_stride + item_bytes
+    lib().ssor_first_touch_fill(_p(buf), C.c_uint64(n_items), C.c_uint64(item_bytes), C.c_uint64(item_stride),
+                                C.c_uint64(seed), 1 if zero else 0, threads)
+
+
 def have_avx2() -> bool:
     return bool(lib().ssor_have_avx2())
 

@@ -334,18 +334,20 @@ int ssor_rs_encode_batch(int d, int p, const uint8_t *data, const uint64_t *data
                          uint64_t plane_stride, const uint64_t *par_off, int mode, int threads) {
     int rc = rs_check_dp(d, p);
     if (rc) return rc;
-    mode = resolve_mode(mode);
+    const int sched_static = mode & SSOR_MODE_STATIC;     /* contiguous block of codewords per thread (NUMA first-touch) */
+    mode = resolve_mode(mode & 0xff);
     uint8_t *m = (uint8_t *)malloc((size_t)(d + p) * d);
     ssor_rs_build_matrix(d, p, m);
     const uint8_t *prow = m + (size_t)d * d;
 #ifdef _OPENMP
     if (threads <= 0) threads = omp_get_max_threads();
+    if (sched_static) omp_set_schedule(omp_sched_static, 0); else omp_set_schedule(omp_sched_dynamic, 256);
 #pragma omp parallel num_threads(threads)
 #endif
     {
         uint8_t *tail = NULL; size_t tail_cap = 0;
 #ifdef _OPENMP
-#pragma omp for schedule(dynamic, 256)
+#pragma omp for schedule(runtime)
 #endif
         for (uint64_t g = 0; g < n; g++) {
             size_t len = data_len[g];
@@ -373,6 +375,28 @@ int ssor_rs_encode_batch(int d, int p, const uint8_t *data, const uint64_t *data
     }
     free(m);
     return SSOR_OK;
+}
+
+/* Fills n_items items of item_bytes bytes (item g at buf + g*item_stride) with a seeded byte stream, in the SAME
+ * static thread partition SSOR_MODE_STATIC uses for the encode loop, so that on a NUMA host every page is first
+ * touched -- hence placed -- on the node of the thread that will later read or write it.  Benchmark plumbing. */
+void ssor_first_touch_fill(uint8_t *buf, uint64_t n_items, uint64_t item_bytes, uint64_t item_stride,
+                           uint64_t seed, int zero, int threads) {
+#ifdef _OPENMP
+    if (threads <= 0) threads = omp_get_max_threads();
+#pragma omp parallel for schedule(static) num_threads(threads)
+#endif
+    for (uint64_t g = 0; g < n_items; g++) {
+        uint8_t *q = buf + g * item_stride;
+        if (zero) { memset(q, 0, item_bytes); continue; }
+        uint64_t x = seed ^ (g * 0x9E3779B97F4A7C15ull + 0xD1B54A32D192ED03ull);
+        uint64_t i = 0;
+        for (; i + 8 <= item_bytes; i += 8) {
+            x ^= x << 13; x ^= x >> 7; x ^= x << 17;       /* xorshift64 */
+            memcpy(q + i, &x, 8);
+        }
+        for (; i < item_bytes; i++) { x ^= x << 13; x ^= x >> 7; x ^= x << 17; q[i] = (uint8_t)x; }
+    }
 }
 
 int ssor_rs_reconstruct_batch(int d, int p, uint8_t *shards, uint64_t plane_stride,

@@ -89,7 +89,9 @@ void ssor_cw_split(const uint8_t *data, size_t data_len, int d, uint8_t *out);
  * parity shard j of codeword g is written to parity[j*plane_stride + par_off[g] .. +L_g).
  * mode: 0 = scalar MUL_TABLE loops (crate default), 1 = AVX2 vpshufb nibble tables
  * (what the crate's simd-accel gives), falls back to 0 if the CPU lacks AVX2.
- * threads: OpenMP threads (<=0: all). */
+ * threads: OpenMP threads (<=0: all).  mode | SSOR_MODE_STATIC: one contiguous block of codewords per thread
+ * instead of dynamic chunks of 256 (uniform batches on NUMA hosts: see ssor_first_touch_fill). */
+#define SSOR_MODE_STATIC 0x100
 int ssor_rs_encode_batch(int d, int p, const uint8_t *data, const uint64_t *data_off,
                          const uint32_t *data_len, uint64_t n, uint8_t *parity,
                          uint64_t plane_stride, const uint64_t *par_off, int mode, int threads);
@@ -100,6 +102,8 @@ int ssor_rs_reconstruct_batch(int d, int p, uint8_t *shards, uint64_t plane_stri
                               const uint64_t *off, const uint32_t *data_len,
                               const uint32_t *present, uint64_t n, int data_only,
                               int32_t *status, int mode, int threads);
+void ssor_first_touch_fill(uint8_t *buf, uint64_t n_items, uint64_t item_bytes, uint64_t item_stride,
+                           uint64_t seed, int zero, int threads);
 int ssor_have_avx2(void);
 int ssor_max_threads(void);
 

@@ -58,7 +58,9 @@ SIGNATURES = {
     "ss_ipc_export": (_i, [_vp, _vp, _vp]),
     "ss_ipc_open": (_i, [_vp, _vp, C.POINTER(_vp)]),
     "ss_ipc_close": (_i, [_vp, _vp]),
-    "ss_accept_step_replicate_dev": (_i, [_vp, _vp, _u64, _u32, _u64, C.POINTER(_vp), _u64, _vp, _u32, _u32, _vp, _vp]),
+    "ss_accept_step_replicate_dev": (_i, [_vp, _vp, _u64, _u32, _u64, C.POINTER(_vp), _u64, _vp, _u32, _u32, _vp, _vp, _vp]),
+    "ss_follower_ack_dev": (_i, [_vp, _vp, C.POINTER(_vp), _u32, _u64, _vp]),
+    "ss_ctx_device_status": (_i, [_vp, C.POINTER(_u32)]),
     "ss_rs_coder_create": (_i, [_vp, _i, _i, C.POINTER(_vp)]),
     "ss_rs_coder_destroy": (_i, [_vp]),
     "ss_rs_data_shard_count": (_i, [_vp]),
@@ -85,9 +87,16 @@ SIGNATURES = {
     "ss_raft_kth_match_dev": (_i, [_vp, _vp, _u32, _u64, _u32, _vp]),
     "ss_prepare_merge_dev": (_i, [_vp, _vp, _vp, _u32, _u64, _vp, _u32, _u32, _u32, _vp, _vp, _vp]),
     "ss_accept_step_fused_dev": (_i, [_vp, _vp, _u64, _u32, _u64, _vp, _u64, _u64, _u32, _vp, _u32, _u32, _vp, _vp]),
+    "ss_accept_step_fused": (_i, [_vp, _vp, _u64, _u32, _u64, _vp, _u64, _u64, _vp, _u32, _u32, _vp, _vp]),
     "ss_rs_set_variant": (_i, [_vp, _i]),
     "ss_rs_last_kernel": (C.c_char_p, [_vp]),
 }
+
+
+class StepSync(C.Structure):
+    """ss_step_sync (include/summerset_b200.h): device-side wait / signal flags of one multi-GPU step call."""
+    _fields_ = [("wait_flags", C.c_void_p), ("n_wait", C.c_uint32), ("wait_value", C.c_uint64),
+                ("signal_flags", C.POINTER(C.c_void_p)), ("n_signal", C.c_uint32), ("signal_value", C.c_uint64)]
 
 
 class SummersetError(RuntimeError):

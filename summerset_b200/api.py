@@ -98,6 +98,19 @@ class Context:
     def copy_d2d(self, dst_ptr: int, src_ptr: int, nbytes: int) -> None:
         check(self.lib.ss_copy_d2d(self.h, dst_ptr, src_ptr, nbytes))
 
+    def device_status(self) -> int:
+        """Reads and clears the device status word (bit 0: a step-flag wait timed out); synchronises the stream."""
+        st = C.c_uint32(0)
+        check(self.lib.ss_ctx_device_status(self.h, C.byref(st)))
+        return int(st.value)
+
+    def follower_ack(self, ack_src: torch.Tensor, ack_dst: Sequence[int], sync: Optional["StepSync"] = None) -> None:
+        """ack_src int64 [R, G] on the GPU; ack_dst: R raw device pointers (0 = skip) into the leaders' ack buffers."""
+        assert ack_src.is_cuda and ack_src.dtype == torch.int64 and ack_src.is_contiguous() and ack_src.dim() == 2
+        R, G = ack_src.shape
+        arr = (C.c_void_p * R)(*[p if p else None for p in ack_dst])
+        check(self.lib.ss_follower_ack_dev(self.h, _ptr(ack_src), arr, R, G, C.byref(sync.c) if sync else None))
+
     # ---- tallies -------------------------------------------------------------------------------
     def tally_planes(self, planes: torch.Tensor, threshold: int, want_bar: bool = True,
                      committed: Optional[torch.Tensor] = None, commit_bar: Optional[torch.Tensor] = None):
@@ -168,6 +181,17 @@ class Context:
         check(self.lib.ss_raft_commit_scan_dev(self.h, _ptr(match), P, G, _ptr(last_commit), _ptr(log_end),
                                                _ptr(curr_term), _ptr(terms), W, threshold, _ptr(out), _ptr(window_overflow)))
         return out
+
+
+class StepSync:
+    """Host-side builder of an ss_step_sync: wait until every flag of `wait_flags` (a LOCAL device array of n_wait u64
+    counters) is >= wait_value, and store signal_value to each pointer of `signal_ptrs` (local or peer) afterwards."""
+
+    def __init__(self, wait_flags_ptr: int = 0, n_wait: int = 0, wait_value: int = 0,
+                 signal_ptrs: Sequence[int] = (), signal_value: int = 0):
+        self._sig = (C.c_void_p * max(1, len(signal_ptrs)))(*signal_ptrs)
+        self.c = _lib.StepSync(C.c_void_p(wait_flags_ptr or None), n_wait, max(0, wait_value),
+                               C.cast(self._sig, C.POINTER(C.c_void_p)), len(signal_ptrs), signal_value)
 
 
 def _ctx_extras():
@@ -402,14 +426,15 @@ class ReedSolomon:
 
     def accept_step_replicate(self, data: torch.Tensor, data_len: int, shard_planes: Sequence[int], shard_stride: int,
                               planes: Optional[torch.Tensor], threshold: int, committed: Optional[torch.Tensor],
-                              commit_bar: Optional[torch.Tensor]) -> None:
+                              commit_bar: Optional[torch.Tensor], sync: Optional["StepSync"] = None) -> None:
         """Multi-GPU accept step: encode + tally + write every shard plane to its (local or peer) destination.
-        shard_planes: d+p raw device pointers (ints)."""
+        shard_planes: d+p raw device pointers (ints).  sync: step flags (tally waits, followers are signalled)."""
         arr = (C.c_void_p * len(shard_planes))(*shard_planes)
         n = data.shape[0]
         R = planes.shape[0] if planes is not None else 0
         check(self.lib.ss_accept_step_replicate_dev(self.h, _ptr(data), data.shape[1], data_len, n, arr, shard_stride,
-                                                    _ptr(planes), R, threshold, _ptr(committed), _ptr(commit_bar)))
+                                                    _ptr(planes), R, threshold, _ptr(committed), _ptr(commit_bar),
+                                                    C.byref(sync.c) if sync else None))
 
     def crossword_distribute(self, data: torch.Tensor, data_off: torch.Tensor, data_len: torch.Tensor, spr: torch.Tensor,
                              rep_off: torch.Tensor, replica_logs: Sequence[int]) -> None:
@@ -418,6 +443,20 @@ class ReedSolomon:
         arr = (C.c_void_p * 5)(*replica_logs)
         check(self.lib.ss_crossword_distribute_dev(self.h, _ptr(data), _ptr(data_off), _ptr(data_len), _ptr(spr),
                                                    _ptr(rep_off), data_len.numel(), arr))
+
+    def accept_step_fused_host(self, data: np.ndarray, data_len: int, parity: np.ndarray, planes: np.ndarray,
+                               threshold: int, committed: np.ndarray, commit_bar: Optional[np.ndarray]) -> None:
+        """HOST buffers through ss_accept_step_fused: data uint8 [n, stride]; parity uint8 [p, n, shard_stride];
+        planes uint64 [R, n]; committed uint64 [n]; commit_bar uint32 [n] or None."""
+        assert data.dtype == np.uint8 and parity.dtype == np.uint8 and data.flags.c_contiguous and parity.flags.c_contiguous
+        assert planes.dtype == np.uint64 and planes.flags.c_contiguous and committed.dtype == np.uint64
+        n, stride = data.shape
+        p, n2, ss = parity.shape
+        R, G = planes.shape
+        assert p == self.p and n2 == n and G == n and committed.shape == (n,)
+        check(self.lib.ss_accept_step_fused(self.h, data.ctypes.data, stride, data_len, n, parity.ctypes.data, n * ss, ss,
+                                            planes.ctypes.data, R, threshold, committed.ctypes.data,
+                                            commit_bar.ctypes.data if commit_bar is not None else None))
 
     def encode_uniform_host(self, data: np.ndarray, data_len: int, parity: np.ndarray) -> None:
         """HOST buffers through ss_rs_encode_uniform: data uint8 [n, stride]; parity uint8 [p, n, shard_stride]."""

@@ -198,6 +198,20 @@ static int check_shard_args(const ss_rs_coder *c, const void *shards, size_t n_s
     return SS_OK;
 }
 
+// validates the wait half of an ss_step_sync and turns it into the kernels' argument
+int make_flag_wait(ss_ctx *ctx, const ss_step_sync *sync, dev::FlagWait *out) {
+    *out = dev::FlagWait{nullptr, 0, 0, 0, nullptr};
+    if (sync == nullptr) return SS_OK;
+    if (sync->n_wait > 32 || sync->n_signal > 32) return set_error(SS_ERR_INVALID_ARG, "at most 32 wait / signal flags");
+    if (sync->n_wait != 0 && sync->wait_flags == nullptr) return set_error(SS_ERR_INVALID_ARG, "null wait_flags");
+    if (sync->n_signal != 0 && sync->signal_flags == nullptr) return set_error(SS_ERR_INVALID_ARG, "null signal_flags");
+    if (sync->n_wait == 0 || sync->wait_value == 0) return SS_OK;        // counters start at 0: nothing to wait for
+    out->flags = sync->wait_flags; out->n = sync->n_wait; out->value = sync->wait_value;
+    out->timeout_ns = 2000000000ull;
+    out->status = ctx->dev_status;
+    return SS_OK;
+}
+
 // frees everything the context owns; only called once no coder / engine handle refers to it any more
 static void ctx_teardown(ss_ctx *ctx) {
     cudaSetDevice(ctx->device);
@@ -218,6 +232,7 @@ static void ctx_teardown(ss_ctx *ctx) {
         if (ctx->stage_out[i]) cudaFree(ctx->stage_out[i]);
     }
     if (ctx->scratch) cudaFree(ctx->scratch);
+    if (ctx->dev_status) cudaFree(ctx->dev_status);
     if (ctx->owns_stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -293,6 +308,13 @@ static int ctx_create_common(int device, void *stream, bool borrow, ss_ctx **out
         e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
         if (e != cudaSuccess) { delete ctx; return cuda_error(e, "cudaStreamCreateWithFlags", __FILE__, __LINE__); }
         ctx->owns_stream = true;
+    }
+    e = cudaMalloc(reinterpret_cast<void **>(&ctx->dev_status), 256);
+    if (e == cudaSuccess) e = cudaMemset(ctx->dev_status, 0, 256);
+    if (e != cudaSuccess) {
+        if (ctx->owns_stream) cudaStreamDestroy(ctx->stream);
+        delete ctx;
+        return cuda_error(e, "allocate device status word", __FILE__, __LINE__);
     }
     *out = ctx;
     return SS_OK;
@@ -666,7 +688,7 @@ int ss_accept_step_fused_dev(ss_rs_coder *c, const uint8_t *data, uint64_t data_
 int ss_accept_step_replicate_dev(ss_rs_coder *c, const uint8_t *data, uint64_t data_stride, uint32_t data_len,
                                  uint64_t n_groups, uint8_t *const *shard_planes, uint64_t shard_stride,
                                  const uint64_t *planes, uint32_t n_replicas, uint32_t threshold,
-                                 uint64_t *committed, uint32_t *commit_bar) {
+                                 uint64_t *committed, uint32_t *commit_bar, const ss_step_sync *sync) {
     if (c == nullptr) return set_error(SS_ERR_INVALID_ARG, "null coder");
     if (n_groups == 0) return SS_OK;
     if (!data || !shard_planes) return set_error(SS_ERR_INVALID_ARG, "null buffer");
@@ -683,6 +705,7 @@ int ss_accept_step_replicate_dev(ss_rs_coder *c, const uint8_t *data, uint64_t d
     g.parity = shard_planes[3]; g.plane_stride = 16; g.shard_stride = shard_stride; g.n = n_groups;
     g.flags = SS_RS_OUT_PADDED16 | SS_RS_EMIT_DATA;
     g.planes5 = shard_planes;
+    SS_TRY(make_flag_wait(c->ctx, sync, &g.wait));
     TallyArgs t;
     const bool with_tally = planes != nullptr;
     if (with_tally) {
@@ -695,47 +718,81 @@ int ss_accept_step_replicate_dev(ss_rs_coder *c, const uint8_t *data, uint64_t d
     if ((c->variant & 15) == 1) c->variant &= ~15;     // the flat kernel has no peer-plane mode
     const int rc = launch_rs_encode(c, g, with_tally ? &t : nullptr);
     c->variant = saved;
-    return rc;
+    if (rc != SS_OK) return rc;
+    return launch_flag_signal(c->ctx, sync);
 }
 
-// ---- host-buffer batch encode: chunked, copy/compute overlapped -----------------------------------
-int ss_rs_encode_uniform(ss_rs_coder *c, const uint8_t *data, uint64_t data_stride, uint32_t data_len, uint64_t n,
-                         uint8_t *parity, uint64_t plane_stride, uint64_t shard_stride) {
-    if (c == nullptr) return set_error(SS_ERR_INVALID_ARG, "null coder");
-    if (n == 0 || data_len == 0) return SS_OK;
-    if (!data || !parity) return set_error(SS_ERR_INVALID_ARG, "null buffer");
+int ss_follower_ack_dev(ss_ctx *ctx, const uint64_t *ack_src, uint64_t *const *ack_dst, uint32_t R, uint64_t G,
+                        const ss_step_sync *sync) {
+    if (ctx == nullptr) return set_error(SS_ERR_INVALID_ARG, "null context");
+    if (!ack_src || !ack_dst) return set_error(SS_ERR_INVALID_ARG, "null buffer");
+    if (R == 0 || R > 16) return set_error(SS_ERR_INVALID_ARG, "n_replicas must be 1..16");
+    dev::FlagWait w;
+    SS_TRY(make_flag_wait(ctx, sync, &w));
+    SS_TRY(launch_follower_ack(ctx, ack_src, ack_dst, R, G, w));
+    return launch_flag_signal(ctx, sync);
+}
+
+int ss_ctx_device_status(ss_ctx *ctx, uint32_t *status) {
+    SS_TRY(ctx_bind(ctx));
+    if (status == nullptr) return set_error(SS_ERR_INVALID_ARG, "null status pointer");
+    SS_CUDA(cudaMemcpyAsync(status, ctx->dev_status, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    SS_CUDA(cudaMemsetAsync(ctx->dev_status, 0, sizeof(uint32_t), ctx->stream));
+    SS_CUDA(cudaStreamSynchronize(ctx->stream));
+    return SS_OK;
+}
+
+// ---- host-buffer batch encode (+ optional fused tally): chunked, copy/compute overlapped -----------------
+// Per chunk of C codewords: H2D of the payloads (and of the chunk's R ack-plane slices) on the copy-in stream, ONE
+// fused kernel on the context's stream, D2H of the parity slices (and commit words / commit_bar) on the copy-out
+// stream; three staging buffers deep, so chunk k+1 uploads and chunk k-1 downloads while chunk k computes.
+static int encode_uniform_host(ss_rs_coder *c, const uint8_t *data, uint64_t data_stride, uint32_t data_len, uint64_t n,
+                               uint8_t *parity, uint64_t plane_stride, uint64_t shard_stride, const uint64_t *planes,
+                               uint32_t R, uint32_t threshold, uint64_t *committed, uint32_t *commit_bar) {
     ss_ctx *ctx = c->ctx;
     SS_TRY(ctx_bind(ctx));
     const int d = c->d, p = c->p;
+    const bool tally = planes != nullptr;
     const uint64_t L = (uint64_t(data_len) + d - 1) / d, ds = (L + 15) & ~uint64_t(15);
     if (data_stride < data_len || shard_stride < L) return set_error(SS_ERR_INVALID_ARG, "stride shorter than element");
     // chunk: 16 MiB of payload measured best (profiles/r01_pcie_probe.txt); SS_E2E_CHUNK_MB overrides, for tuning
     uint64_t chunk_mb = 16;
     if (const char *e = getenv("SS_E2E_CHUNK_MB")) { const long v = atol(e); if (v >= 1 && v <= 4096) chunk_mb = static_cast<uint64_t>(v); }
     uint64_t C = (chunk_mb << 20) / data_stride;
-    if (C < 1) C = 1;
+    if (C < 2) C = 2;
+    C &= ~uint64_t(1);                      // even: the chunk's ack-plane slices stay 16-byte aligned
     if (C > n) C = n;
     const uint64_t in_stride_dev = (data_stride + 15) & ~uint64_t(15);
     const bool in_contig = (in_stride_dev == data_stride);
-    SS_TRY(pipeline_staging(ctx, C * in_stride_dev + 256, uint64_t(p) * C * ds));
+    const uint64_t in_pay = (C * in_stride_dev + 256 + 255) & ~uint64_t(255);
+    const uint64_t out_par = (uint64_t(p) * C * ds + 255) & ~uint64_t(255);
+    const uint64_t out_cm = (C * 8 + 255) & ~uint64_t(255);
+    SS_TRY(pipeline_staging(ctx, in_pay + (tally ? uint64_t(R) * C * 8 : 0), out_par + (tally ? out_cm + C * 4 : 0)));
     const uint64_t nchunks = (n + C - 1) / C;
     for (uint64_t k = 0; k < nchunks; ++k) {
         const int b = static_cast<int>(k % ss_ctx::kStages);
         const uint64_t g0 = k * C, nc = (n - g0) < C ? (n - g0) : C;
         uint8_t *din = static_cast<uint8_t *>(ctx->stage_in[b]);
         uint8_t *dout = static_cast<uint8_t *>(ctx->stage_out[b]);
+        uint64_t *dpl = reinterpret_cast<uint64_t *>(din + in_pay);
+        uint64_t *dcm = reinterpret_cast<uint64_t *>(dout + out_par);
+        uint32_t *dbar = reinterpret_cast<uint32_t *>(dout + out_par + out_cm);
         if (k >= ss_ctx::kStages) SS_CUDA(cudaStreamWaitEvent(ctx->h2d_stream, ctx->ev_done[b], 0));
         if (in_contig)
             SS_CUDA(cudaMemcpyAsync(din, data + g0 * data_stride, nc * data_stride, cudaMemcpyHostToDevice, ctx->h2d_stream));
         else
             SS_CUDA(cudaMemcpy2DAsync(din, in_stride_dev, data + g0 * data_stride, data_stride, data_len, nc,
                                       cudaMemcpyHostToDevice, ctx->h2d_stream));
+        if (tally)      // R slices of nc words, packed as planes[r*nc + g] on the device
+            SS_CUDA(cudaMemcpy2DAsync(dpl, nc * 8, planes + g0, n * 8, nc * 8, R, cudaMemcpyHostToDevice, ctx->h2d_stream));
         SS_CUDA(cudaEventRecord(ctx->ev_h2d[b], ctx->h2d_stream));
         SS_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_h2d[b], 0));
         EncGeom g{};
         g.data = din; g.data_off = nullptr; g.data_stride = in_stride_dev; g.uni_len = data_len; g.parity = dout;
         g.plane_stride = C * ds; g.shard_stride = ds; g.n = nc; g.flags = SS_RS_OUT_PADDED16;
-        SS_TRY(launch_rs_encode(c, g, nullptr));
+        TallyArgs t;
+        if (tally) { t.planes = dpl; t.R = R; t.threshold = threshold; t.G = nc; t.committed = dcm; t.commit_bar = commit_bar ? dbar : nullptr; }
+        SS_TRY(launch_rs_encode(c, g, tally ? &t : nullptr));
         SS_CUDA(cudaEventRecord(ctx->ev_kernel[b], ctx->stream));
         SS_CUDA(cudaStreamWaitEvent(ctx->d2h_stream, ctx->ev_kernel[b], 0));
         for (int j = 0; j < p; ++j) {
@@ -746,11 +803,36 @@ int ss_rs_encode_uniform(ss_rs_coder *c, const uint8_t *data, uint64_t data_stri
             else
                 SS_CUDA(cudaMemcpy2DAsync(hdst, shard_stride, dsrc, ds, L, nc, cudaMemcpyDeviceToHost, ctx->d2h_stream));
         }
+        if (tally) {
+            SS_CUDA(cudaMemcpyAsync(committed + g0, dcm, nc * 8, cudaMemcpyDeviceToHost, ctx->d2h_stream));
+            if (commit_bar) SS_CUDA(cudaMemcpyAsync(commit_bar + g0, dbar, nc * 4, cudaMemcpyDeviceToHost, ctx->d2h_stream));
+        }
         SS_CUDA(cudaEventRecord(ctx->ev_done[b], ctx->d2h_stream));
     }
     SS_CUDA(cudaStreamSynchronize(ctx->d2h_stream));
     SS_CUDA(cudaStreamSynchronize(ctx->stream));
     return SS_OK;
+}
+
+int ss_rs_encode_uniform(ss_rs_coder *c, const uint8_t *data, uint64_t data_stride, uint32_t data_len, uint64_t n,
+                         uint8_t *parity, uint64_t plane_stride, uint64_t shard_stride) {
+    if (c == nullptr) return set_error(SS_ERR_INVALID_ARG, "null coder");
+    if (n == 0 || data_len == 0) return SS_OK;
+    if (!data || !parity) return set_error(SS_ERR_INVALID_ARG, "null buffer");
+    return encode_uniform_host(c, data, data_stride, data_len, n, parity, plane_stride, shard_stride, nullptr, 0, 0, nullptr,
+                               nullptr);
+}
+
+int ss_accept_step_fused(ss_rs_coder *c, const uint8_t *data, uint64_t data_stride, uint32_t data_len, uint64_t n_groups,
+                         uint8_t *parity, uint64_t plane_stride, uint64_t shard_stride, const uint64_t *planes,
+                         uint32_t n_replicas, uint32_t threshold, uint64_t *committed, uint32_t *commit_bar) {
+    if (c == nullptr) return set_error(SS_ERR_INVALID_ARG, "null coder");
+    if (n_groups == 0) return SS_OK;
+    if (!data || !parity || !planes || !committed) return set_error(SS_ERR_INVALID_ARG, "null buffer");
+    if (data_len == 0) return set_error(SS_ERR_INVALID_ARG, "null codewords cannot be encoded");
+    if (n_replicas == 0 || n_replicas > 16) return set_error(SS_ERR_INVALID_ARG, "n_replicas must be 1..16");
+    return encode_uniform_host(c, data, data_stride, data_len, n_groups, parity, plane_stride, shard_stride, planes, n_replicas,
+                               threshold, committed, commit_bar);
 }
 
 // ---- tallies ----------------------------------------------------------------------------------------

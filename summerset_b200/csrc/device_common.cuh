@@ -137,6 +137,43 @@ __device__ __forceinline__ void store16(uint8_t *p, uint4 v, int nvalid, bool pa
         if (b < nb) p[b] = static_cast<uint8_t>(w[b >> 2] >> (8 * (b & 3)));
 }
 
+// ---- cross-GPU step flags (multi-GPU accept step) -------------------------------
+// A flag is a u64 step counter in some GPU's memory.  Producers publish with st.release.sys after their data
+// stores are visible system-wide; consumers poll with ld.acquire.sys.  Waits are bounded: on time-out bit 0 of the
+// context's device status word is set and the kernel carries on (a wrong result that the host can see, not a hang).
+__device__ __forceinline__ uint64_t ld_acquire_sys(const uint64_t *p) {
+    uint64_t v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_sys(uint64_t *p, uint64_t v) {
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ uint64_t globaltimer_ns() {
+    uint64_t t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+struct FlagWait {
+    const uint64_t *flags;    // n counters in LOCAL memory (written by peers), nullptr: no wait
+    uint32_t n;               // <= 32
+    uint64_t value;           // proceed once every flags[i] >= value
+    uint64_t timeout_ns;
+    uint32_t *status;         // context's device status word
+};
+// the first n threads of the CTA poll one flag each, then the CTA barrier releases everybody
+__device__ __forceinline__ void cta_wait_flags(const FlagWait &w) {
+    if (w.flags == nullptr) return;
+    if (threadIdx.x < w.n) {
+        const uint64_t t0 = globaltimer_ns();
+        while (ld_acquire_sys(w.flags + threadIdx.x) < w.value) {
+            if (globaltimer_ns() - t0 > w.timeout_ns) { atomicOr(w.status, 1u); break; }
+            __nanosleep(100);
+        }
+    }
+    __syncthreads();
+}
+
 // ---- bit-sliced quorum tally of one 64-slot window ------------------------------------------
 // planes[r*G + g] holds replica r's ack bits for the 64 slots of group g.  The per-slot count of
 // set planes is kept bit-sliced in five 64-bit words (counts up to 31), then compared against the

@@ -172,6 +172,7 @@ struct Enc32Row {
     uint32_t R, threshold;
     uint64_t *committed;
     uint32_t *commit_bar;
+    dev::FlagWait wait;       // replicate mode: every CTA first waits for the followers' ack flags (flags == nullptr: no wait)
 };
 
 // bytes [s, s+16) of the 32-byte window {lo, hi}; s is kernel-uniform
@@ -307,6 +308,9 @@ __global__ void __launch_bounds__(MAXT, MINB) rs32_encode_row_kernel(const __gri
     const uint32_t lane = threadIdx.x & 31u, wid = threadIdx.x >> 5, nblk = blockDim.x >> 5;
     const uint32_t s1 = P.s1, s2 = P.s2;
     auto clamp16 = [](int64_t r) { return r > 16 ? 16 : (r < 0 ? 0 : static_cast<int>(r)); };
+
+    // replicate mode only: the ack planes tallied below are written by peer GPUs; wait for their step flags
+    if constexpr (EMIT) dev::cta_wait_flags(P.wait);
 
     // ---- fused tally: this CTA's contiguous slice of groups, coalesced (one pass, before the encode loop) ----
     if (P.planes != nullptr) {
@@ -1359,6 +1363,7 @@ int launch_rs_encode(ss_rs_coder *coder, const EncGeom &g, const TallyArgs *tall
                 Rw.planes = tally->planes; Rw.R = tally->R; Rw.threshold = tally->threshold;
                 Rw.committed = tally->committed; Rw.commit_bar = tally->commit_bar;
             }
+            Rw.wait = g.wait;
             const uint32_t threads = (vpc + 31u) & ~31u;
             // resident CTAs per SM (2048 threads, 32 CTAs) x a few waves; every CTA strides over codewords
             uint32_t per_sm = 2048u / threads; if (per_sm > 32u) per_sm = 32u;

@@ -9,6 +9,7 @@
 #include <vector>
 
 #include "../../include/summerset_b200.h"
+#include "device_common.cuh"
 
 namespace ssb {
 
@@ -84,6 +85,8 @@ struct ss_ctx {
     void *stage_in[kStages] = {};
     void *stage_out[kStages] = {};
     size_t stage_in_bytes = 0, stage_out_bytes = 0;
+    // device status word (bit 0: a step-flag wait timed out), allocated with the context
+    uint32_t *dev_status = nullptr;
 };
 
 struct ss_rs_coder {
@@ -133,6 +136,7 @@ struct EncGeom {
     uint64_t n;
     uint32_t flags;
     uint8_t *const *planes5 = nullptr;   // RS(3,2) replicate mode: 5 explicit plane bases (local or peer memory)
+    dev::FlagWait wait = {nullptr, 0, 0, 0, nullptr};   // replicate mode: flags to wait for before the tally
 };
 
 struct TallyArgs {              // optional fused tally
@@ -165,6 +169,12 @@ int launch_raft_scan(ss_ctx *ctx, const uint32_t *match, uint32_t n_peers, uint6
                      const uint32_t *last_commit, const uint32_t *log_end, const uint32_t *curr_term,
                      const uint32_t *terms, uint32_t window, uint32_t threshold, uint32_t *new_commit,
                      uint32_t *window_overflow);
+
+// multi-GPU step flags
+int make_flag_wait(ss_ctx *ctx, const ss_step_sync *sync, dev::FlagWait *out);
+int launch_flag_signal(ss_ctx *ctx, const ss_step_sync *sync);
+int launch_follower_ack(ss_ctx *ctx, const uint64_t *ack_src, uint64_t *const *ack_dst, uint32_t R, uint64_t G,
+                        const dev::FlagWait &wait);
 
 int launch_kth_match(ss_ctx *ctx, const uint32_t *match, uint32_t n_peers, uint64_t G, uint32_t k, uint32_t *out);
 int launch_prepare_merge(ss_ctx *ctx, const uint64_t *vote_bal, const uint32_t *vote_mask, uint32_t R, uint64_t N,

@@ -497,8 +497,84 @@ gossip_plan_kernel(uint32_t me, uint32_t population, uint32_t d, const uint8_t *
 }
 
 // ------------------------------------------------------------------------------------------------
+// multi-GPU step: flag signal + the simulated followers' ack
+// ------------------------------------------------------------------------------------------------
+struct SignalArgs {
+    uint64_t *flag[32];
+    uint32_t n;
+    uint64_t value;
+};
+// Launched right behind the kernel whose stores it publishes: a kernel boundary orders those stores (local and peer)
+// before this one, and each lane then releases one flag at system scope.
+__global__ void flag_signal_kernel(const __grid_constant__ SignalArgs A) {
+    if (threadIdx.x < A.n) {
+        __threadfence_system();
+        dev::st_release_sys(A.flag[threadIdx.x], A.value);
+    }
+}
+
+struct AckArgs {
+    const uint64_t *src;      // [R][G] local
+    uint64_t *dst[16];        // per replica: G words in the leader GPU's memory (local or peer), or nullptr
+    uint32_t R;
+    uint64_t G;
+    dev::FlagWait wait;
+};
+// rspaxos/durability.rs:101-118 for a whole batch: the follower has the shard in its log (the leader's kernel stored
+// it there), so it replies -- its ack bit-plane goes into the leader's ack buffer with plain (possibly NVLink) stores.
+__global__ void __launch_bounds__(kTallyThreads) follower_ack_kernel(const __grid_constant__ AckArgs A) {
+    dev::cta_wait_flags(A.wait);
+    const uint64_t G2 = A.G / 2;                       // 128-bit vectors (G even, checked on the host)
+    const uint64_t stride = static_cast<uint64_t>(gridDim.x) * kTallyThreads;
+    for (uint32_t r = 0; r < A.R; ++r) {
+        if (A.dst[r] == nullptr) continue;
+        const uint4 *s = reinterpret_cast<const uint4 *>(A.src + static_cast<uint64_t>(r) * A.G);
+        uint4 *d = reinterpret_cast<uint4 *>(A.dst[r]);
+        for (uint64_t i = static_cast<uint64_t>(blockIdx.x) * kTallyThreads + threadIdx.x; i < G2; i += stride)
+            dev::stg128_mode(d + i, dev::ldg128(s + i), 1u);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // host launchers
 // ------------------------------------------------------------------------------------------------
+int launch_flag_signal(ss_ctx *ctx, const ss_step_sync *sync) {
+    if (sync == nullptr || sync->n_signal == 0) return SS_OK;
+    SS_TRY(ctx_bind(ctx));
+    SignalArgs A;
+    A.n = sync->n_signal; A.value = sync->signal_value;
+    for (uint32_t i = 0; i < 32; ++i) A.flag[i] = i < A.n ? sync->signal_flags[i] : nullptr;
+    for (uint32_t i = 0; i < A.n; ++i)
+        if (A.flag[i] == nullptr || (reinterpret_cast<uintptr_t>(A.flag[i]) & 7u))
+            return set_error(SS_ERR_INVALID_ARG, "signal flag %u is null or not 8-byte aligned", i);
+    flag_signal_kernel<<<1, 32, 0, ctx->stream>>>(A);
+    SS_CUDA(cudaGetLastError());
+    ctx->launches++;
+    return SS_OK;
+}
+
+int launch_follower_ack(ss_ctx *ctx, const uint64_t *ack_src, uint64_t *const *ack_dst, uint32_t R, uint64_t G,
+                        const dev::FlagWait &wait) {
+    SS_TRY(ctx_bind(ctx));
+    if (G == 0) return SS_OK;
+    if ((G & 1ull) || (reinterpret_cast<uintptr_t>(ack_src) & 15u))
+        return set_error(SS_ERR_INVALID_ARG, "follower ack needs an even group count and 16-byte aligned planes");
+    AckArgs A;
+    A.src = ack_src; A.R = R; A.G = G; A.wait = wait;
+    for (uint32_t r = 0; r < 16; ++r) {
+        A.dst[r] = r < R ? ack_dst[r] : nullptr;
+        if (A.dst[r] != nullptr && (reinterpret_cast<uintptr_t>(A.dst[r]) & 15u))
+            return set_error(SS_ERR_INVALID_ARG, "ack destination %u is not 16-byte aligned", r);
+    }
+    uint64_t ctas = (G / 2 + kTallyThreads - 1) / kTallyThreads;
+    const uint64_t cap = static_cast<uint64_t>(ctx->sm_count) * 2ull;     // small, latency-bound: two CTAs per SM are plenty
+    if (ctas > cap) ctas = cap;
+    follower_ack_kernel<<<static_cast<uint32_t>(ctas), kTallyThreads, 0, ctx->stream>>>(A);
+    SS_CUDA(cudaGetLastError());
+    ctx->launches++;
+    return SS_OK;
+}
+
 static inline uint32_t stream_grid(ss_ctx *ctx, uint64_t items) {
     uint64_t ctas = (items + kTallyThreads - 1) / kTallyThreads;
     const uint64_t cap = static_cast<uint64_t>(ctx->sm_count) * 8ull * 4ull;
