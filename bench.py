@@ -33,11 +33,14 @@ from pathlib import Path
 ROOT = Path(__file__).resolve().parent
 sys.path.insert(0, str(ROOT))
 
-# The CPU arm's OpenMP team is pinned one thread per physical core; libgomp reads these when it is first loaded, so
-# they are set before anything imports it.  (torchrun's OMP_NUM_THREADS=1 does not matter: thread counts are passed
-# explicitly.)
-os.environ.setdefault("OMP_PROC_BIND", "close")
-os.environ.setdefault("OMP_PLACES", "cores")
+# The CPU arm's OpenMP team is pinned one thread per physical core; libgomp reads these when it is first loaded and
+# then also binds the INITIAL thread to the first place, so they are set only in the process that runs the CPU arm
+# (--impl reference; the GPU arm's cpu_baseline leg runs that in a subprocess).  torchrun's OMP_NUM_THREADS=1 does not
+# matter: thread counts are passed explicitly.
+FULL_AFFINITY = os.sched_getaffinity(0) if hasattr(os, "sched_getaffinity") else None
+if "reference" in sys.argv:
+    os.environ.setdefault("OMP_PROC_BIND", os.environ.get("SS_CPU_BIND", "close"))
+    os.environ.setdefault("OMP_PLACES", "cores")
 
 import numpy as np  # noqa: E402
 
@@ -196,7 +199,7 @@ class NumaPin:
     def __init__(self, torch, index: int):
         self.node, cpus = gpu_numa_cpus(torch, index)
         self.saved = os.sched_getaffinity(0) if hasattr(os, "sched_getaffinity") else None
-        self.cpus = (cpus & self.saved) if (cpus and self.saved) else None
+        self.cpus = (cpus & FULL_AFFINITY) if (cpus and FULL_AFFINITY) else None
 
     def __enter__(self):
         if self.cpus:
@@ -220,9 +223,11 @@ def cpu_arm(steps: int, warmup: int, n_cw: int, workload: str):
     construction: one thread per physical core (OMP_PLACES=cores, OMP_PROC_BIND=close), a static partition of the
     codewords, and every input / output page first touched by the thread that later encodes it."""
     from oracle import pyoracle as oracle
-    cpus = sorted(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else list(range(os.cpu_count() or 1))
+    cpus = sorted(FULL_AFFINITY) if FULL_AFFINITY else list(range(os.cpu_count() or 1))
     threads = physical_cores(cpus)
-    mode = (1 if oracle.have_avx2() else 0) | oracle.MODE_STATIC
+    if os.environ.get("SS_CPU_THREADS"):                 # tuning knobs (profiles/r02_cpu_arm_sweep.txt)
+        threads = int(os.environ["SS_CPU_THREADS"])
+    mode = (1 if oracle.have_avx2() else 0) | (0 if os.environ.get("SS_CPU_SCHED") == "dynamic" else oracle.MODE_STATIC)
     L = oracle.cw_shard_len(DATA_LEN, D)
     ds = (L + 15) // 16 * 16
     stride = (DATA_LEN + 15) // 16 * 16
@@ -594,10 +599,14 @@ def run_ours(args):
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
-        r = cpu_arm(5, 1, n, args.workload)
-        cpu = {"value": r["gbs"] if args.workload != "cfg2" else r["slots_per_s"], "unit": unit, "cores": r["threads"],
-               "hw_threads": r["hw_threads"], "kind": "port", "sample": r["sample"], "path": r["path"],
-               "min": r["gbs_min"], "max": r["gbs_max"], "slots_per_s": r["slots_per_s"]}
+        # the CPU arm in its own process (its OpenMP binding must not touch this one): the reference line's cpu_baseline
+        try:
+            out = subprocess.run([sys.executable, str(ROOT / "bench.py"), "--impl", "reference", "--steps", "5", "--warmup", "1",
+                                  "--workload", args.workload, "--groups", str(n), "--replicas", str(R)],
+                                 capture_output=True, text=True, timeout=600)
+            cpu = json.loads(out.stdout.strip().splitlines()[-1])["cpu_baseline"]
+        except Exception as ex:                         # reported, never silently dropped
+            cpu = {"value": None, "unit": unit, "cores": 0, "kind": "port", "sample": f"CPU arm failed: {ex!r}"}
 
     if rank == 0:
         line = {

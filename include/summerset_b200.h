@@ -369,6 +369,85 @@ int ss_gossip_plan_dev(ss_ctx *ctx, uint32_t me, uint32_t population, uint32_t d
                        const uint32_t *avail, const uint8_t *policy_idx, const uint32_t *policies_host,
                        uint32_t n_policies, uint32_t peer_alive, uint64_t n_instances, uint32_t *targets, uint32_t *excl);
 
+/* ---- batched multi-group consensus engine ----------------------------------------------------------------------
+ * The leader-side state of n_groups independent replica groups (64-slot instance window each) lives in HBM as a
+ * struct of arrays; the host drives all groups together, once per event-loop turn:
+ *   ss_engine_propose   one new instance per group at window position `slot`: RS-encode the request batches into the
+ *                       shard planes (per-peer packed send buffers) and enter Status::Accepting under the group's
+ *                       prepared ballot with an empty ack set   (multipaxos/request.rs:112-221,
+ *                       rspaxos/request.rs:72-142, crossword/request.rs:82-185)
+ *   ss_engine_ingest    a batch of AcceptReply records through handle_msg_accept_reply's filters
+ *                       (multipaxos/messages.rs:377-409, rspaxos/messages.rs:402-437, crossword/messages.rs:489-530)
+ *   ss_engine_tick      ONE kernel: commit decision of every Accepting instance (MultiPaxos quorum_cnt,
+ *                       multipaxos/messages.rs:412-413; RSPaxos majority + fault_tolerance, rspaxos/messages.rs:438-440;
+ *                       Crossword #acks >= majority && coverage_under_faults >= d, crossword/messages.rs:535-542),
+ *                       committed |= newly, accepting &= ~newly, commit_bar = committed prefix
+ *                       (multipaxos/durability.rs:161-170)
+ * Raft / CRaft engines keep match_slot / next_slot / log terms instead: ss_engine_raft_append (the leader appends
+ * entries in its term), ss_engine_raft_ingest (successful AppendEntriesReply, raft/messages.rs:243-252) and
+ * ss_engine_tick (commit scan raft/messages.rs:254-275,295 with quorum_cnt -- CRaft: majority + fault_tolerance,
+ * craft/messages.rs:300-308 -- and last_snap, raft/messages.rs:298-309).  Conflict replies, elections, heartbeats,
+ * durability and execution stay in the host's event loop (out of scope).
+ * All array arguments are DEVICE pointers; calls are asynchronous on the context's stream. */
+typedef struct ss_engine ss_engine;
+#define SS_PROTO_MULTIPAXOS 0u
+#define SS_PROTO_RSPAXOS 1u
+#define SS_PROTO_CROSSWORD 2u
+#define SS_PROTO_RAFT 3u
+#define SS_PROTO_CRAFT 4u
+typedef struct ss_engine_config {
+    uint32_t protocol;          /* SS_PROTO_* */
+    uint32_t population;        /* n <= 12 */
+    uint32_t fault_tolerance;   /* f <= n - majority (rspaxos/mod.rs:599-605); ignored by MultiPaxos / Raft */
+    uint32_t data_len;          /* bytes of every request batch (RS-coded protocols) */
+    uint32_t rs_total_shards;   /* Crossword: T (0 = n; must be a multiple of n, crossword/mod.rs:805-830) */
+    uint32_t rs_data_shards;    /* Crossword: d (0 = majority) */
+    uint32_t keep_slots;        /* depth of the shard store: proposals of slot s live in store s % keep_slots (0 = 1) */
+    uint32_t raft_window;       /* Raft: uncommitted-tail capacity per group, power of two (0 = 64) */
+} ss_engine_config;
+/* device pointers into the engine's state (valid until ss_engine_destroy), for hosts that read results in place or
+ * install state (recovery, tests).  Arrays a protocol does not use are NULL. */
+typedef struct ss_engine_view {
+    uint64_t n_groups;
+    uint32_t population, threshold, data_shards, total_shards, shard_len, shard_stride, raft_window, pad0;
+    uint64_t plane_stride;      /* bytes between shard planes of one proposal */
+    uint64_t slot_stride;       /* bytes between the shard stores of consecutive keep slots */
+    uint64_t *planes;           /* [n][G]  valid-ack bit-planes */
+    uint64_t *bal_prepared;     /* [G] */
+    uint64_t *inst_bal;         /* [G*64] */
+    uint64_t *accepting;        /* [G]  bit s = Status::Accepting */
+    uint64_t *committed;        /* [G]  bit s = Status::Committed */
+    uint32_t *commit_bar;       /* [G] */
+    uint8_t *shards;            /* [keep][T][G][shard_stride] */
+    uint8_t *policy_idx;        /* Crossword [G*64]: assignment policy of each instance */
+    uint32_t *match, *next_slot;/* Raft [n-1][G] */
+    uint32_t *last_commit, *log_end, *curr_term, *last_snap;   /* Raft [G] */
+    uint32_t *terms;            /* Raft [G][raft_window]: term of slot s at index s & (raft_window-1) */
+} ss_engine_view;
+int ss_engine_create(ss_ctx *ctx, const ss_engine_config *cfg, uint64_t n_groups, ss_engine **out);
+int ss_engine_destroy(ss_engine *engine);
+int ss_engine_view_get(ss_engine *engine, ss_engine_view *view);
+/* bal_prepared of every group (become_a_leader ... handle_msg_prepare_reply, outside this path) */
+int ss_engine_set_prepared_ballots(ss_engine *engine, const uint64_t *ballots);
+/* Crossword: the assignment policies instances may use (policies_host[k*n + r] = shard bitmask of replica r, as
+ * ss_tally_crossword_dev) and whether the balanced closed form applies (crossword/mod.rs:849-850) */
+int ss_engine_set_policies(ss_engine *engine, const uint32_t *policies_host, uint32_t n_policies, int balanced);
+/* payloads: request batch of group g at payloads + g*payload_stride (data_len bytes; NULL for MultiPaxos).  policy:
+ * Crossword only, [G] policy index of the new instance (NULL = 0).  *shard_planes (may be NULL) receives the base of
+ * this proposal's T shard planes: shard j of group g at base + j*plane_stride + g*shard_stride. */
+int ss_engine_propose(ss_engine *engine, uint32_t slot, const uint8_t *payloads, uint64_t payload_stride,
+                      const uint8_t *policy, uint8_t **shard_planes);
+int ss_engine_ingest(ss_engine *engine, const uint32_t *rec_group, const uint8_t *rec_slot, const uint8_t *rec_peer,
+                     const uint64_t *rec_ballot, uint64_t n_records);
+/* newly (may be NULL): [G] bit s = instance s committed in THIS tick (what the host logs as WalEntry::CommitSlot) */
+int ss_engine_tick(ss_engine *engine, uint64_t *newly);
+/* Raft: n_new[g] entries appended by the leader in curr_term[g]; exceeding raft_window uncommitted entries sets bit 1
+ * of ss_ctx_device_status and leaves that group unchanged */
+#define SS_DEV_STATUS_RAFT_WINDOW_FULL 2u
+int ss_engine_raft_append(ss_engine *engine, const uint32_t *n_new);
+int ss_engine_raft_ingest(ss_engine *engine, const uint32_t *rec_group, const uint8_t *rec_peer,
+                          const uint32_t *rec_end_slot, uint64_t n_records);
+
 /* ---- tuning / introspection (bench + tests) ------------------------------------------------ */
 /* Tuning knob for experiments (profiles/r01_row_kernel_sweep.txt); 0 = the measured-best defaults.
  *   bits 0-3  kernel choice / register budget: 1 = flat one-column-per-thread RS(3,2) kernel instead of the row kernel,

@@ -205,6 +205,37 @@ def tally_stream(rec_g, rec_s, rec_p, rec_b, S: int, population: int, threshold:
                             _p(np.ascontiguousarray(inst_bal, dtype=np.uint64)), _p(status), _p(acks))
 
 
+def tally_stream_crossword(rec_g, rec_s, rec_p, rec_b, S: int, population: int, T: int, d: int, majority: int, f: int,
+                           balanced: bool, policies: np.ndarray, policy_idx: np.ndarray, bal_prepared, inst_bal, status,
+                           acks) -> None:
+    """crossword/messages.rs:481-574 per record; policies uint32 [K, population], policy_idx uint8 [G*S]."""
+    rec_g = np.ascontiguousarray(rec_g, dtype=np.uint32)
+    rec_s = np.ascontiguousarray(rec_s, dtype=np.uint8)
+    rec_p = np.ascontiguousarray(rec_p, dtype=np.uint8)
+    rec_b = np.ascontiguousarray(rec_b, dtype=np.uint64)
+    policies = np.ascontiguousarray(policies, dtype=np.uint32)
+    policy_idx = np.ascontiguousarray(policy_idx, dtype=np.uint8)
+    assert status.dtype == np.uint8 and acks.dtype == np.uint16 and policies.shape[1] == population
+    lib().ssor_tally_stream_crossword(_p(rec_g), _p(rec_s), _p(rec_p), _p(rec_b), C.c_uint64(len(rec_g)), S, population, T, d,
+                                      majority, f, 1 if balanced else 0, _p(policies), policies.shape[0], _p(policy_idx),
+                                      _p(np.ascontiguousarray(bal_prepared, dtype=np.uint64)),
+                                      _p(np.ascontiguousarray(inst_bal, dtype=np.uint64)), _p(status), _p(acks))
+
+
+def raft_reply_stream(rec_g, rec_peer, rec_end, npeers: int, threshold: int, next_slot, match, last_commit, last_snap,
+                      log_end, curr_term, terms) -> None:
+    """raft/messages.rs:221-309 for successful replies, per record, in place on next_slot/match [P,G], last_commit, last_snap."""
+    rec_g = np.ascontiguousarray(rec_g, dtype=np.uint32)
+    rec_peer = np.ascontiguousarray(rec_peer, dtype=np.uint8)
+    rec_end = np.ascontiguousarray(rec_end, dtype=np.uint32)
+    G, W = terms.shape
+    for a in (next_slot, match, last_commit, last_snap, log_end, curr_term, terms):
+        assert a.dtype == np.uint32 and a.flags.c_contiguous
+    lib().ssor_raft_reply_stream(_p(rec_g), _p(rec_peer), _p(rec_end), C.c_uint64(len(rec_g)), npeers, threshold, C.c_uint64(G),
+                                 _p(next_slot), _p(match), _p(last_commit), _p(last_snap), _p(log_end), _p(curr_term),
+                                 _p(terms), W)
+
+
 def tally_planes(planes: np.ndarray, threshold: int, threads: int = 1):
     planes = np.ascontiguousarray(planes, dtype=np.uint64)
     R, G = planes.shape

@@ -454,6 +454,31 @@ void ssor_tally_stream(const uint32_t *rec_g, const uint8_t *rec_s, const uint8_
     }
 }
 
+/* crossword/messages.rs:481-574: the same handler with the Crossword commit condition.  The ack set is
+ * HashMap<peer, assignment[peer]>: a peer bitmask plus the instance's assignment (policies[policy_idx[k]]). */
+void ssor_tally_stream_crossword(const uint32_t *rec_g, const uint8_t *rec_s, const uint8_t *rec_p,
+                                 const uint64_t *rec_b, uint64_t n_rec, uint32_t S, uint32_t population,
+                                 uint32_t T, uint32_t d, uint32_t majority, uint32_t f, int balanced,
+                                 const uint32_t *policies, uint32_t n_policies, const uint8_t *policy_idx,
+                                 const uint64_t *bal_prepared, const uint64_t *inst_bal, uint8_t *status,
+                                 uint16_t *acks) {
+    for (uint64_t i = 0; i < n_rec; i++) {
+        uint32_t g = rec_g[i];
+        uint32_t s = rec_s[i], peer = rec_p[i];
+        uint64_t ballot = rec_b[i];
+        if (ballot != bal_prepared[g]) continue;                    /* :500 */
+        uint64_t k = (uint64_t)g * S + s;
+        if (status[k] != SSOR_ST_ACCEPTING || ballot < inst_bal[k]) continue; /* :513-519 */
+        if (peer >= population) continue;                           /* assignment[peer] would be out of range */
+        if (acks[k] & (1u << peer)) continue;                       /* :524-526 contains_key */
+        acks[k] |= (uint16_t)(1u << peer);                          /* :529-531 */
+        if (policy_idx[k] >= n_policies) continue;
+        if (ssor_cw_committed(T, population, d, majority, f, acks[k],
+                              policies + (size_t)policy_idx[k] * population, balanced))
+            status[k] = SSOR_ST_COMMITTED;                          /* :535-544 */
+    }
+}
+
 uint32_t ssor_commit_bar(uint64_t w) {
     /* multipaxos/durability.rs:161-170: advance while status >= Committed */
     uint32_t bar = 0;
@@ -574,6 +599,40 @@ void ssor_raft_scan_batch(const uint32_t *match, uint32_t npeers, uint64_t G,
         for (uint32_t q = 0; q < npeers && q < 64; q++) m[q] = match[(uint64_t)q * G + g];
         new_commit[g] = ssor_raft_scan(m, npeers, last_commit[g], log_end[g], curr_term[g],
                                        terms + g * (uint64_t)W, threshold);
+    }
+}
+
+/* Incremental per-reply restatement of handle_msg_append_entries_reply for SUCCESSFUL replies of the current
+ * term to a leader (raft/messages.rs:221-309 with conflict == None; check_term / heartbeat bookkeeping and the
+ * conflict branch are outside the path).  State per group: next_slot / match_slot per peer ([P][G]), last_commit,
+ * last_snap; the log is its term ring (term of slot s at terms[g*W + s % W]) and log_end.  threshold = quorum_cnt,
+ * or CRaft's majority + fault_tolerance (craft/messages.rs:300-308). */
+void ssor_raft_reply_stream(const uint32_t *rec_g, const uint8_t *rec_peer, const uint32_t *rec_end,
+                            uint64_t n_rec, uint32_t npeers, uint32_t threshold, uint64_t G, uint32_t *next_slot,
+                            uint32_t *match, uint32_t *last_commit, uint32_t *last_snap, const uint32_t *log_end,
+                            const uint32_t *curr_term, const uint32_t *terms, uint32_t W) {
+    for (uint64_t i = 0; i < n_rec; i++) {
+        uint64_t g = rec_g[i];
+        uint32_t peer = rec_peer[i], end_slot = rec_end[i];
+        if (g >= G || peer >= npeers) continue;                     /* not a peer of this group */
+        uint32_t *nx = &next_slot[(uint64_t)peer * G + g], *mt = &match[(uint64_t)peer * G + g];
+        if (*nx > end_slot + 1) continue;                           /* :245-247 */
+        *nx = end_slot + 1;                                         /* :248 */
+        *mt = end_slot;                                             /* :252 */
+        uint32_t new_commit = last_commit[g];                       /* :256-275 */
+        for (uint32_t slot = last_commit[g] + 1; slot < log_end[g]; slot++) {
+            if (terms[g * W + slot % W] != curr_term[g]) continue;
+            uint32_t cnt = 1;
+            for (uint32_t q = 0; q < npeers; q++) cnt += match[(uint64_t)q * G + g] >= slot ? 1u : 0u;
+            if (cnt >= threshold) new_commit = slot;
+        }
+        last_commit[g] = new_commit;                                /* :295 */
+        uint32_t snap0 = last_snap[g];                              /* :298-309 */
+        for (uint32_t slot = snap0 + 1; slot <= end_slot; slot++) {
+            uint32_t cnt = 1;
+            for (uint32_t q = 0; q < npeers; q++) cnt += match[(uint64_t)q * G + g] >= slot ? 1u : 0u;
+            if (cnt == npeers + 1) last_snap[g] = slot;
+        }
     }
 }
 

@@ -125,6 +125,12 @@ void ssor_tally_planes(const uint64_t *planes, uint32_t R, uint64_t G, uint32_t 
 /* per-instance vote-mask form: masks[i] = Bitmap of acks (bit r), count() >= threshold */
 void ssor_tally_masks(const uint16_t *masks, uint64_t n, uint32_t threshold, uint8_t *commit);
 /* commit_bar = length of committed prefix of the 64-slot window (durability.rs:148-218) */
+void ssor_tally_stream_crossword(const uint32_t *rec_g, const uint8_t *rec_s, const uint8_t *rec_p,
+                                 const uint64_t *rec_b, uint64_t n_rec, uint32_t S, uint32_t population,
+                                 uint32_t T, uint32_t d, uint32_t majority, uint32_t f, int balanced,
+                                 const uint32_t *policies, uint32_t n_policies, const uint8_t *policy_idx,
+                                 const uint64_t *bal_prepared, const uint64_t *inst_bal, uint8_t *status,
+                                 uint16_t *acks);
 uint32_t ssor_commit_bar(uint64_t committed_word);
 
 /* ---- Crossword ---- */
@@ -158,6 +164,10 @@ void ssor_raft_scan_batch(const uint32_t *match, uint32_t npeers, uint64_t G,
 
 /* ---- CRaft ----
  * commit threshold (craft/messages.rs:300-308): full_copy_mode ? majority : majority + fault_tolerance */
+void ssor_raft_reply_stream(const uint32_t *rec_g, const uint8_t *rec_peer, const uint32_t *rec_end,
+                            uint64_t n_rec, uint32_t npeers, uint32_t threshold, uint64_t G, uint32_t *next_slot,
+                            uint32_t *match, uint32_t *last_commit, uint32_t *last_snap, const uint32_t *log_end,
+                            const uint32_t *curr_term, const uint32_t *terms, uint32_t W);
 uint32_t ssor_craft_threshold(uint32_t majority, uint32_t fault_tolerance, int full_copy_mode);
 /* shadow_last_commit (craft/messages.rs:677-690): peers' match slots sorted descending, element
  * [threshold - 2]; i.e. the (threshold-1)-th largest peer match */

@@ -88,6 +88,16 @@ SIGNATURES = {
     "ss_prepare_merge_dev": (_i, [_vp, _vp, _vp, _u32, _u64, _vp, _u32, _u32, _u32, _vp, _vp, _vp]),
     "ss_accept_step_fused_dev": (_i, [_vp, _vp, _u64, _u32, _u64, _vp, _u64, _u64, _u32, _vp, _u32, _u32, _vp, _vp]),
     "ss_accept_step_fused": (_i, [_vp, _vp, _u64, _u32, _u64, _vp, _u64, _u64, _vp, _u32, _u32, _vp, _vp]),
+    "ss_engine_create": (_i, [_vp, _vp, _u64, C.POINTER(_vp)]),
+    "ss_engine_destroy": (_i, [_vp]),
+    "ss_engine_view_get": (_i, [_vp, _vp]),
+    "ss_engine_set_prepared_ballots": (_i, [_vp, _vp]),
+    "ss_engine_set_policies": (_i, [_vp, _vp, _u32, _i]),
+    "ss_engine_propose": (_i, [_vp, _u32, _vp, _u64, _vp, C.POINTER(_vp)]),
+    "ss_engine_ingest": (_i, [_vp, _vp, _vp, _vp, _vp, _u64]),
+    "ss_engine_tick": (_i, [_vp, _vp]),
+    "ss_engine_raft_append": (_i, [_vp, _vp]),
+    "ss_engine_raft_ingest": (_i, [_vp, _vp, _vp, _vp, _u64]),
     "ss_rs_set_variant": (_i, [_vp, _i]),
     "ss_rs_last_kernel": (C.c_char_p, [_vp]),
 }
@@ -97,6 +107,27 @@ class StepSync(C.Structure):
     """ss_step_sync (include/summerset_b200.h): device-side wait / signal flags of one multi-GPU step call."""
     _fields_ = [("wait_flags", C.c_void_p), ("n_wait", C.c_uint32), ("wait_value", C.c_uint64),
                 ("signal_flags", C.POINTER(C.c_void_p)), ("n_signal", C.c_uint32), ("signal_value", C.c_uint64)]
+
+
+SS_PROTO_MULTIPAXOS, SS_PROTO_RSPAXOS, SS_PROTO_CROSSWORD, SS_PROTO_RAFT, SS_PROTO_CRAFT = range(5)
+
+
+class EngineConfig(C.Structure):
+    """ss_engine_config"""
+    _fields_ = [("protocol", C.c_uint32), ("population", C.c_uint32), ("fault_tolerance", C.c_uint32), ("data_len", C.c_uint32),
+                ("rs_total_shards", C.c_uint32), ("rs_data_shards", C.c_uint32), ("keep_slots", C.c_uint32),
+                ("raft_window", C.c_uint32)]
+
+
+class EngineView(C.Structure):
+    """ss_engine_view"""
+    _fields_ = [("n_groups", C.c_uint64), ("population", C.c_uint32), ("threshold", C.c_uint32), ("data_shards", C.c_uint32),
+                ("total_shards", C.c_uint32), ("shard_len", C.c_uint32), ("shard_stride", C.c_uint32), ("raft_window", C.c_uint32),
+                ("pad0", C.c_uint32), ("plane_stride", C.c_uint64), ("slot_stride", C.c_uint64),
+                ("planes", C.c_void_p), ("bal_prepared", C.c_void_p), ("inst_bal", C.c_void_p), ("accepting", C.c_void_p),
+                ("committed", C.c_void_p), ("commit_bar", C.c_void_p), ("shards", C.c_void_p), ("policy_idx", C.c_void_p),
+                ("match", C.c_void_p), ("next_slot", C.c_void_p), ("last_commit", C.c_void_p), ("log_end", C.c_void_p),
+                ("curr_term", C.c_void_p), ("last_snap", C.c_void_p), ("terms", C.c_void_p)]
 
 
 class SummersetError(RuntimeError):

@@ -168,7 +168,14 @@ int launch_tally_crossword(ss_ctx *ctx, const void *masks, uint32_t mask_bytes, 
 int launch_raft_scan(ss_ctx *ctx, const uint32_t *match, uint32_t n_peers, uint64_t G,
                      const uint32_t *last_commit, const uint32_t *log_end, const uint32_t *curr_term,
                      const uint32_t *terms, uint32_t window, uint32_t threshold, uint32_t *new_commit,
-                     uint32_t *window_overflow);
+                     uint32_t *window_overflow, uint32_t ring = 0);
+// same scan over the engine's ring-indexed term store (terms[g*W + (slot & (W-1))]); new_commit may alias last_commit
+int launch_raft_scan_ring(ss_ctx *ctx, const uint32_t *match, uint32_t n_peers, uint64_t G, const uint32_t *last_commit,
+                          const uint32_t *log_end, const uint32_t *curr_term, const uint32_t *terms, uint32_t window,
+                          uint32_t threshold, uint32_t *new_commit);
+// (policy, ack set) -> commit bit table of the Crossword predicate, from DEVICE policies
+int launch_crossword_lut(ss_ctx *ctx, const uint32_t *d_policies, uint32_t n_policies, uint32_t n_replicas, uint32_t T, uint32_t d,
+                         uint32_t majority, uint32_t f, int balanced, uint32_t *d_lut_bits);
 
 // multi-GPU step flags
 int make_flag_wait(ss_ctx *ctx, const ss_step_sync *sync, dev::FlagWait *out);

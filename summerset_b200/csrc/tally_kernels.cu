@@ -242,7 +242,10 @@ __global__ void __launch_bounds__(kTallyThreads)
 raft_scan_kernel(const uint32_t *__restrict__ match, uint32_t n_peers, uint64_t G,
                  const uint32_t *__restrict__ last_commit, const uint32_t *__restrict__ log_end,
                  const uint32_t *__restrict__ curr_term, const uint32_t *__restrict__ terms, uint32_t W,
-                 uint32_t threshold, uint32_t *__restrict__ new_commit, uint32_t *__restrict__ window_overflow) {
+                 uint32_t threshold, uint32_t *new_commit, uint32_t *__restrict__ window_overflow, uint32_t ring) {
+    // ring != 0 (engine state): the term of slot s sits at terms[g*W + (s & (W-1))] (W a power of two) instead of at the
+    // window-relative offset s - last_commit - 1; new_commit may then alias last_commit (each lane reads its group's
+    // last_commit before anything is written).
     const uint32_t lane = threadIdx.x & 31u;
     const uint64_t warp = (static_cast<uint64_t>(blockIdx.x) * kTallyThreads + threadIdx.x) >> 5;
     const uint64_t nwarps = (static_cast<uint64_t>(gridDim.x) * kTallyThreads) >> 5;
@@ -296,7 +299,7 @@ raft_scan_kernel(const uint32_t *__restrict__ match, uint32_t n_peers, uint64_t 
         //      whole window.  Only groups whose top candidate is an older-term entry take the cooperative scan.
         if (live && any) {
             const uint32_t o = upper - lc - 1u;
-            if (o < W && __ldg(terms + g * W + o) == ct) { result = upper; any = false; }
+            if (o < W && __ldg(terms + g * W + (ring ? (upper & (W - 1u)) : o)) == ct) { result = upper; any = false; }
         }
         // ---- cooperative part: for each remaining group of the batch, find the last slot in (lc, upper]
         //      whose term equals curr_term (raft/messages.rs:261-263,271-274: last one wins) ----
@@ -316,7 +319,7 @@ raft_scan_kernel(const uint32_t *__restrict__ match, uint32_t n_peers, uint64_t 
             const uint32_t limit = span < W ? span : W;
             for (int base = static_cast<int>((limit - 1u) & ~31u); base >= 0; base -= 32) {
                 const uint32_t o = static_cast<uint32_t>(base) + lane;
-                const bool hit = o < limit && __ldg(row + o) == s_ct;
+                const bool hit = o < limit && __ldg(row + (ring ? ((s_lc + 1u + o) & (W - 1u)) : o)) == s_ct;
                 const uint32_t m = __ballot_sync(0xffffffffu, hit);
                 if (m) { found = static_cast<uint32_t>(base) + (31u - __clz(m)); break; }
             }
@@ -685,8 +688,9 @@ int launch_tally_crossword(ss_ctx *ctx, const void *masks, uint32_t mask_bytes, 
 
 int launch_raft_scan(ss_ctx *ctx, const uint32_t *match, uint32_t n_peers, uint64_t G, const uint32_t *last_commit,
                      const uint32_t *log_end, const uint32_t *curr_term, const uint32_t *terms, uint32_t window,
-                     uint32_t threshold, uint32_t *new_commit, uint32_t *window_overflow) {
+                     uint32_t threshold, uint32_t *new_commit, uint32_t *window_overflow, uint32_t ring) {
     SS_TRY(ctx_bind(ctx));
+    if (ring && (window & (window - 1u))) return set_error(SS_ERR_INVALID_ARG, "ring term windows need a power-of-two size");
     if (n_peers > kRaftMaxPeers) return set_error(SS_ERR_INVALID_ARG, "n_peers must be <= %d, got %u", kRaftMaxPeers, n_peers);
     if (G == 0) return SS_OK;
     const uint64_t warps = (G + 31) / 32;
@@ -695,13 +699,31 @@ int launch_raft_scan(ss_ctx *ctx, const uint32_t *match, uint32_t n_peers, uint6
     if (ctas > cap) ctas = cap;
     const uint32_t grid = static_cast<uint32_t>(ctas);
 #define SS_RAFT_LAUNCH(NP) raft_scan_kernel<NP><<<grid, kTallyThreads, 0, ctx->stream>>>( \
-        match, n_peers, G, last_commit, log_end, curr_term, terms, window, threshold, new_commit, window_overflow)
+        match, n_peers, G, last_commit, log_end, curr_term, terms, window, threshold, new_commit, window_overflow, ring)
     if (n_peers <= 2) SS_RAFT_LAUNCH(2);
     else if (n_peers <= 4) SS_RAFT_LAUNCH(4);
     else if (n_peers <= 6) SS_RAFT_LAUNCH(6);
     else if (n_peers <= 8) SS_RAFT_LAUNCH(8);
     else SS_RAFT_LAUNCH(16);
 #undef SS_RAFT_LAUNCH
+    SS_CUDA(cudaGetLastError());
+    ctx->launches++;
+    return SS_OK;
+}
+
+int launch_raft_scan_ring(ss_ctx *ctx, const uint32_t *match, uint32_t n_peers, uint64_t G, const uint32_t *last_commit,
+                          const uint32_t *log_end, const uint32_t *curr_term, const uint32_t *terms, uint32_t window,
+                          uint32_t threshold, uint32_t *new_commit) {
+    return launch_raft_scan(ctx, match, n_peers, G, last_commit, log_end, curr_term, terms, window, threshold, new_commit, nullptr, 1u);
+}
+
+int launch_crossword_lut(ss_ctx *ctx, const uint32_t *d_policies, uint32_t n_policies, uint32_t n_replicas, uint32_t T, uint32_t d,
+                         uint32_t majority, uint32_t f, int balanced, uint32_t *d_lut_bits) {
+    SS_TRY(ctx_bind(ctx));
+    const uint32_t entries = n_policies << n_replicas;
+    SS_CUDA(cudaMemsetAsync(d_lut_bits, 0, ((entries + 31) / 32) * 4, ctx->stream));
+    crossword_lut_kernel<<<(entries + 127) / 128, 128, 0, ctx->stream>>>(d_policies, n_policies, n_replicas, T, d, majority, f,
+                                                                         balanced, d_lut_bits);
     SS_CUDA(cudaGetLastError());
     ctx->launches++;
     return SS_OK;
