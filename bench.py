@@ -766,10 +766,8 @@ def bench_cfg3b(env, steps, warmup):
     pm = torch.from_numpy(present.astype(np.int32)).to(dev)
     for j in range(D + P):
         sh[j][((pm >> j) & 1) == 0] = 0x5A
-    off = torch.arange(n, dtype=torch.int64, device=dev) * ds
-    lens = torch.full((n,), DATA_LEN, dtype=torch.int32, device=dev)
     l0 = ctx.launches
-    ms = _time_steps(torch, lambda: rs.reconstruct_batch(sh, n * ds, off, lens, pm, True), steps, warmup)
+    ms = _time_steps(torch, lambda: rs.reconstruct_uniform(sh, DATA_LEN, pm, True), steps, warmup)
     launches = (ctx.launches - l0) * steps // (steps + max(3, warmup))
     ok = all(torch.equal(sh[i], keep[i]) for i in range(D))
     assert ok, "cfg3b round trip failed"

@@ -184,6 +184,15 @@ int ss_rs_reconstruct_batch_dev(ss_rs_coder *coder, uint8_t *shards, uint64_t pl
                                 const uint32_t *present, uint64_t n, int data_only,
                                 int32_t *status, uint32_t flags);
 
+/* uniform geometry: every codeword has data_len bytes and its shard j sits at shards + j*plane_stride + g*shard_stride
+ * (16-byte aligned slots of capacity round_up(L,16), the layout ss_rs_encode_uniform_dev writes with
+ * SS_RS_OUT_PADDED16; regenerated shards get zero padding).  For RS(3,2) -- every 5-replica deployment -- this runs
+ * the pattern-specialised row kernel (compile-time decode rows per present mask); other codes go through the kernels of
+ * the ragged call.  status as above. */
+int ss_rs_reconstruct_uniform_dev(ss_rs_coder *coder, uint8_t *shards, uint64_t plane_stride, uint64_t shard_stride,
+                                  uint32_t data_len, const uint32_t *present, uint64_t n, int data_only,
+                                  int32_t *status);
+
 /* host-buffer forms of the two batch calls (H2D, kernel, D2H inside; chunked + overlapped) */
 int ss_rs_encode_uniform(ss_rs_coder *coder, const uint8_t *data, uint64_t data_stride,
                          uint32_t data_len, uint64_t n, uint8_t *parity, uint64_t plane_stride,

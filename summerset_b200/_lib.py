@@ -74,6 +74,7 @@ SIGNATURES = {
     "ss_rs_encode_batch_dev": (_i, [_vp, _vp, _vp, _vp, _u64, _vp, _u64, _vp, _u32]),
     "ss_rs_encode_uniform_dev": (_i, [_vp, _vp, _u64, _u32, _u64, _vp, _u64, _u64, _u32]),
     "ss_rs_reconstruct_batch_dev": (_i, [_vp, _vp, _u64, _vp, _vp, _vp, _u64, _i, _vp, _u32]),
+    "ss_rs_reconstruct_uniform_dev": (_i, [_vp, _vp, _u64, _u64, _u32, _vp, _u64, _i, _vp]),
     "ss_rs_encode_uniform": (_i, [_vp, _vp, _u64, _u32, _u64, _vp, _u64, _u64]),
     "ss_tally_planes_dev": (_i, [_vp, _vp, _u32, _u64, _u32, _vp, _vp]),
     "ss_tally_planes": (_i, [_vp, _vp, _u32, _u64, _u32, _vp, _vp]),

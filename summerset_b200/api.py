@@ -413,6 +413,17 @@ class ReedSolomon:
                                                    SS_RS_OUT_PADDED16 if padded else 0))
         return status
 
+    def reconstruct_uniform(self, shards: torch.Tensor, data_len: int, present: torch.Tensor, data_only: bool) -> torch.Tensor:
+        """shards uint8 [d+p, n, shard_stride] (padded-16 slots); present int32 [n].  Regenerates in place; returns status."""
+        assert shards.is_cuda and shards.dtype == torch.uint8 and shards.is_contiguous() and shards.dim() == 3
+        assert present.dtype == torch.int32 and present.numel() == shards.shape[1]
+        t, n, ss = shards.shape
+        assert t == self.d + self.p
+        status = torch.empty(n, dtype=torch.int32, device=shards.device)
+        check(self.lib.ss_rs_reconstruct_uniform_dev(self.h, _ptr(shards), n * ss, ss, data_len, _ptr(present), n,
+                                                     1 if data_only else 0, _ptr(status)))
+        return status
+
     def accept_step_fused(self, data: torch.Tensor, data_len: int, parity: torch.Tensor, planes: torch.Tensor,
                           threshold: int, committed: torch.Tensor, commit_bar: Optional[torch.Tensor]) -> None:
         """BASELINE config 3 step: RS-encode n groups' request batches + tally their ack windows, one launch."""

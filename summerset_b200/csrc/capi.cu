@@ -668,6 +668,16 @@ int ss_rs_reconstruct_batch_dev(ss_rs_coder *c, uint8_t *shards, uint64_t plane_
     return launch_rs_reconstruct(c, shards, plane_stride, off, data_len, present, n, data_only, status, flags);
 }
 
+int ss_rs_reconstruct_uniform_dev(ss_rs_coder *c, uint8_t *shards, uint64_t plane_stride, uint64_t shard_stride,
+                                  uint32_t data_len, const uint32_t *present, uint64_t n, int data_only, int32_t *status) {
+    if (c == nullptr) return set_error(SS_ERR_INVALID_ARG, "null coder");
+    if (n == 0) return SS_OK;
+    if (!shards || !present || !status) return set_error(SS_ERR_INVALID_ARG, "null buffer");
+    if (!c->batch_ok || !c->dec_ok)
+        return set_error(SS_ERR_UNSUPPORTED, "batched reconstruct needs d+p <= 12 (coder is %d,%d)", c->d, c->p);
+    return launch_rs_reconstruct_uniform(c, shards, plane_stride, shard_stride, data_len, present, n, data_only, status);
+}
+
 int ss_accept_step_fused_dev(ss_rs_coder *c, const uint8_t *data, uint64_t data_stride, uint32_t data_len,
                              uint64_t n_groups, uint8_t *parity, uint64_t plane_stride, uint64_t shard_stride,
                              uint32_t flags, const uint64_t *planes, uint32_t n_replicas, uint32_t threshold,

@@ -34,6 +34,7 @@
 #include "device_common.cuh"
 #include "ss_internal.hpp"
 #include "static_codes.hpp"
+#include "rs32_decode.cuh"
 
 namespace ssb {
 
@@ -795,6 +796,70 @@ __global__ void __launch_bounds__(kThreads, PAIR ? 3 : 4) rs_reconstruct_small_k
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// RS(3,2) reconstruct, uniform geometry: the row structure of the encode kernel.  A CTA walks codewords, thread = 16-byte
+// column; the codeword's present mask is CTA-uniform, so one switch per codeword selects the pattern's COMPILE-TIME
+// column routine (rs32_decode.cuh): three aligned source loads, a fully unrolled Horner row per missing shard (XOR chain
+// where the all-ones parity row allows), one or two 128-bit stores.  Intact codewords cost one 4-byte read (prefetched an
+// iteration ahead) and a status write; nothing is looked up in memory between a codeword's mask and its shard loads.
+// ------------------------------------------------------------------------------------------------
+struct Dec32Row {
+    uint8_t *shards;
+    uint64_t plane_stride, shard_stride;
+    const uint32_t *present;
+    int32_t *status;
+    uint32_t n, L, vpc;
+};
+
+template <uint32_t PAT, bool DATA_ONLY>
+__device__ __forceinline__ void rs32_dec_column(uint8_t *__restrict__ base, uint64_t plane_stride, int nv) {
+    constexpr rs32::Decode D = rs32::make_decode(PAT, DATA_ONLY);
+    const uint4 x0 = dev::ldg128(base + D.src[0] * plane_stride);
+    const uint4 x1 = dev::ldg128(base + D.src[1] * plane_stride);
+    const uint4 x2 = dev::ldg128(base + D.src[2] * plane_stride);
+    uint4 y0, y1 = make_uint4(0u, 0u, 0u, 0u);
+    rs32::decode_column<PAT, DATA_ONLY>(x0, x1, x2, y0, y1);
+    dev::stg128_cs(base + D.dst[0] * plane_stride, nv < 16 ? keep_bytes(y0, nv) : y0);
+    if constexpr (D.n_out == 2) dev::stg128_cs(base + D.dst[1] * plane_stride, nv < 16 ? keep_bytes(y1, nv) : y1);
+}
+
+template <bool DATA_ONLY, int MAXT, int MINB>
+__global__ void __launch_bounds__(MAXT, MINB) rs32_reconstruct_row_kernel(const __grid_constant__ Dec32Row P) {
+    uint32_t g = blockIdx.x;
+    uint32_t nx_pat = g < P.n ? __ldg(P.present + g) : 0u;
+#pragma unroll 1
+    for (; g < P.n; g += gridDim.x) {
+        const uint32_t pat = nx_pat & 31u;
+        if (g + gridDim.x < P.n) nx_pat = __ldg(P.present + g + gridDim.x);     // next codeword's mask, one iteration ahead
+        const bool enough = __popc(pat) >= 3;                                   // crate: Error::TooFewShardsPresent
+        if (threadIdx.x == 0u) P.status[g] = enough ? SS_OK : SS_ERR_TOO_FEW_SHARDS_PRESENT;
+        if (!enough || !rs32::needs_work(pat, DATA_ONLY)) continue;             // never partial output
+        uint8_t *cw = P.shards + static_cast<uint64_t>(g) * P.shard_stride;
+        for (uint32_t v = threadIdx.x; v < P.vpc; v += blockDim.x) {
+            const int nv = static_cast<int>(P.L - v * 16u) > 16 ? 16 : static_cast<int>(P.L - v * 16u);
+            // a switch the compiler turns into a jump table over the pattern-specialised column routines
+            switch (pat) {
+#define SS_DEC_CASE(PT) case PT: if constexpr (rs32::make_decode(PT, DATA_ONLY).valid && rs32::needs_work(PT, DATA_ONLY)) \
+                                     rs32_dec_column<PT, DATA_ONLY>(cw + v * 16u, P.plane_stride, nv); break;
+                SS_DEC_CASE(7) SS_DEC_CASE(11) SS_DEC_CASE(13) SS_DEC_CASE(14) SS_DEC_CASE(15) SS_DEC_CASE(19) SS_DEC_CASE(21)
+                SS_DEC_CASE(22) SS_DEC_CASE(23) SS_DEC_CASE(25) SS_DEC_CASE(26) SS_DEC_CASE(27) SS_DEC_CASE(28) SS_DEC_CASE(29)
+                SS_DEC_CASE(30) SS_DEC_CASE(31)
+#undef SS_DEC_CASE
+                default: break;
+            }
+        }
+    }
+}
+
+// off[g] = g * stride, len[g] = data_len: lets the ragged kernels serve a uniform batch of any code
+__global__ void uniform_meta_kernel(uint64_t *off, uint32_t *len, uint64_t n, uint64_t stride, uint32_t data_len) {
+    const uint64_t step = static_cast<uint64_t>(gridDim.x) * blockDim.x;
+    for (uint64_t g = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x; g < n; g += step) {
+        off[g] = g * stride;
+        len[g] = data_len;
+    }
+}
+
 template <int D>
 __device__ __forceinline__ void horner_payload_column(const uint8_t *src, uint32_t len, uint32_t L, uint32_t k,
                                                       uint8_t *out, uint64_t plane_stride, uint32_t oflags,
@@ -1222,7 +1287,8 @@ __device__ __forceinline__ void distribute_store(const CwDistribute &P, uint64_t
     }
 }
 
-__global__ void __launch_bounds__(kThreads, 3) rs32_crossword_distribute_kernel(const __grid_constant__ CwDistribute P) {
+template <bool PAIR>
+__global__ void __launch_bounds__(kThreads, PAIR ? 3 : 5) rs32_crossword_distribute_kernel(const __grid_constant__ CwDistribute P) {
     const uint32_t lane = threadIdx.x & 31u;
     const uint64_t warp = (static_cast<uint64_t>(blockIdx.x) * kThreads + threadIdx.x) >> 5;
     const uint64_t nwarps = (static_cast<uint64_t>(gridDim.x) * kThreads) >> 5;
@@ -1242,16 +1308,18 @@ __global__ void __launch_bounds__(kThreads, 3) rs32_crossword_distribute_kernel(
         const uint32_t fast_cols = len >= 2u * L ? (((len - 2u * L) < L ? (len - 2u * L) : L) / 16u) : 0u;
         uint32_t v0 = 0;
         // interior columns, two per lane per iteration: all loads in flight before any compute
-        for (; v0 + 64u <= fast_cols; v0 += 64u) {
-            const uint32_t k = (v0 + lane) * 16u, k2 = k + 512u;
-            Raw6 r1, r2;
-            rs32_issue_loads(src, k, s0 + L + k - s1, s0 + 2u * L + k - s2, s0, s1, s2, r1);
-            rs32_issue_loads(src, k2, s0 + L + k2 - s1, s0 + 2u * L + k2 - s2, s0, s1, s2, r2);
-            uint4 sh[5];
-            rs32_shards_from_raw(r1, s0, s1, s2, sh);
-            distribute_store(P, ro, k, Lpad, spr, sh);
-            rs32_shards_from_raw(r2, s0, s1, s2, sh);
-            distribute_store(P, ro, k2, Lpad, spr, sh);
+        if constexpr (PAIR) {
+            for (; v0 + 64u <= fast_cols; v0 += 64u) {
+                const uint32_t k = (v0 + lane) * 16u, k2 = k + 512u;
+                Raw6 r1, r2;
+                rs32_issue_loads(src, k, s0 + L + k - s1, s0 + 2u * L + k - s2, s0, s1, s2, r1);
+                rs32_issue_loads(src, k2, s0 + L + k2 - s1, s0 + 2u * L + k2 - s2, s0, s1, s2, r2);
+                uint4 sh[5];
+                rs32_shards_from_raw(r1, s0, s1, s2, sh);
+                distribute_store(P, ro, k, Lpad, spr, sh);
+                rs32_shards_from_raw(r2, s0, s1, s2, sh);
+                distribute_store(P, ro, k2, Lpad, spr, sh);
+            }
         }
         for (; v0 < vpc; v0 += 32u) {
             const uint32_t v = v0 + lane;
@@ -1294,6 +1362,83 @@ __global__ void __launch_bounds__(kThreads, 3) rs32_crossword_distribute_kernel(
     }
 }
 
+// one column (masked when it touches the payload tail / the last partial vector) of codeword geometry (len, L, s0)
+__device__ __forceinline__ void cw_column(const CwDistribute &P, const uint8_t *__restrict__ src, uint32_t len, uint32_t L, uint32_t v,
+                                          uint32_t s0, uint32_t s1, uint32_t s2, bool fast, uint64_t ro, uint32_t Lpad, uint32_t spr) {
+    auto clamp16 = [](int64_t r) { return r > 16 ? 16 : (r < 0 ? 0 : static_cast<int>(r)); };
+    const uint32_t k = v * 16u;
+    const uint32_t o1 = s0 + L + k - s1, o2 = s0 + 2u * L + k - s2;
+    uint4 sh[5];
+    if (fast) {
+        Raw6 r1;
+        rs32_issue_loads(src, k, o1, o2, s0, s1, s2, r1);
+        rs32_shards_from_raw(r1, s0, s1, s2, sh);
+    } else {
+        const int nva = clamp16(static_cast<int64_t>(len) - k);
+        const int nvb = clamp16(static_cast<int64_t>(len) - L - k);
+        const int nvc = clamp16(static_cast<int64_t>(len) - 2ll * L - k);
+        const int onv = clamp16(static_cast<int64_t>(L) - k);
+        const uint4 a0 = dev::ldg128(src + k);
+        uint4 a1 = make_uint4(0u, 0u, 0u, 0u);
+        if (s0 != 0u && static_cast<int>(s0) + nva > 16) a1 = dev::ldg128(src + k + 16u);
+        uint4 b0 = make_uint4(0u, 0u, 0u, 0u), c0 = make_uint4(0u, 0u, 0u, 0u);
+        if (nvb > 0) b0 = dev::ldg128(src + o1);
+        uint4 b1 = make_uint4(0u, 0u, 0u, 0u);
+        if (s1 != 0u && static_cast<int>(s1) + nvb > 16) b1 = dev::ldg128(src + o1 + 16u);
+        if (nvc > 0) c0 = dev::ldg128(src + o2);
+        uint4 c1 = make_uint4(0u, 0u, 0u, 0u);
+        if (s2 != 0u && static_cast<int>(s2) + nvc > 16) c1 = dev::ldg128(src + o2 + 16u);
+        sh[0] = keep_bytes(s0 != 0u ? funnel16(a0, a1, s0) : a0, nva < onv ? nva : onv);
+        sh[1] = keep_bytes(s1 != 0u ? funnel16(b0, b1, s1) : b0, nvb < onv ? nvb : onv);
+        sh[2] = keep_bytes(s2 != 0u ? funnel16(c0, c1, s2) : c0, nvc < onv ? nvc : onv);
+        rs32_word_fast(sh[0].x, sh[1].x, sh[2].x, sh[3].x, sh[4].x);
+        rs32_word_fast(sh[0].y, sh[1].y, sh[2].y, sh[3].y, sh[4].y);
+        rs32_word_fast(sh[0].z, sh[1].z, sh[2].z, sh[3].z, sh[4].z);
+        rs32_word_fast(sh[0].w, sh[1].w, sh[2].w, sh[3].w, sh[4].w);
+        sh[3] = keep_bytes(sh[3], onv);
+        sh[4] = keep_bytes(sh[4], onv);
+    }
+    distribute_store(P, ro, k, Lpad, spr, sh);
+}
+
+// Cooperative flavour: a CTA of 8 warps takes 8 consecutive codewords at a time.  Short codewords (up to 64 columns, i.e.
+// payloads up to 3 KB) go one per warp; every longer one is walked by ALL eight warps together, 32-column blocks dealt round
+// robin -- so the long codewords, which carry almost all of the bytes of a mixed-size batch, are streamed by 256 threads with
+// one column each (high memory-level parallelism at 40 registers) and every destination slot is written in 4 KB runs.
+__global__ void __launch_bounds__(kThreads, 5) rs32_crossword_distribute_coop_kernel(const __grid_constant__ CwDistribute P) {
+    const uint32_t lane = threadIdx.x & 31u, wid = threadIdx.x >> 5;
+    constexpr uint32_t kBatch = kThreads / 32;
+    const uint64_t nbatches = (P.n + kBatch - 1) / kBatch;
+    for (uint64_t b = blockIdx.x; b < nbatches; b += gridDim.x) {
+        // lanes 0..7 fetch the batch's metadata; everyone gets it by shuffle
+        const uint64_t gm = b * kBatch + (lane & (kBatch - 1u));
+        uint32_t m_len = 0, m_spr = 0; uint64_t m_off = 0, m_ro = 0;
+        if (gm < P.n) { m_len = __ldg(P.data_len + gm); m_spr = __ldg(P.spr + gm); m_off = __ldg(P.data_off + gm); m_ro = __ldg(P.rep_off + gm); }
+#pragma unroll 1
+        for (uint32_t i = 0; i < kBatch; ++i) {
+            const uint32_t len = __shfl_sync(0xffffffffu, m_len, i);
+            if (len == 0u) continue;                                   // null codeword or past the end
+            const uint32_t L = (len + 2u) / 3u, vpc = (L + 15u) >> 4;
+            const bool shortcw = vpc <= 64u;
+            if (shortcw && i != wid) continue;                         // short: warp i alone
+            const uint32_t spr = __shfl_sync(0xffffffffu, m_spr, i);
+            const uint64_t off = __shfl_sync(0xffffffffu, m_off, i), ro = __shfl_sync(0xffffffffu, m_ro, i);
+            const uint8_t *pay = P.data + off;
+            const uint32_t s0 = static_cast<uint32_t>(reinterpret_cast<uintptr_t>(pay)) & 15u;
+            const uint8_t *src = pay - s0;
+            const uint32_t s1 = (s0 + L) & 15u, s2 = (s0 + 2u * L) & 15u;
+            const uint32_t fast_cols = len >= 2u * L ? (((len - 2u * L) < L ? (len - 2u * L) : L) / 16u) : 0u;
+            const uint32_t Lpad = vpc * 16u;
+            const uint32_t first = shortcw ? 0u : wid * 32u, step = shortcw ? 32u : kThreads;
+            for (uint32_t v0 = first; v0 < vpc; v0 += step) {
+                const uint32_t v = v0 + lane;
+                if (v >= vpc) break;
+                cw_column(P, src, len, L, v, s0, s1, s2, v0 + 32u <= fast_cols, ro, Lpad, spr);
+            }
+        }
+    }
+}
+
 int launch_crossword_distribute(ss_rs_coder *coder, const uint8_t *data, const uint64_t *data_off,
                                 const uint32_t *data_len, const uint8_t *spr, const uint64_t *rep_off, uint64_t n,
                                 uint8_t *const *replica_logs) {
@@ -1308,8 +1453,23 @@ int launch_crossword_distribute(ss_rs_coder *coder, const uint8_t *data, const u
             return set_error(SS_ERR_INVALID_ARG, "replica log %d is null or not 16-byte aligned", r);
         P.rep[r] = replica_logs[r];
     }
-    rs32_crossword_distribute_kernel<<<ragged_grid(ctx, n), kThreads, 0, ctx->stream>>>(P);
-    coder->last_kernel = "rs32_crossword_distribute_kernel";
+    // variant bits 0-3 (tuning): 0 = cooperative kernel (default), 1 = warp per codeword, one column per pass,
+    // 2 = warp per codeword, two columns per pass (the round-1 kernel)
+    const int vk = coder->variant & 15;
+    if (vk == 2) {
+        rs32_crossword_distribute_kernel<true><<<ragged_grid(ctx, n), kThreads, 0, ctx->stream>>>(P);
+        coder->last_kernel = "rs32_crossword_distribute_kernel<pair>";
+    } else if (vk == 1) {
+        const uint64_t cap = static_cast<uint64_t>(ctx->sm_count) * 5ull * 8ull;
+        uint64_t ctas = (n + 7) / 8; if (ctas > cap) ctas = cap;
+        rs32_crossword_distribute_kernel<false><<<static_cast<uint32_t>(ctas), kThreads, 0, ctx->stream>>>(P);
+        coder->last_kernel = "rs32_crossword_distribute_kernel";
+    } else {
+        const uint64_t cap = static_cast<uint64_t>(ctx->sm_count) * 5ull * 16ull;
+        uint64_t ctas = (n + 7) / 8; if (ctas > cap) ctas = cap;
+        rs32_crossword_distribute_coop_kernel<<<static_cast<uint32_t>(ctas), kThreads, 0, ctx->stream>>>(P);
+        coder->last_kernel = "rs32_crossword_distribute_coop_kernel";
+    }
     SS_CUDA(cudaGetLastError());
     ctx->launches++;
     return SS_OK;
@@ -1674,6 +1834,51 @@ int launch_rs_reconstruct(ss_rs_coder *coder, uint8_t *shards, uint64_t plane_st
     SS_CUDA(cudaGetLastError());
     ctx->launches++;
     return SS_OK;
+}
+
+int launch_rs_reconstruct_uniform(ss_rs_coder *coder, uint8_t *shards, uint64_t plane_stride, uint64_t shard_stride,
+                                  uint32_t data_len, const uint32_t *present, uint64_t n, int data_only, int32_t *status) {
+    ss_ctx *ctx = coder->ctx;
+    SS_TRY(ctx_bind(ctx));
+    if (n == 0) return SS_OK;
+    if (data_len == 0) return set_error(SS_ERR_INVALID_ARG, "null codewords cannot be reconstructed (rscoding.rs:495-497)");
+    const uint32_t d = static_cast<uint32_t>(coder->d);
+    const uint32_t L = (data_len + d - 1u) / d, vpc = (L + 15u) >> 4;
+    if (((reinterpret_cast<uintptr_t>(shards) | plane_stride | shard_stride) & 15u) || shard_stride < static_cast<uint64_t>(vpc) * 16u)
+        return set_error(SS_ERR_INVALID_ARG, "uniform reconstruct needs 16-byte aligned, padded shard slots (shard_stride >= round_up(L,16))");
+    if (coder->is_rs32 && (coder->variant & 15) != 8 && (coder->variant & 15) != 5 && n <= 0xffffffffull) {
+        Dec32Row P;
+        P.shards = shards; P.plane_stride = plane_stride; P.shard_stride = shard_stride; P.present = present; P.status = status;
+        P.n = static_cast<uint32_t>(n); P.L = L; P.vpc = vpc;
+        uint32_t threads = (vpc + 31u) & ~31u;
+        if (threads > 256u) threads = 256u;
+        uint32_t per_sm = 2048u / threads; if (per_sm > 32u) per_sm = 32u;
+        static const uint64_t kWaves[8] = {16, 1, 32, 4, 64, 256, 128, 8};   // variant bits 5-7 (tuning); [0] = default
+        uint64_t ctas = static_cast<uint64_t>(ctx->sm_count) * per_sm * kWaves[(coder->variant >> 5) & 7];
+        if (ctas > n) ctas = n;
+        const uint32_t grid = static_cast<uint32_t>(ctas);
+        if (threads > 128u) {
+            if (data_only) rs32_reconstruct_row_kernel<true, 256, 5><<<grid, threads, 0, ctx->stream>>>(P);
+            else rs32_reconstruct_row_kernel<false, 256, 5><<<grid, threads, 0, ctx->stream>>>(P);
+        } else {
+            if (data_only) rs32_reconstruct_row_kernel<true, 128, 12><<<grid, threads, 0, ctx->stream>>>(P);
+            else rs32_reconstruct_row_kernel<false, 128, 12><<<grid, threads, 0, ctx->stream>>>(P);
+        }
+        coder->last_kernel = "rs32_reconstruct_row_kernel";
+        SS_CUDA(cudaGetLastError());
+        ctx->launches++;
+        return SS_OK;
+    }
+    // any other code: the per-pattern program kernels over synthesised offsets
+    void *scr = nullptr;
+    SS_TRY(ctx_scratch(ctx, n * 12 + 256, &scr));
+    uint64_t *off = static_cast<uint64_t *>(scr);
+    uint32_t *len = reinterpret_cast<uint32_t *>(off + n);
+    uint64_t mg = (n + 255) / 256; if (mg > 4096) mg = 4096;
+    uniform_meta_kernel<<<static_cast<uint32_t>(mg), 256, 0, ctx->stream>>>(off, len, n, shard_stride, data_len);
+    SS_CUDA(cudaGetLastError());
+    ctx->launches++;
+    return launch_rs_reconstruct(coder, shards, plane_stride, off, len, present, n, data_only, status, SS_RS_OUT_PADDED16);
 }
 
 }  // namespace ssb

@@ -153,6 +153,8 @@ int match_static_code(int d, int p, const uint8_t *matrix);
 int launch_rs_reconstruct(ss_rs_coder *coder, uint8_t *shards, uint64_t plane_stride,
                           const uint64_t *off, const uint32_t *data_len, const uint32_t *present,
                           uint64_t n, int data_only, int32_t *status, uint32_t flags);
+int launch_rs_reconstruct_uniform(ss_rs_coder *coder, uint8_t *shards, uint64_t plane_stride, uint64_t shard_stride,
+                                  uint32_t data_len, const uint32_t *present, uint64_t n, int data_only, int32_t *status);
 int launch_tally_planes(ss_ctx *ctx, const uint64_t *planes, uint32_t R, uint64_t G, uint32_t thr,
                         uint64_t *committed, uint32_t *commit_bar);
 int launch_tally_masks(ss_ctx *ctx, const void *masks, uint32_t mask_bytes, uint64_t n, uint32_t thr,

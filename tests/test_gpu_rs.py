@@ -327,6 +327,50 @@ def _check_reconstruct_every_pattern(ctx, oracle, d, p, data_only, data_len, var
     assert (got[:, :, :L] == want[:, :, :L]).all()
 
 
+@pytest.mark.parametrize("d,p", [(3, 2), (4, 3), (2, 1)])
+@pytest.mark.parametrize("data_len", [1, 17, 100, 4096, 12288, 20000])
+@pytest.mark.parametrize("data_only", [True, False])
+def test_reconstruct_uniform_every_pattern(ctx, oracle, d, p, data_len, data_only):
+    """ss_rs_reconstruct_uniform_dev: RS(3,2) takes the pattern-specialised row kernel (compile-time decode rows per
+    present mask, incl. codewords wider than one CTA pass), other codes the program kernels -- every present mask, several
+    times over so CTAs walk mixed patterns, data-only and full, against the oracle (rscoding.rs:490-537)."""
+    rs = ReedSolomon(ctx, d, p)
+    t = d + p
+    reps = 7
+    pats = [pat for _ in range(reps) for pat in range(1 << t)]
+    rng = np.random.default_rng(data_len + d)
+    rng.shuffle(pats)
+    n = len(pats)
+    data = wl.payload_uniform(n, data_len, seed_extra=99 + d)
+    full, L, ds = _planes_from(oracle, d, p, data, data_len)
+    present = np.array(pats, dtype=np.uint32)
+    damaged = full.copy()
+    for g, pat in enumerate(pats):
+        for j in range(t):
+            if not (pat >> j) & 1:
+                damaged[j, g, :] = 0xCC
+    sh = torch.from_numpy(damaged).to(DEV)
+    st = rs.reconstruct_uniform(sh, data_len, torch.from_numpy(present.astype(np.int32)).to(DEV), data_only)
+    torch.cuda.synchronize()
+    if (d, p) == (3, 2):
+        assert rs.last_kernel() == "rs32_reconstruct_row_kernel"
+    got = sh.cpu().numpy()
+    st = st.cpu().numpy()
+    upto = d if data_only else t
+    for g, pat in enumerate(pats):
+        if bin(pat).count("1") < d:
+            assert st[g] == -10 and (got[:, g] == damaged[:, g]).all()      # refused, nothing written
+            continue
+        assert st[g] == 0
+        for j in range(t):
+            if j < upto:
+                assert (got[j, g, :L] == full[j, g, :L]).all(), (pat, j)
+                if not (pat >> j) & 1:
+                    assert (got[j, g, L:] == 0).all(), "regenerated shards carry zero padding"
+            else:
+                assert (got[j, g] == damaged[j, g]).all()                    # untouched
+
+
 def test_reconstruct_null_codeword_and_ragged(ctx, oracle):
     d, p = 3, 2
     rs = ReedSolomon(ctx, d, p)

@@ -188,14 +188,17 @@ def test_prepare_merge_on_gpu_and_recovery_roundtrip(ctx, oracle):
 
 
 @pytest.mark.gpu
-def test_crossword_distribute_matches_assignment_and_oracle(ctx, oracle):
+@pytest.mark.parametrize("variant,kernel", [(0, "rs32_crossword_distribute_coop_kernel"), (1, "rs32_crossword_distribute_kernel"),
+                                            (2, "rs32_crossword_distribute_kernel<pair>")])
+def test_crossword_distribute_matches_assignment_and_oracle(ctx, oracle, variant, kernel):
     """config 4 distribute (crossword/request.rs:137-185): every replica's log holds exactly the shards the balanced
     round-robin assignment gives it (crossword/mod.rs:866-888), bytes equal to the oracle's encode."""
     from summerset_b200.api import ReedSolomon
     rng = np.random.default_rng(6)
     d, p, n_rep = 3, 2, 5
     rs = ReedSolomon(ctx, d, p)
-    lens = np.concatenate([rng.integers(1, 3000, 300), wl.CFG4_SIZES, [0, 1, 2, 16, 48, 4096]]).astype(np.uint32)
+    rs.set_variant(variant)
+    lens = np.concatenate([rng.integers(1, 3000, 300), wl.CFG4_SIZES, wl.CFG4_SIZES + 1, [0, 1, 2, 16, 48, 4096, 3072, 3073, 9001]]).astype(np.uint32)
     rng.shuffle(lens)
     n = len(lens)
     spr = rng.integers(1, 4, n).astype(np.uint8)
@@ -211,7 +214,7 @@ def test_crossword_distribute_matches_assignment_and_oracle(ctx, oracle):
                             torch.from_numpy(lens.astype(np.int32)).to(DEV), torch.from_numpy(spr).to(DEV),
                             torch.from_numpy(rep_off).to(DEV), [logs[r].data_ptr() for r in range(n_rep)])
     torch.cuda.synchronize()
-    assert rs.last_kernel() == "rs32_crossword_distribute_kernel"
+    assert rs.last_kernel() == kernel
     got = logs.cpu().numpy()
     par = np.zeros((p, lay["plane_bytes"]), dtype=np.uint8)
     oracle.rs_encode_batch(d, p, arena, lay["data_off"], lens, par.reshape(-1), lay["plane_bytes"], lay["par_off"])

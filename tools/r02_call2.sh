@@ -14,6 +14,20 @@ timeout 600 $TR --master-port 29512 bench.py --gpus 2 --steps 40 --warmup 3 --la
 for v in 0 256 512 768; do
   timeout 300 $TR --master-port 2952$((v/256)) bench.py --gpus 2 --steps 20 --warmup 3 --lag 2 --no-sub --no-e2e --variant $v > gpurun_out/r02_bench_n2_st$v.json 2>/dev/null
 done
+# distribute kernel variants + reconstruct (one rank each is enough)
+for v in 0 1 2; do
+  timeout 300 python bench.py --workload cfg4 --steps 10 --warmup 3 --variant $v > gpurun_out/r02_cfg4_v$v.json 2>/dev/null
+done
+timeout 300 python bench.py --workload cfg3b --steps 20 --warmup 3 > gpurun_out/r02_cfg3b_row.json 2>/dev/null
+for w in 32 96 224; do timeout 300 python bench.py --workload cfg3b --steps 20 --warmup 3 --variant $w > gpurun_out/r02_cfg3b_row_v$w.json 2>/dev/null; done
+python - <<'PY'
+import json,glob
+for f in sorted(glob.glob('gpurun_out/r02_cfg4_v*.json')+glob.glob('gpurun_out/r02_cfg3b_row*.json')):
+    try:
+        j=json.loads(open(f).read().strip().splitlines()[-1])
+        print(f, 'ms', round(j['ms_per_step'],4), 'frac', round(j['roofline']['frac'],3), j['roofline']['kernel'], (j.get('distribute') or {}).get('kernel_ms'), ((j.get('distribute') or {}).get('roofline') or {}).get('frac'))
+    except Exception as e: print(f,'ERR',e)
+PY
 # CPU arm: schedule / thread-count / binding sweep (host only)
 for cfg in "static 0 close" "dynamic 0 close" "static 128 close" "dynamic 128 close" "static 0 spread" "static 32 close"; do
   set -- $cfg
