@@ -360,12 +360,80 @@ int ss_crossword_distribute_dev(ss_rs_coder *coder, const uint8_t *data, const u
  * shard_plane: shard `shard_idx` of codeword g at shard_plane + g*shard_stride.  Frame g is written inside
  * out[g*frame_stride .. (g+1)*frame_stride) at frame_off[g] (so that the shard bytes are 16-byte aligned) and is
  * frame_len[g] bytes long.  frame_stride: multiple of 16, >= shard_len + 96 + d + p.  msg_variant = the index of
- * the Accept variant in the protocol's PeerMsg enum (2 for RSPaxos).  bincode layout from knowledge of the crate:
- * unpinned against the reference (it cannot run here); tested byte-for-byte against summerset_b200/wire.py. */
+ * the Accept variant in the protocol's PeerMsg enum (2 for RSPaxos).  This is the single-shard fast path (the shard
+ * is copied with aligned 128-bit accesses on both sides); ss_frame_accept_pack_dev is the general packer.  bincode
+ * layout from knowledge of the crate: unpinned against the reference (it cannot run here); tested byte for byte against
+ * the oracle's independent C encoder (oracle/ss_wire.c). */
 int ss_frame_accept_batch_dev(ss_ctx *ctx, const uint8_t *shard_plane, uint64_t shard_stride, uint32_t shard_idx,
                               uint32_t data_shards, uint32_t parity_shards, uint32_t data_len, uint32_t msg_variant,
                               const uint64_t *slot, const uint64_t *ballot, uint64_t n, uint8_t *out,
                               uint64_t frame_stride, uint64_t *frame_off, uint32_t *frame_len);
+
+/* ---- wire / WAL formats on the device -------------------------------------------------------------
+ * General Accept packer: for n codewords and ONE destination, builds either the frames an unmodified Summerset peer
+ * reads off its TCP connection -- 8-byte big-endian body length (utils/safetcp.rs:30-88) + bincode(PeerMessage::Msg {
+ * msg: PeerMsg::Accept { slot, ballot, reqs_cw [, assignment] } }) (server/transport.rs:37-40, rspaxos/mod.rs:283-288,
+ * crossword/mod.rs:356-362) -- or the records StorageHub appends -- 8-byte big-endian length (server/storage.rs:333-337)
+ * + bincode(WalEntry::AcceptData { slot, ballot, reqs_cw }) (rspaxos/mod.rs:219-228).  reqs_cw carries exactly the shards
+ * policies[policy_idx[g]][peer] names (what subset_copy(.., false) builds for that peer: one shard in RSPaxos,
+ * rspaxos/request.rs:127-142; spr shards in Crossword, crossword/request.rs:164-185), data_copy None, encoded per
+ * utils/rscoding.rs:43-72; with_assignment appends assignment: Vec<Bitmap> = that policy row (utils/bitmap.rs:20-30).
+ * policies: DEVICE array [n_policies][population] of shard bitmasks; policy_idx: device [n] or NULL (policy 0).
+ * Frame g is written inside out[g*frame_stride ..) at frame_off[g] (placed so that its first shard's bytes are 16-byte
+ * aligned) and is frame_len[g] bytes long; frame_stride >= ss_frame_accept_max_len(spec, max shards per frame).
+ * bincode layout from knowledge of the crate: unpinned against the reference; tested byte for byte against the oracle's
+ * independent C encoder (oracle/ss_wire.c), and decode(encode(x)) == x. */
+#define SS_FRAME_PEER_ACCEPT 0u
+#define SS_FRAME_WAL_ACCEPT_DATA 1u
+typedef struct ss_frame_spec {
+    uint32_t kind;             /* SS_FRAME_PEER_ACCEPT / SS_FRAME_WAL_ACCEPT_DATA */
+    uint32_t msg_variant;      /* index of Accept in the protocol's PeerMsg enum (2), or of AcceptData in WalEntry (1) */
+    uint32_t data_shards, parity_shards, data_len;
+    uint32_t population;       /* replicas (columns of the policy table) */
+    uint32_t with_assignment;  /* Crossword Accept: append assignment: Vec<Bitmap> */
+    uint32_t assign_size;      /* bit length of each assignment Bitmap (= rs_total_shards) */
+} ss_frame_spec;
+uint64_t ss_frame_accept_max_len(const ss_frame_spec *spec, uint32_t max_shards_per_frame);
+int ss_frame_accept_pack_dev(ss_ctx *ctx, const ss_frame_spec *spec, const uint8_t *shard_planes, uint64_t plane_stride,
+                             uint64_t shard_stride, const uint32_t *policies, uint32_t n_policies,
+                             const uint8_t *policy_idx, uint32_t peer, const uint64_t *slot, const uint64_t *ballot,
+                             uint64_t n, uint8_t *out, uint64_t frame_stride, uint64_t *frame_off, uint32_t *frame_len);
+
+/* AcceptReply frames -> ack records.  buf holds frames as read off the peers' connections (8-byte big-endian length +
+ * body each); frame i starts at frame_off[i], came from replica frame_peer[i] of group frame_group[i].  A well-formed
+ * PeerMessage::Msg{PeerMsg::AcceptReply{slot, ballot}} (rspaxos/mod.rs:290-291; with_size: crossword's
+ * {slot, ballot, size, reply_ts}, crossword/mod.rs:365-373) yields rec_kind[i] = reply_variant and the record
+ * (group, slot - window_base[group], peer, ballot) in the layout ss_ack_ingest_dev / ss_engine_ingest take; slots below
+ * the group's window base (`slot < start_slot`, messages.rs:377) or beyond the 64-slot window get rec_slot = 0xff, which
+ * the ingest kernel drops.  Other messages: rec_kind = their PeerMsg variant index (0x80000000 | k for the
+ * PeerMessage variants LeaseMsg / Leave / LeaveReply) -- the host handles them; malformed: SS_FRAME_KIND_MALFORMED. */
+#define SS_FRAME_KIND_MALFORMED 0xffffffffu
+int ss_accept_reply_parse_dev(ss_ctx *ctx, const uint8_t *buf, uint64_t buf_len, const uint64_t *frame_off,
+                              const uint32_t *frame_group, const uint8_t *frame_peer, const uint64_t *window_base,
+                              uint64_t n_frames, uint64_t n_groups, uint32_t reply_variant, int with_size,
+                              uint32_t *rec_group, uint8_t *rec_slot, uint8_t *rec_peer, uint64_t *rec_ballot,
+                              uint32_t *rec_kind);
+
+/* WalEntry::CommitSlot { slot } records (rspaxos/mod.rs:231; commit_variant = 2) for every instance that committed in a
+ * tick: newly[g] bit s (ss_engine_tick's output) -> one 24-byte cell in `entries` holding the 8-byte big-endian length
+ * + bincode record of absolute slot window_base[g] + s, with entry_group / entry_len beside it.  *n_entries (device u64)
+ * = number of records; cells beyond `capacity` are counted but not written.  Cell order is unspecified (every group
+ * has its own WAL; the host routes by entry_group). */
+int ss_wal_commit_pack_dev(ss_ctx *ctx, const uint64_t *newly, const uint64_t *window_base, uint64_t n_groups,
+                           uint32_t commit_variant, uint8_t *entries, uint32_t *entry_group, uint32_t *entry_len,
+                           uint64_t capacity, uint64_t *n_entries);
+
+/* Reconstruct serving (crossword/messages.rs:577-632, rspaxos/messages.rs:468-517) for n_requests
+ * (slot, exclude) pairs of a Reconstruct message: request i concerns the instance of group req_group[i] whose shards sit
+ * in shard_planes (shard j at shard_planes + j*plane_stride + req_group[i]*shard_stride), of which this replica holds
+ * req_held[i]; req_status[i] is the instance's Status (>= 2 = Accepting).  reply_mask[i] = held & flip(exclude) -- 0 when
+ * the status is below Accepting or nothing is left, in which case the slot gets no entry in the reply -- and the
+ * selected shards are copied in index order, each in a round_up(shard_len,16)-byte slot, to out + reply_off[i]
+ * (16-byte aligned offsets). */
+int ss_reconstruct_serve_dev(ss_ctx *ctx, const uint8_t *shard_planes, uint64_t plane_stride, uint64_t shard_stride,
+                             uint32_t total_shards, uint32_t shard_len, const uint32_t *req_group,
+                             const uint32_t *req_held, const uint32_t *req_excl, const uint8_t *req_status,
+                             const uint64_t *reply_off, uint64_t n_requests, uint32_t *reply_mask, uint8_t *out);
 
 /* Crossword follower gossip planning (crossword/gossiping.rs:35-84 gossip_targets_excl) for
  * n_instances committed-but-incomplete instances of replica `me`: walking peers me+1, me+2, ... (mod population) and

@@ -18,7 +18,7 @@ _lib = None
 
 
 def build(force: bool = False) -> Path:
-    src = [_DIR / "ss_oracle.c", _DIR / "ss_oracle.h", _DIR / "Makefile"]
+    src = [_DIR / "ss_oracle.c", _DIR / "ss_wire.c", _DIR / "ss_oracle.h", _DIR / "Makefile"]
     if force or not LIB_PATH.exists() or any(s.stat().st_mtime > LIB_PATH.stat().st_mtime for s in src):
         subprocess.run(["make", "-C", str(_DIR), "-B" if force else "-s"], check=True,
                        stdout=subprocess.PIPE, stderr=subprocess.STDOUT)
@@ -338,3 +338,96 @@ def gossip_targets_excl(me: int, population: int, d: int, src_peer: int, avail: 
     lib().ssor_gossip_targets_excl.restype = C.c_uint32
     t = int(lib().ssor_gossip_targets_excl(me, population, d, src_peer, avail, _p(a), peer_alive, _p(excl)))
     return t, excl
+
+
+# ---- wire / WAL byte formats and reconstruct serving (oracle/ss_wire.c) ---------------------------------------
+def _shard_ptrs(shards):
+    bufs = [None if s is None else np.ascontiguousarray(np.frombuffer(bytes(s), dtype=np.uint8)) for s in shards]
+    arr = (C.c_void_p * len(bufs))(*[None if b is None else b.ctypes.data for b in bufs])
+    return arr, bufs
+
+
+def varint(v: int) -> bytes:
+    out = np.zeros(16, dtype=np.uint8)
+    lib().ssor_varint_put.restype = C.c_size_t
+    n = lib().ssor_varint_put(_p(out), C.c_uint64(v))
+    return out[:n].tobytes()
+
+
+def bitmap_encode(size: int, bits: int) -> bytes:
+    out = np.zeros(64, dtype=np.uint8)
+    lib().ssor_bitmap_encode.restype = C.c_size_t
+    n = lib().ssor_bitmap_encode(size, C.c_uint64(bits), _p(out))
+    return out[:n].tobytes()
+
+
+def frame_accept(accept_variant: int, slot: int, ballot: int, d: int, p: int, data_len: int, shards, assignment=None,
+                 assign_size: int = 0) -> bytes:
+    """shards: d+p entries, bytes or None.  assignment: list of per-replica shard bitmasks (Crossword) or None."""
+    L = next(len(s) for s in shards if s is not None)
+    arr, keep = _shard_ptrs(shards)
+    out = np.zeros(64 + (d + p) * (L + 16) + (len(assignment) * 16 if assignment else 0), dtype=np.uint8)
+    asg = np.ascontiguousarray(np.array(assignment, dtype=np.uint32)) if assignment is not None else None
+    lib().ssor_frame_accept.restype = C.c_size_t
+    n = lib().ssor_frame_accept(accept_variant, C.c_uint64(slot), C.c_uint64(ballot), d, p, C.c_uint64(data_len), C.c_uint64(L), arr,
+                                _p(asg), len(assignment) if assignment is not None else 0, assign_size, _p(out))
+    return out[:n].tobytes()
+
+
+def frame_accept_reply(reply_variant: int, slot: int, ballot: int, with_size: bool = False, size: int = 0) -> bytes:
+    out = np.zeros(64, dtype=np.uint8)
+    lib().ssor_frame_accept_reply.restype = C.c_size_t
+    n = lib().ssor_frame_accept_reply(reply_variant, C.c_uint64(slot), C.c_uint64(ballot), 1 if with_size else 0, C.c_uint64(size), _p(out))
+    return out[:n].tobytes()
+
+
+def parse_accept_reply(frame: bytes, reply_variant: int, with_size: bool = False):
+    """-> (frame_len, slot, ballot, size, kind); frame_len -1 = malformed, -2 = another message kind"""
+    buf = np.frombuffer(frame, dtype=np.uint8)
+    slot, ballot, size, kind = C.c_uint64(0), C.c_uint64(0), C.c_uint64(0), C.c_uint32(0)
+    lib().ssor_parse_accept_reply.restype = C.c_long
+    n = lib().ssor_parse_accept_reply(_p(np.ascontiguousarray(buf)), C.c_size_t(len(frame)), reply_variant, 1 if with_size else 0,
+                                      C.byref(slot), C.byref(ballot), C.byref(size), C.byref(kind))
+    return int(n), slot.value, ballot.value, size.value, kind.value
+
+
+def wal_accept_data(slot: int, ballot: int, d: int, p: int, data_len: int, shards) -> bytes:
+    L = next(len(s) for s in shards if s is not None)
+    arr, keep = _shard_ptrs(shards)
+    out = np.zeros(64 + (d + p) * (L + 16), dtype=np.uint8)
+    lib().ssor_wal_accept_data.restype = C.c_size_t
+    n = lib().ssor_wal_accept_data(C.c_uint64(slot), C.c_uint64(ballot), d, p, C.c_uint64(data_len), C.c_uint64(L), arr, _p(out))
+    return out[:n].tobytes()
+
+
+def wal_commit_slot(slot: int) -> bytes:
+    out = np.zeros(32, dtype=np.uint8)
+    lib().ssor_wal_commit_slot.restype = C.c_size_t
+    n = lib().ssor_wal_commit_slot(C.c_uint64(slot), _p(out))
+    return out[:n].tobytes()
+
+
+def decode_accept(frame: bytes, kind: int, with_assignment: bool = False):
+    """kind 0 = peer Accept frame, 1 = WAL AcceptData.  -> dict or None when malformed."""
+    buf = np.ascontiguousarray(np.frombuffer(frame, dtype=np.uint8))
+    variant, d, p, n_assign, asz = C.c_uint32(0), C.c_uint32(0), C.c_uint32(0), C.c_uint32(0), C.c_uint32(0)
+    slot, ballot, dl, sl = C.c_uint64(0), C.c_uint64(0), C.c_uint64(0), C.c_uint64(0)
+    shard_at = np.zeros(256, dtype=np.uint64)
+    asg = np.zeros(64, dtype=np.uint32)
+    lib().ssor_decode_accept.restype = C.c_long
+    n = lib().ssor_decode_accept(_p(buf), C.c_size_t(len(frame)), kind, C.byref(variant), C.byref(slot), C.byref(ballot), C.byref(d),
+                                 C.byref(p), C.byref(dl), C.byref(sl), _p(shard_at), 256, 1 if with_assignment else 0, _p(asg),
+                                 C.byref(n_assign), C.byref(asz))
+    if n < 0:
+        return None
+    t = d.value + p.value
+    L = sl.value
+    shards = [None if shard_at[j] == 0 else frame[int(shard_at[j]):int(shard_at[j]) + L] for j in range(t)]
+    return dict(length=int(n), variant=variant.value, slot=slot.value, ballot=ballot.value, d=d.value, p=p.value, data_len=dl.value,
+                shard_len=L, shards=shards, assignment=[int(x) for x in asg[:n_assign.value]] if with_assignment else None,
+                assign_size=asz.value)
+
+
+def reconstruct_serve_mask(held: int, exclude: int, total_shards: int, status: int) -> int:
+    lib().ssor_reconstruct_serve_mask.restype = C.c_uint32
+    return int(lib().ssor_reconstruct_serve_mask(held, exclude, total_shards, status))

@@ -197,6 +197,29 @@ uint32_t ssor_prepare_decide(uint32_t merged, uint32_t acks_cnt, uint32_t data_s
 uint32_t ssor_gossip_targets_excl(uint32_t me, uint32_t population, uint32_t data_shards, uint32_t src_peer,
                                   uint32_t avail, const uint32_t *assignment, uint32_t peer_alive, uint32_t *excl);
 
+
+/* ---- wire / WAL byte formats and reconstruct serving (ss_wire.c) ---- */
+size_t ssor_varint_put(uint8_t *out, uint64_t v);
+size_t ssor_varint_get(const uint8_t *in, size_t avail, uint64_t *v);
+size_t ssor_bitmap_encode(uint32_t size, uint64_t bits, uint8_t *out);
+size_t ssor_rscodeword_encode(uint32_t d, uint32_t p, uint64_t data_len, uint64_t shard_len,
+                              const uint8_t *const *shards, uint8_t *out);
+size_t ssor_frame_accept(uint32_t accept_variant, uint64_t slot, uint64_t ballot, uint32_t d, uint32_t p,
+                         uint64_t data_len, uint64_t shard_len, const uint8_t *const *shards,
+                         const uint32_t *assignment, uint32_t n_assign, uint32_t assign_size, uint8_t *out);
+size_t ssor_frame_accept_reply(uint32_t reply_variant, uint64_t slot, uint64_t ballot, int with_size, uint64_t size,
+                               uint8_t *out);
+long ssor_parse_accept_reply(const uint8_t *frame, size_t avail, uint32_t reply_variant, int with_size,
+                             uint64_t *slot, uint64_t *ballot, uint64_t *size, uint32_t *kind);
+size_t ssor_wal_accept_data(uint64_t slot, uint64_t ballot, uint32_t d, uint32_t p, uint64_t data_len,
+                            uint64_t shard_len, const uint8_t *const *shards, uint8_t *out);
+size_t ssor_wal_commit_slot(uint64_t slot, uint8_t *out);
+long ssor_decode_accept(const uint8_t *frame, size_t avail, int kind, uint32_t *variant, uint64_t *slot, uint64_t *ballot,
+                        uint32_t *d, uint32_t *p, uint64_t *data_len, uint64_t *shard_len, uint64_t *shard_at,
+                        uint32_t max_shards, int with_assignment, uint32_t *assignment, uint32_t *n_assign,
+                        uint32_t *assign_size);
+uint32_t ssor_reconstruct_serve_mask(uint32_t held, uint32_t exclude, uint32_t total_shards, int status);
+
 #ifdef __cplusplus
 }
 #endif

@@ -89,6 +89,11 @@ SIGNATURES = {
     "ss_prepare_merge_dev": (_i, [_vp, _vp, _vp, _u32, _u64, _vp, _u32, _u32, _u32, _vp, _vp, _vp]),
     "ss_accept_step_fused_dev": (_i, [_vp, _vp, _u64, _u32, _u64, _vp, _u64, _u64, _u32, _vp, _u32, _u32, _vp, _vp]),
     "ss_accept_step_fused": (_i, [_vp, _vp, _u64, _u32, _u64, _vp, _u64, _u64, _vp, _u32, _u32, _vp, _vp]),
+    "ss_frame_accept_max_len": (_u64, [_vp, _u32]),
+    "ss_frame_accept_pack_dev": (_i, [_vp, _vp, _vp, _u64, _u64, _vp, _u32, _vp, _u32, _vp, _vp, _u64, _vp, _u64, _vp, _vp]),
+    "ss_accept_reply_parse_dev": (_i, [_vp, _vp, _u64, _vp, _vp, _vp, _vp, _u64, _u64, _u32, _i, _vp, _vp, _vp, _vp, _vp]),
+    "ss_wal_commit_pack_dev": (_i, [_vp, _vp, _vp, _u64, _u32, _vp, _vp, _vp, _u64, _vp]),
+    "ss_reconstruct_serve_dev": (_i, [_vp, _vp, _u64, _u64, _u32, _u32, _vp, _vp, _vp, _vp, _vp, _u64, _vp, _vp]),
     "ss_engine_create": (_i, [_vp, _vp, _u64, C.POINTER(_vp)]),
     "ss_engine_destroy": (_i, [_vp]),
     "ss_engine_view_get": (_i, [_vp, _vp]),
@@ -111,6 +116,12 @@ class StepSync(C.Structure):
 
 
 SS_PROTO_MULTIPAXOS, SS_PROTO_RSPAXOS, SS_PROTO_CROSSWORD, SS_PROTO_RAFT, SS_PROTO_CRAFT = range(5)
+
+
+class FrameSpec(C.Structure):
+    """ss_frame_spec"""
+    _fields_ = [("kind", C.c_uint32), ("msg_variant", C.c_uint32), ("data_shards", C.c_uint32), ("parity_shards", C.c_uint32),
+                ("data_len", C.c_uint32), ("population", C.c_uint32), ("with_assignment", C.c_uint32), ("assign_size", C.c_uint32)]
 
 
 class EngineConfig(C.Structure):

@@ -13,7 +13,7 @@ from pathlib import Path
 PKG = Path(__file__).resolve().parent
 CSRC = PKG / "csrc"
 OUT = PKG / "libsummerset_b200.so"
-SOURCES = ["capi.cu", "rs_kernels.cu", "tally_kernels.cu", "engine.cu"]
+SOURCES = ["capi.cu", "rs_kernels.cu", "tally_kernels.cu", "engine.cu", "wire_kernels.cu"]
 HEADERS = ["ss_internal.hpp", "device_common.cuh", "gf256.hpp", "static_codes.hpp", "../../include/summerset_b200.h"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 CCBIN = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"

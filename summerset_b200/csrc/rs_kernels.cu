@@ -1453,10 +1453,11 @@ int launch_crossword_distribute(ss_rs_coder *coder, const uint8_t *data, const u
             return set_error(SS_ERR_INVALID_ARG, "replica log %d is null or not 16-byte aligned", r);
         P.rep[r] = replica_logs[r];
     }
-    // variant bits 0-3 (tuning): 0 = cooperative kernel (default), 1 = warp per codeword, one column per pass,
-    // 2 = warp per codeword, two columns per pass (the round-1 kernel)
+    // variant bits 0-3 (tuning; measured in profiles/r02_distribute_variants.txt): 0 = warp per codeword, two columns per
+    // pass (default: 13.0 ms on the cfg-4 mix), 1 = one column per pass at 5 CTAs/SM (14.1 ms), 3 = cooperative CTA per long
+    // codeword (18.7 ms: more DRAM traffic, lower DRAM efficiency)
     const int vk = coder->variant & 15;
-    if (vk == 2) {
+    if (vk != 1 && vk != 3) {
         rs32_crossword_distribute_kernel<true><<<ragged_grid(ctx, n), kThreads, 0, ctx->stream>>>(P);
         coder->last_kernel = "rs32_crossword_distribute_kernel<pair>";
     } else if (vk == 1) {

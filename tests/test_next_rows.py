@@ -188,8 +188,8 @@ def test_prepare_merge_on_gpu_and_recovery_roundtrip(ctx, oracle):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("variant,kernel", [(0, "rs32_crossword_distribute_coop_kernel"), (1, "rs32_crossword_distribute_kernel"),
-                                            (2, "rs32_crossword_distribute_kernel<pair>")])
+@pytest.mark.parametrize("variant,kernel", [(0, "rs32_crossword_distribute_kernel<pair>"), (1, "rs32_crossword_distribute_kernel"),
+                                            (3, "rs32_crossword_distribute_coop_kernel")])
 def test_crossword_distribute_matches_assignment_and_oracle(ctx, oracle, variant, kernel):
     """config 4 distribute (crossword/request.rs:137-185): every replica's log holds exactly the shards the balanced
     round-robin assignment gives it (crossword/mod.rs:866-888), bytes equal to the oracle's encode."""

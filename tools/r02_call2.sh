@@ -14,29 +14,7 @@ timeout 600 $TR --master-port 29512 bench.py --gpus 2 --steps 40 --warmup 3 --la
 for v in 0 256 512 768; do
   timeout 300 $TR --master-port 2952$((v/256)) bench.py --gpus 2 --steps 20 --warmup 3 --lag 2 --no-sub --no-e2e --variant $v > gpurun_out/r02_bench_n2_st$v.json 2>/dev/null
 done
-# distribute kernel variants + reconstruct (one rank each is enough)
-for v in 0 1 2; do
-  timeout 300 python bench.py --workload cfg4 --steps 10 --warmup 3 --variant $v > gpurun_out/r02_cfg4_v$v.json 2>/dev/null
-done
-timeout 300 python bench.py --workload cfg3b --steps 20 --warmup 3 > gpurun_out/r02_cfg3b_row.json 2>/dev/null
-for w in 32 96 224; do timeout 300 python bench.py --workload cfg3b --steps 20 --warmup 3 --variant $w > gpurun_out/r02_cfg3b_row_v$w.json 2>/dev/null; done
-python - <<'PY'
-import json,glob
-for f in sorted(glob.glob('gpurun_out/r02_cfg4_v*.json')+glob.glob('gpurun_out/r02_cfg3b_row*.json')):
-    try:
-        j=json.loads(open(f).read().strip().splitlines()[-1])
-        print(f, 'ms', round(j['ms_per_step'],4), 'frac', round(j['roofline']['frac'],3), j['roofline']['kernel'], (j.get('distribute') or {}).get('kernel_ms'), ((j.get('distribute') or {}).get('roofline') or {}).get('frac'))
-    except Exception as e: print(f,'ERR',e)
-PY
-# CPU arm: schedule / thread-count / binding sweep (host only)
-for cfg in "static 0 close" "dynamic 0 close" "static 128 close" "dynamic 128 close" "static 0 spread" "static 32 close"; do
-  set -- $cfg
-  SS_CPU_SCHED=$1 SS_CPU_THREADS=$( [ "$2" = 0 ] && echo "" || echo $2 ) SS_CPU_BIND=$3 timeout 200 python bench.py --impl reference --steps 7 --warmup 1 2>/dev/null | python -c "
-import json,sys
-j=json.loads(sys.stdin.read().strip().splitlines()[-1]); c=j['cpu_baseline']
-print('cpu_arm sched=$1 threads=$2 bind=$3 ->', round(j['value'],1), 'GB/s median; min', round(c['min'],1), 'max', round(c['max'],1), 'cores', c['cores'])" >> gpurun_out/r02_cpu_arm_sweep.txt
-done
-cat gpurun_out/r02_cpu_arm_sweep.txt
+timeout 200 ./tools/hbm_probe_bin > gpurun_out/r02_hbm_patterns.txt 2>&1; cat gpurun_out/r02_hbm_patterns.txt
 python - <<'PY'
 import json
 for f in ('r02_bench_n2_lag2','r02_bench_n2_lag1','r02_bench_n2_st0','r02_bench_n2_st256','r02_bench_n2_st512','r02_bench_n2_st768'):
