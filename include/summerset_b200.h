@@ -539,8 +539,16 @@ int ss_engine_raft_ingest(ss_engine *engine, const uint32_t *rec_group, const ui
  *   bit 11    run-time coefficient masks even when the matrix is one of the compile-time cluster codes
  *   bit 13    never / bit 14 always use the packed layout (m codewords side by side per CTA, tail columns apart)
  *   bit 15    software-pipelined packed loop also for shards that are not 16-byte aligned
- *   bit 16    small-code reconstruct kernel: two columns per lane and pass (80 registers) instead of one (64) */
+ *   bit 16    small-code reconstruct kernel: two columns per lane and pass (80 registers) instead of one (64)
+ *   bit 17    no run-time specialisation: codes without a compile-time table use the run-time-mask kernels */
 int ss_rs_set_variant(ss_rs_coder *coder, int variant);
+/* Codes without a compile-time table (anything but the cluster codes RS(2,1) RS(3,1) RS(3,2) RS(4,2) RS(4,3) RS(5,4)) with
+ * d <= 8 get their row / packed encode kernels specialised at run time by NVRTC for the coder's own parity rows (once
+ * per coder, on the first batched encode).  ss_rs_jit_status tells what happened; if libnvrtc is unavailable the coder
+ * keeps the run-time-mask kernels.  ss_jit_selftest compiles the kernels for RS(d,p) without a GPU and returns the
+ * CUBIN size (> 0) or a negative error code with the compiler log in `log`. */
+const char *ss_rs_jit_status(const ss_rs_coder *coder);
+long ss_jit_selftest(int data_shards, int parity_shards, char *log, size_t log_cap);
 /* name of the kernel the last batch call on this coder launched (static string) */
 const char *ss_rs_last_kernel(const ss_rs_coder *coder);
 

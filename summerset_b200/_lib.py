@@ -106,6 +106,8 @@ SIGNATURES = {
     "ss_engine_raft_ingest": (_i, [_vp, _vp, _vp, _vp, _u64]),
     "ss_rs_set_variant": (_i, [_vp, _i]),
     "ss_rs_last_kernel": (C.c_char_p, [_vp]),
+    "ss_rs_jit_status": (C.c_char_p, [_vp]),
+    "ss_jit_selftest": (C.c_long, [_i, _i, C.c_char_p, _sz]),
 }
 
 

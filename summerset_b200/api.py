@@ -242,6 +242,64 @@ def _ctx_extras():
                                           pol.ctypes.data, pol.shape[0], peer_alive, N, _ptr(targets), _ptr(excl)))
         return targets, excl
 
+    def frame_accept_pack(self, shard_planes: torch.Tensor, data_len: int, d: int, p: int, policies: Sequence[Sequence[int]],
+                          policy_idx: Optional[torch.Tensor], peer: int, slot: torch.Tensor, ballot: torch.Tensor, kind: int = 0,
+                          msg_variant: int = 2, with_assignment: bool = False, max_shards: Optional[int] = None):
+        """General Accept / WAL AcceptData packer.  shard_planes uint8 [d+p, n, shard_stride]; policies [K][population] shard
+        bitmasks.  Returns (out uint8 [n, frame_stride], frame_off int64 [n], frame_len int32 [n])."""
+        T, n, ss = shard_planes.shape
+        assert T == d + p and shard_planes.is_contiguous()
+        pol = np.ascontiguousarray(np.array(policies, dtype=np.uint32))
+        dev = shard_planes.device
+        pol_dev = torch.from_numpy(pol.view(np.int32)).to(dev)
+        spec = _lib.FrameSpec(kind, msg_variant, d, p, data_len, pol.shape[1], 1 if with_assignment else 0, T)
+        stride = int(self.lib.ss_frame_accept_max_len(C.byref(spec), max_shards if max_shards is not None else T))
+        out = torch.full((n, stride), 0xA5, dtype=torch.uint8, device=dev)       # the C ABI does not require a zeroed buffer
+        off = torch.empty(n, dtype=torch.int64, device=dev)
+        ln = torch.empty(n, dtype=torch.int32, device=dev)
+        check(self.lib.ss_frame_accept_pack_dev(self.h, C.byref(spec), _ptr(shard_planes), n * ss, ss, _ptr(pol_dev), pol.shape[0],
+                                                _ptr(policy_idx), peer, _ptr(slot), _ptr(ballot), n, _ptr(out), stride, _ptr(off), _ptr(ln)))
+        return out, off, ln
+
+    def accept_reply_parse(self, buf: torch.Tensor, frame_off: torch.Tensor, frame_group: torch.Tensor, frame_peer: torch.Tensor,
+                           window_base: torch.Tensor, reply_variant: int = 3, with_size: bool = False):
+        """AcceptReply frames -> (rec_group int32, rec_slot uint8, rec_peer uint8, rec_ballot int64, rec_kind int32)."""
+        assert buf.dtype == torch.uint8 and frame_off.dtype == torch.int64 and frame_group.dtype == torch.int32
+        assert frame_peer.dtype == torch.uint8 and window_base.dtype == torch.int64
+        n, dev = frame_off.numel(), buf.device
+        rg = torch.empty(n, dtype=torch.int32, device=dev); rs_ = torch.empty(n, dtype=torch.uint8, device=dev)
+        rp = torch.empty(n, dtype=torch.uint8, device=dev); rb = torch.empty(n, dtype=torch.int64, device=dev)
+        rk = torch.empty(n, dtype=torch.int32, device=dev)
+        check(self.lib.ss_accept_reply_parse_dev(self.h, _ptr(buf), buf.numel(), _ptr(frame_off), _ptr(frame_group), _ptr(frame_peer),
+                                                 _ptr(window_base), n, window_base.numel(), reply_variant, 1 if with_size else 0,
+                                                 _ptr(rg), _ptr(rs_), _ptr(rp), _ptr(rb), _ptr(rk)))
+        return rg, rs_, rp, rb, rk
+
+    def wal_commit_pack(self, newly: torch.Tensor, window_base: torch.Tensor, capacity: int, commit_variant: int = 2):
+        """newly int64 [G] -> (entries uint8 [capacity, 24], entry_group int32, entry_len int32, n_entries int64 [1])."""
+        dev = newly.device
+        entries = torch.zeros((capacity, 24), dtype=torch.uint8, device=dev)
+        eg = torch.empty(capacity, dtype=torch.int32, device=dev); el = torch.empty(capacity, dtype=torch.int32, device=dev)
+        cnt = torch.zeros(1, dtype=torch.int64, device=dev)
+        check(self.lib.ss_wal_commit_pack_dev(self.h, _ptr(newly), _ptr(window_base), newly.numel(), commit_variant, _ptr(entries),
+                                              _ptr(eg), _ptr(el), capacity, _ptr(cnt)))
+        return entries, eg, el, cnt
+
+    def reconstruct_serve(self, shard_planes: torch.Tensor, shard_len_: int, req_group: torch.Tensor, req_held: torch.Tensor,
+                          req_excl: torch.Tensor, req_status: torch.Tensor, reply_off: torch.Tensor, out_bytes: int):
+        """shard_planes uint8 [T, n, shard_stride].  Returns (reply_mask int32 [R], out uint8 [out_bytes])."""
+        T, n, ss = shard_planes.shape
+        dev = shard_planes.device
+        mask = torch.empty(req_group.numel(), dtype=torch.int32, device=dev)
+        out = torch.full((out_bytes,), 0x77, dtype=torch.uint8, device=dev)
+        check(self.lib.ss_reconstruct_serve_dev(self.h, _ptr(shard_planes), n * ss, ss, T, shard_len_, _ptr(req_group), _ptr(req_held),
+                                                _ptr(req_excl), _ptr(req_status), _ptr(reply_off), req_group.numel(), _ptr(mask), _ptr(out)))
+        return mask, out
+
+    Context.frame_accept_pack = frame_accept_pack
+    Context.accept_reply_parse = accept_reply_parse
+    Context.wal_commit_pack = wal_commit_pack
+    Context.reconstruct_serve = reconstruct_serve
     Context.gossip_plan = gossip_plan
     Context.frame_accept_batch = frame_accept_batch
     Context.raft_kth_match = raft_kth_match

@@ -525,6 +525,7 @@ int ss_rs_coder_destroy(ss_rs_coder *c) {
     if (c->dec_progs_data) cudaFree(c->dec_progs_data);
     if (c->fast_progs) cudaFree(c->fast_progs);
     if (c->fast_progs_data) cudaFree(c->fast_progs_data);
+    jit_release(c);
     if (c->ctx) ctx_release(c->ctx);
     delete c;
     return SS_OK;

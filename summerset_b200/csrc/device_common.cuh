@@ -1,8 +1,19 @@
 // device_common.cuh -- device-side helpers shared by the kernel files (sm_100a).
 #pragma once
+#ifndef __CUDACC_RTC__
 #include <cuda_runtime.h>
 
 #include <cstdint>
+#else
+// NVRTC (run-time specialisation, jit.cu): no host headers; the fixed-width types are spelled out
+typedef unsigned char uint8_t;
+typedef unsigned short uint16_t;
+typedef unsigned int uint32_t;
+typedef int int32_t;
+typedef unsigned long long uint64_t;
+typedef long long int64_t;
+typedef unsigned long long uintptr_t;
+#endif
 
 namespace ssb {
 namespace dev {
@@ -118,6 +129,25 @@ __device__ __forceinline__ uint4 raw16_finish(const Raw16 &r, int nvalid) {
     return keep_bytes(o, nvalid);
 }
 __device__ __forceinline__ uint4 load16(const uint8_t *p, int nvalid) { return raw16_finish(raw16_issue(p, nvalid), nvalid); }
+
+// bytes [s, s+16) of the 32-byte window {lo, hi}; s is kernel-uniform
+__device__ __forceinline__ uint4 funnel16(const uint4 &lo, const uint4 &hi, uint32_t s) {
+    const uint32_t sel = 0x3210u + 0x1111u * (s & 3u);
+    switch (s >> 2) {
+        case 0:
+            return make_uint4(prmt(lo.x, lo.y, sel), prmt(lo.y, lo.z, sel), prmt(lo.z, lo.w, sel),
+                              prmt(lo.w, hi.x, sel));
+        case 1:
+            return make_uint4(prmt(lo.y, lo.z, sel), prmt(lo.z, lo.w, sel), prmt(lo.w, hi.x, sel),
+                              prmt(hi.x, hi.y, sel));
+        case 2:
+            return make_uint4(prmt(lo.z, lo.w, sel), prmt(lo.w, hi.x, sel), prmt(hi.x, hi.y, sel),
+                              prmt(hi.y, hi.z, sel));
+        default:
+            return make_uint4(prmt(lo.w, hi.x, sel), prmt(hi.x, hi.y, sel), prmt(hi.y, hi.z, sel),
+                              prmt(hi.z, hi.w, sel));
+    }
+}
 
 // Store the first nvalid (1..16) bytes of v at p.  padded: p is 16-byte aligned with 16 bytes of
 // capacity, and the bytes past nvalid are written as zeros (one 128-bit store).  Otherwise exact.

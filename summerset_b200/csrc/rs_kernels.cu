@@ -35,9 +35,11 @@
 #include "ss_internal.hpp"
 #include "static_codes.hpp"
 #include "rs32_decode.cuh"
+#include "horner_row_kernels.cuh"
 
 namespace ssb {
 
+using dev::funnel16;
 using dev::keep_bytes;
 using dev::load16;
 using dev::msb_mask;
@@ -175,25 +177,6 @@ struct Enc32Row {
     uint32_t *commit_bar;
     dev::FlagWait wait;       // replicate mode: every CTA first waits for the followers' ack flags (flags == nullptr: no wait)
 };
-
-// bytes [s, s+16) of the 32-byte window {lo, hi}; s is kernel-uniform
-__device__ __forceinline__ uint4 funnel16(const uint4 &lo, const uint4 &hi, uint32_t s) {
-    const uint32_t sel = 0x3210u + 0x1111u * (s & 3u);
-    switch (s >> 2) {
-        case 0:
-            return make_uint4(dev::prmt(lo.x, lo.y, sel), dev::prmt(lo.y, lo.z, sel), dev::prmt(lo.z, lo.w, sel),
-                              dev::prmt(lo.w, hi.x, sel));
-        case 1:
-            return make_uint4(dev::prmt(lo.y, lo.z, sel), dev::prmt(lo.z, lo.w, sel), dev::prmt(lo.w, hi.x, sel),
-                              dev::prmt(hi.x, hi.y, sel));
-        case 2:
-            return make_uint4(dev::prmt(lo.z, lo.w, sel), dev::prmt(lo.w, hi.x, sel), dev::prmt(hi.x, hi.y, sel),
-                              dev::prmt(hi.y, hi.z, sel));
-        default:
-            return make_uint4(dev::prmt(lo.w, hi.x, sel), dev::prmt(hi.x, hi.y, sel), dev::prmt(hi.y, hi.z, sel),
-                              dev::prmt(hi.z, hi.w, sel));
-    }
-}
 
 // one Horner step r*x ^ u on four packed field elements: shift on the FMA pipe (imad), then
 // prmt (sign mask) + two lop3 on the ALU pipe.
@@ -931,260 +914,6 @@ horner_encode_ragged_kernel(const __grid_constant__ EncRagged E, const uint32_t 
 }
 
 
-// ------------------------------------------------------------------------------------------------
-// Generic "row" encode kernel for any code with d <= 8 (RS(2,1), RS(4,3), RS(5,4), RS(6,4) ...): the structure of
-// rs32_encode_row_kernel -- a CTA walks codewords, thread = column, kernel-uniform byte funnels, rotating block
-// assignment, coalesced tally prologue -- with the parity rows evaluated by run-time Horner programs.
-// hmT8[(j*8 + k)*8 + i] = all-ones if bit k of coefficient M[d+j][i] is set.
-// ------------------------------------------------------------------------------------------------
-struct EncRowGen {
-    const uint8_t *data;
-    uint64_t data_stride;
-    uint8_t *parity;
-    uint64_t plane_stride, shard_stride;
-    uint32_t n, len, L, vpc, fast_cols;
-    uint32_t d, p;
-    uint32_t pack_m, tail_ctas, ntail;   // packed kernel: codewords per CTA pass, CTAs that do tail columns, tail columns per codeword
-    const uint32_t *hmT8;
-    uint8_t top[kMaxP];
-    const uint64_t *planes;   // fused tally (nullptr: none); G == n
-    uint32_t R, threshold;
-    uint64_t *committed;
-    uint32_t *commit_bar;
-};
-
-// multiply four packed field elements by x: shift on the FMA pipe, prmt sign mask + two lop3 on the ALU pipe.
-// (A flavour that took the reduction term from a high multiply -- 1 ALU + 3 FMA-pipe instructions -- measured the
-// same on B200 and was dropped: profiles/r01_cluster_codes_sweep.txt, variant 4096.)
-__device__ __forceinline__ uint32_t xtime_word(uint32_t x) { return ((x * 2u) & 0xfefefefeu) ^ (msb_mask(x) & 0x1d1d1d1du); }
-
-// the d source vectors of column k of one codeword, funnelled to shard alignment and masked to the payload
-template <int D, bool MASKED, bool EXACT>
-__device__ __forceinline__ int row_load_column(const EncRowGen &P, const uint8_t *__restrict__ src, uint32_t k, uint4 (&x)[D]) {
-    auto clamp16 = [](int64_t r) { return r > 16 ? 16 : (r < 0 ? 0 : static_cast<int>(r)); };
-    const int d = EXACT ? D : static_cast<int>(P.d);            // EXACT: the code's width is the template's
-    uint4 lo[D], hi[D];
-#pragma unroll
-    for (int i = 0; i < D; ++i) {
-        lo[i] = make_uint4(0u, 0u, 0u, 0u);
-        hi[i] = lo[i];
-        if (i < d) {
-            const uint32_t pos = static_cast<uint32_t>(i) * P.L + k;
-            const uint32_t s = (static_cast<uint32_t>(i) * P.L) & 15u;      // kernel-uniform (k is a multiple of 16)
-            const int nv = MASKED ? clamp16(static_cast<int64_t>(P.len) - pos) : 16;
-            if (!MASKED || nv > 0) lo[i] = dev::ldg128(src + pos - s);
-            // hi stays zero when unused: copying lo here would make every later load wait for this one to land
-            if (s != 0u && (!MASKED || static_cast<int>(s) + nv > 16)) hi[i] = dev::ldg128(src + pos - s + 16u);
-        }
-    }
-    const int onv = MASKED ? clamp16(static_cast<int64_t>(P.L) - k) : 16;
-#pragma unroll
-    for (int i = 0; i < D; ++i) {
-        x[i] = lo[i];
-        if (i < d) {
-            const uint32_t s = (static_cast<uint32_t>(i) * P.L) & 15u;
-            if (s != 0u) x[i] = funnel16(lo[i], hi[i], s);
-            if (MASKED) {
-                const int nv = clamp16(static_cast<int64_t>(P.len) - (static_cast<uint32_t>(i) * P.L + k));
-                x[i] = keep_bytes(x[i], nv < onv ? nv : onv);
-            }
-        }
-    }
-    return onv;
-}
-
-// the p parity vectors of one column from its d source vectors x[], stored at out + j*plane_stride + k
-template <int D, int CODE, bool MASKED>
-__device__ __forceinline__ void parity_rows(const EncRowGen &P, const uint4 (&x)[D], int onv, uint8_t *__restrict__ out, uint32_t k) {
-    if constexpr (CODE != kCodeGeneric) {
-        static_assert(D == static_code_d(CODE), "static code width");
-#pragma unroll
-        for (int j = 0; j < static_code_p(CODE); ++j) {
-            const int top = static_code_top(CODE, j);
-            uint4 acc = make_uint4(0u, 0u, 0u, 0u);
-#pragma unroll
-            for (int kk = 7; kk >= 0; --kk) {
-                if (kk > top) continue;
-                if (kk != top) {
-                    acc.x = xtime_word(acc.x); acc.y = xtime_word(acc.y);
-                    acc.z = xtime_word(acc.z); acc.w = xtime_word(acc.w);
-                }
-#pragma unroll
-                for (int i = 0; i < D; ++i)
-                    if ((static_code_coef(CODE, j, i) >> kk) & 1u) {
-                        acc.x ^= x[i].x; acc.y ^= x[i].y; acc.z ^= x[i].z; acc.w ^= x[i].w;
-                    }
-            }
-            if (MASKED) acc = keep_bytes(acc, onv);
-            dev::stg128_cs(out + static_cast<uint64_t>(j) * P.plane_stride + k, acc);
-        }
-    } else {
-        for (uint32_t j = 0; j < P.p; ++j) {
-            const uint4 *hm = reinterpret_cast<const uint4 *>(P.hmT8 + j * 64u);
-            uint4 acc = make_uint4(0u, 0u, 0u, 0u);
-            const int top = P.top[j];
-            for (int kk = top; kk >= 0; --kk) {
-                const uint4 m0 = __ldg(hm + kk * 2);
-                const uint4 m1 = D > 4 ? __ldg(hm + kk * 2 + 1) : make_uint4(0u, 0u, 0u, 0u);
-                const uint32_t mk[8] = {m0.x, m0.y, m0.z, m0.w, m1.x, m1.y, m1.z, m1.w};
-                if (kk != top) {
-                    acc.x = xtime_word(acc.x); acc.y = xtime_word(acc.y);
-                    acc.z = xtime_word(acc.z); acc.w = xtime_word(acc.w);
-                }
-#pragma unroll
-                for (int i = 0; i < D; ++i) {
-                    acc.x ^= x[i].x & mk[i];
-                    acc.y ^= x[i].y & mk[i];
-                    acc.z ^= x[i].z & mk[i];
-                    acc.w ^= x[i].w & mk[i];
-                }
-            }
-            if (MASKED) acc = keep_bytes(acc, onv);
-            dev::stg128_cs(out + static_cast<uint64_t>(j) * P.plane_stride + k, acc);
-        }
-    }
-}
-
-template <int D, int CODE, bool MASKED>
-__device__ __forceinline__ void horner_row_column(const EncRowGen &P, const uint8_t *__restrict__ src, uint8_t *__restrict__ out,
-                                                  uint32_t k) {
-    uint4 x[D];
-    const int onv = row_load_column<D, MASKED, CODE != kCodeGeneric>(P, src, k, x);
-    parity_rows<D, CODE, MASKED>(P, x, onv, out, k);
-}
-
-// Split load for the software-pipelined packed kernel (complete columns only): issue the aligned 128-bit loads of one
-// column into raw registers, and later funnel them to shard alignment.  Shard 0 always starts 16-byte aligned; with
-// ALIGNED (shard_len % 16 == 0) every shard does and no second load exists.
-template <int D, bool ALIGNED>
-struct RawColumn {
-    uint4 lo[D];
-    uint4 hi[ALIGNED ? 1 : D];
-};
-template <int D, bool ALIGNED, bool EXACT>
-__device__ __forceinline__ void raw_issue(const EncRowGen &P, const uint8_t *__restrict__ src, uint32_t k, RawColumn<D, ALIGNED> &r) {
-    const int d = EXACT ? D : static_cast<int>(P.d);
-#pragma unroll
-    for (int i = 0; i < D; ++i) {
-        if (i < d) {
-            const uint32_t pos = static_cast<uint32_t>(i) * P.L + k;
-            const uint32_t s = ALIGNED ? 0u : (static_cast<uint32_t>(i) * P.L) & 15u;
-            r.lo[i] = dev::ldg128(src + pos - s);
-            if constexpr (!ALIGNED) {
-                if (i > 0) {
-                    r.hi[i] = make_uint4(0u, 0u, 0u, 0u);       // never a copy of lo: that would wait for the load
-                    if (s != 0u) r.hi[i] = dev::ldg128(src + pos - s + 16u);
-                }
-            }
-        } else {
-            r.lo[i] = make_uint4(0u, 0u, 0u, 0u);
-        }
-    }
-}
-template <int D, bool ALIGNED, bool EXACT>
-__device__ __forceinline__ void raw_finish(const EncRowGen &P, const RawColumn<D, ALIGNED> &r, uint4 (&x)[D]) {
-    const int d = EXACT ? D : static_cast<int>(P.d);
-#pragma unroll
-    for (int i = 0; i < D; ++i) {
-        x[i] = r.lo[i];
-        if constexpr (!ALIGNED) {
-            if (i > 0 && i < d) {
-                const uint32_t s = (static_cast<uint32_t>(i) * P.L) & 15u;
-                if (s != 0u) x[i] = funnel16(r.lo[i], r.hi[i], s);
-            }
-        }
-    }
-}
-
-template <int D, int CODE, int MAXT, int MINB>
-__global__ void __launch_bounds__(MAXT, MINB) horner_encode_row_kernel(const __grid_constant__ EncRowGen P) {
-    const uint32_t lane = threadIdx.x & 31u, wid = threadIdx.x >> 5, nblk = blockDim.x >> 5;
-    if (P.planes != nullptr) {
-        const uint32_t per = (P.n + gridDim.x - 1) / gridDim.x;
-        const uint32_t lo = blockIdx.x * per;
-        const uint32_t hi = lo + per < P.n ? lo + per : P.n;
-        for (uint32_t g = lo + threadIdx.x; g < hi; g += blockDim.x) {
-            const uint64_t w = dev::tally_word(P.planes, P.R, P.n, g, P.threshold);
-            P.committed[g] = w;
-            if (P.commit_bar != nullptr) P.commit_bar[g] = dev::commit_prefix(w);
-        }
-    }
-    uint32_t wb = wid;
-#pragma unroll 1
-    for (uint32_t g = blockIdx.x; g < P.n; g += gridDim.x) {
-        const uint32_t v = wb * 32u + lane;
-        const bool masked = wb * 32u + 32u > P.fast_cols;           // warp-uniform
-        wb = (wb + 1u == nblk) ? 0u : wb + 1u;                       // rotate the warp -> block assignment
-        if (v >= P.vpc) continue;
-        const uint8_t *src = P.data + static_cast<uint64_t>(g) * P.data_stride;
-        uint8_t *out = P.parity + static_cast<uint64_t>(g) * P.shard_stride;
-        if (!masked) horner_row_column<D, CODE, false>(P, src, out, v * 16u);
-        else horner_row_column<D, CODE, true>(P, src, out, v * 16u);
-    }
-}
-
-// Packed flavour of the row kernel, for shard lengths whose column count is not a multiple of 32.  The complete
-// columns (every source window inside the payload, full 16-byte output) of pack_m consecutive codewords are laid side by
-// side over the CTA's threads with a FIXED thread -> (codeword, column) map -- one division per thread for the whole
-// kernel -- so nearly every lane does unmasked work (RS(5,4) on 4 KB: 5 x 51 columns on 256 threads instead of 52 on 64).
-// The incomplete columns (normally one per codeword) go to the first tail_ctas CTAs, one column per thread, masked.
-// resident 256-thread CTAs per SM for the packed kernel: the pipelined main loop holds one column being computed
-// (4D registers) and the next one in flight (4D aligned, 8D-4 otherwise)
-template <int D, bool ALIGNED, bool PIPE>
-constexpr int packed_min_blocks() {
-    if (!PIPE) return D <= 3 ? 6 : D <= 5 ? 5 : D <= 6 ? 4 : 3;          // 40 / 48 / 64 / 80 registers
-    constexpr int need = 4 * D + (ALIGNED ? 4 * D : 8 * D - 4) + 22;
-    constexpr int b = 65536 / (256 * need);
-    return b > 6 ? 6 : (b < 1 ? 1 : b);
-}
-
-template <int D, int CODE, bool ALIGNED, bool PIPE>
-__global__ void __launch_bounds__(256, packed_min_blocks<D, ALIGNED, PIPE>()) horner_encode_packed_kernel(const __grid_constant__ EncRowGen P) {
-    if (P.planes != nullptr) {
-        const uint32_t per = (P.n + gridDim.x - 1) / gridDim.x;
-        const uint32_t lo = blockIdx.x * per;
-        const uint32_t hi = lo + per < P.n ? lo + per : P.n;
-        for (uint32_t g = lo + threadIdx.x; g < hi; g += blockDim.x) {
-            const uint64_t w = dev::tally_word(P.planes, P.R, P.n, g, P.threshold);
-            P.committed[g] = w;
-            if (P.commit_bar != nullptr) P.commit_bar[g] = dev::commit_prefix(w);
-        }
-    }
-    if (blockIdx.x < P.tail_ctas) {
-        const uint64_t item = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
-        const uint64_t g = P.ntail == 1u ? item : item / P.ntail;
-        if (g >= P.n) return;
-        const uint32_t col = P.fast_cols + static_cast<uint32_t>(item - g * P.ntail);
-        horner_row_column<D, CODE, true>(P, P.data + g * P.data_stride, P.parity + g * P.shard_stride, col * 16u);
-        return;
-    }
-    const uint32_t cg = threadIdx.x / P.fast_cols;               // fast_cols >= 1 whenever main CTAs exist
-    const uint32_t k = (threadIdx.x - cg * P.fast_cols) * 16u;
-    if (cg >= P.pack_m) return;
-    const uint64_t step = static_cast<uint64_t>(gridDim.x - P.tail_ctas) * P.pack_m;
-    uint64_t g = static_cast<uint64_t>(blockIdx.x - P.tail_ctas) * P.pack_m + cg;
-    if (g >= P.n) return;
-    if constexpr (!PIPE) {
-#pragma unroll 1
-        for (; g < P.n; g += step)
-            horner_row_column<D, CODE, false>(P, P.data + g * P.data_stride, P.parity + g * P.shard_stride, k);
-        return;
-    }
-    // software pipeline: the loads of this thread's next column are in flight while the current one is computed
-    RawColumn<D, ALIGNED> raw;
-    raw_issue<D, ALIGNED, CODE != kCodeGeneric>(P, P.data + g * P.data_stride, k, raw);
-#pragma unroll 1
-    while (true) {
-        uint4 x[D];
-        raw_finish<D, ALIGNED, CODE != kCodeGeneric>(P, raw, x);
-        const uint64_t gn = g + step;
-        if (gn < P.n) raw_issue<D, ALIGNED, CODE != kCodeGeneric>(P, P.data + gn * P.data_stride, k, raw);
-        parity_rows<D, CODE, false>(P, x, 16, P.parity + g * P.shard_stride, k);
-        if (gn >= P.n) break;
-        g = gn;
-    }
-}
-
 int match_static_code(int d, int p, const uint8_t *matrix) {
     for (int c = 0; c < kNumStaticCodes; ++c) {
         if (static_code_d(c) != d || static_code_p(c) != p) continue;
@@ -1576,7 +1305,15 @@ int launch_rs_encode(ss_rs_coder *coder, const EncGeom &g, const TallyArgs *tall
                 Rg.planes = tally->planes; Rg.R = tally->R; Rg.threshold = tally->threshold;
                 Rg.committed = tally->committed; Rg.commit_bar = tally->commit_bar;
             }
-            const int sc = ((coder->variant >> 11) & 1) ? kCodeGeneric : coder->static_code;   // bit 11: run-time masks
+            // which flavour of the kernels: a compile-time cluster code, the coder's own NVRTC specialisation (any other
+            // matrix; compiled on first use), or run-time coefficient masks (variant bit 11 forces them, bit 17 skips NVRTC)
+            int sc = ((coder->variant >> 11) & 1) ? kCodeGeneric : coder->static_code;
+            const bool jit_allowed = sc == kCodeGeneric && !((coder->variant >> 11) & 1) && !((coder->variant >> 17) & 1);
+            auto launch_jit = [&](int which, uint32_t grid_x, uint32_t block_x) -> int {
+                void *args[] = {&Rg};
+                SS_CUDA(cudaLaunchKernel(reinterpret_cast<const void *>(coder->jit_kernel[which]), dim3(grid_x), dim3(block_x), args, 0, st));
+                return SS_OK;
+            };
             // Packed flavour when the one-codeword-per-pass layout would idle or mask a good part of the lanes
             // (bit 13 forces it off, bit 14 forces it on).
             const uint32_t fc = Rg.fast_cols;
@@ -1586,6 +1323,11 @@ int launch_rs_encode(ss_rs_coder *coder, const EncGeom &g, const TallyArgs *tall
             if ((coder->variant >> 14) & 1) packed = true;
             // software-pipelined main loop: always when every shard is 16-byte aligned; bit 15 selects it for unaligned too
             const bool pipe = (L & 15u) == 0u || ((coder->variant >> 15) & 1);
+            if (jit_allowed) {
+                // the one instance this geometry needs (compiled by NVRTC on first use, ~1 s; then cached in the coder)
+                const int which = packed ? ((L & 15u) == 0u ? 2 : pipe ? 3 : 4) : (row_threads > 128u ? 1 : 0);
+                if (jit_ensure(coder, which) == SS_OK) sc = kCodeJit;
+            }
             if (packed) {
                 // threads: the multiple of 32 (<= 256) that wastes the fewest lanes; ties go to the larger CTA
                 uint32_t T = 256, m = fc ? 256u / fc : 0u;
@@ -1604,7 +1346,7 @@ int launch_rs_encode(ss_rs_coder *coder, const EncGeom &g, const TallyArgs *tall
                 uint64_t main_ctas = 0;
                 if (m) {
                     const uint32_t dcap = d <= 2 ? 2 : d == 3 ? 3 : d == 4 ? 4 : d <= 6 ? 6 : 8;      // dispatch_d's capacity
-                    const uint32_t dt = sc != kCodeGeneric ? static_cast<uint32_t>(d) : dcap;
+                    const uint32_t dt = sc != kCodeGeneric ? static_cast<uint32_t>(d) : dcap;       // static and NVRTC kernels are exact-width
                     const uint32_t reg_need = 4u * dt + ((L & 15u) == 0u ? 4u * dt : 8u * dt - 4u) + 22u;
                     uint32_t rb = 65536u / (256u * reg_need); rb = rb > 6u ? 6u : (rb < 1u ? 1u : rb);
                     if (!pipe) rb = dt <= 3 ? 6u : dt <= 5 ? 5u : dt <= 6 ? 4u : 3u;
@@ -1627,6 +1369,7 @@ int launch_rs_encode(ss_rs_coder *coder, const EncGeom &g, const TallyArgs *tall
                         gop(std::integral_constant<int, static_code_d(C)>{}, CC);
                     };
                     switch (sc) {
+                        case kCodeJit: SS_TRY(launch_jit((L & 15u) == 0u ? 2 : pipe ? 3 : 4, grid, T)); break;
                         case kCode21: gop_static(std::integral_constant<int, kCode21>{}); break;
                         case kCode43: gop_static(std::integral_constant<int, kCode43>{}); break;
                         case kCode54: gop_static(std::integral_constant<int, kCode54>{}); break;
@@ -1638,7 +1381,9 @@ int launch_rs_encode(ss_rs_coder *coder, const EncGeom &g, const TallyArgs *tall
                                 return SS_OK;
                             }));
                     }
-                    if (sc != kCodeGeneric)
+                    if (sc == kCodeJit)
+                        coder->last_kernel = Rg.planes ? "horner_encode_packed_kernel<nvrtc>+tally" : "horner_encode_packed_kernel<nvrtc>";
+                    else if (sc != kCodeGeneric)
                         coder->last_kernel = Rg.planes ? "horner_encode_packed_kernel<static code>+tally" : "horner_encode_packed_kernel<static code>";
                     else
                         coder->last_kernel = Rg.planes ? "horner_encode_packed_kernel+tally" : "horner_encode_packed_kernel";
@@ -1649,6 +1394,7 @@ int launch_rs_encode(ss_rs_coder *coder, const EncGeom &g, const TallyArgs *tall
             }
             Rg.pack_m = 0; Rg.tail_ctas = 0; Rg.ntail = 0;
             const uint32_t threads = row_threads;
+            if (sc == kCodeJit && jit_ensure(coder, threads > 128u ? 1 : 0) != SS_OK) sc = kCodeGeneric;   // (packed grid did not fit)
             uint32_t per_sm = 2048u / threads; if (per_sm > 32u) per_sm = 32u;
             uint64_t ctas = static_cast<uint64_t>(ctx->sm_count) * per_sm * 64ull;
             if (ctas > g.n) ctas = g.n;
@@ -1671,6 +1417,7 @@ int launch_rs_encode(ss_rs_coder *coder, const EncGeom &g, const TallyArgs *tall
                 go(std::integral_constant<int, static_code_d(C)>{}, CC);
             };
             switch (sc) {
+                case kCodeJit: SS_TRY(launch_jit(threads > 128 ? 1 : 0, grid, threads)); break;
                 case kCode21: go_static(std::integral_constant<int, kCode21>{}); break;
                 case kCode43: go_static(std::integral_constant<int, kCode43>{}); break;
                 case kCode54: go_static(std::integral_constant<int, kCode54>{}); break;
@@ -1682,7 +1429,9 @@ int launch_rs_encode(ss_rs_coder *coder, const EncGeom &g, const TallyArgs *tall
                         return SS_OK;
                     }));
             }
-            if (sc != kCodeGeneric)
+            if (sc == kCodeJit)
+                coder->last_kernel = Rg.planes ? "horner_encode_row_kernel<nvrtc>+tally" : "horner_encode_row_kernel<nvrtc>";
+            else if (sc != kCodeGeneric)
                 coder->last_kernel = Rg.planes ? "horner_encode_row_kernel<static code>+tally" : "horner_encode_row_kernel<static code>";
             else
                 coder->last_kernel = Rg.planes ? "horner_encode_row_kernel+tally" : "horner_encode_row_kernel";

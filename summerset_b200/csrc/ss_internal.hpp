@@ -109,6 +109,11 @@ struct ss_rs_coder {
     size_t prog_stride = 0;           // bytes per program
     bool batch_ok = false;            // d,p within the batched kernels' limits
     bool dec_ok = false;              // d+p small enough for the per-pattern decode table
+    // run-time specialised encode kernels (jit.cu): 0 = not tried, 1 = ready, -1 = unavailable (run-time-mask kernels stay)
+    int jit_state[5] = {};
+    std::string jit_message;
+    void *jit_library[5] = {};
+    cudaKernel_t jit_kernel[5] = {};  // row<128>, row<256>, packed<aligned,pipe>, packed<unaligned,pipe>, packed<unaligned>
     std::vector<uint8_t> verify_buf;  // ss_rs_verify: recomputed parity (grow-only, reused across calls)
     std::vector<uint8_t *> verify_ptrs;
 };
@@ -178,6 +183,10 @@ int launch_raft_scan_ring(ss_ctx *ctx, const uint32_t *match, uint32_t n_peers, 
 // (policy, ack set) -> commit bit table of the Crossword predicate, from DEVICE policies
 int launch_crossword_lut(ss_ctx *ctx, const uint32_t *d_policies, uint32_t n_policies, uint32_t n_replicas, uint32_t T, uint32_t d,
                          uint32_t majority, uint32_t f, int balanced, uint32_t *d_lut_bits);
+
+// run-time specialisation of the row / packed encode kernels for a coder's matrix (jit.cu)
+int jit_ensure(ss_rs_coder *coder, int which);
+void jit_release(ss_rs_coder *coder);
 
 // multi-GPU step flags
 int make_flag_wait(ss_ctx *ctx, const ss_step_sync *sync, dev::FlagWait *out);

@@ -2,7 +2,9 @@
 // Shared by the CUDA kernels (rs_kernels.cu) and a host-only test (tests/cpp/test_static_codes.cpp) that pins every
 // table entry against gf256.hpp's coding matrix, i.e. against the construction the reed-solomon-erasure crate uses.
 #pragma once
+#ifndef __CUDACC_RTC__
 #include <cstdint>
+#endif
 
 #if defined(__CUDACC__)
 #define SSB_HD __host__ __device__
@@ -17,14 +19,28 @@ namespace ssb {
 // (4 -> RS(3,1), 6 -> RS(4,2)).  For those the parity rows are compile-time constants, so the Horner evaluation is
 // fully unrolled and only the set coefficient bits cost an instruction.  The coder only selects a static code when its
 // run-time matrix (built by gf256.hpp exactly as the crate builds it) equals the table below byte for byte.
-enum : int { kCodeGeneric = -1, kCode21 = 0, kCode43 = 1, kCode54 = 2, kCode42 = 3, kCode31 = 4, kNumStaticCodes = 5 };
+enum : int { kCodeGeneric = -1, kCode21 = 0, kCode43 = 1, kCode54 = 2, kCode42 = 3, kCode31 = 4, kNumStaticCodes = 5,
+             kCodeJit = 100 /* the code NVRTC specialises at run time: SS_JIT_D x SS_JIT_P coefficients SS_JIT_COEFS */ };
+#if defined(SS_JIT_D)
+SSB_HD constexpr uint32_t jit_coef(int idx) {
+    constexpr uint32_t c[] = {SS_JIT_COEFS};
+    return c[idx];
+}
+#else
+SSB_HD constexpr uint32_t jit_coef(int) { return 0u; }
+#define SS_JIT_D 0
+#define SS_JIT_P 0
+#endif
 SSB_HD constexpr int static_code_d(int code) {
+    if (code == kCodeJit) return SS_JIT_D;
     return code == kCode21 ? 2 : code == kCode43 ? 4 : code == kCode54 ? 5 : code == kCode42 ? 4 : code == kCode31 ? 3 : 0;
 }
 SSB_HD constexpr int static_code_p(int code) {
+    if (code == kCodeJit) return SS_JIT_P;
     return code == kCode21 ? 1 : code == kCode43 ? 3 : code == kCode54 ? 4 : code == kCode42 ? 2 : code == kCode31 ? 1 : 0;
 }
 SSB_HD constexpr uint32_t static_code_coef(int code, int j, int i) {
+    if (code == kCodeJit) return jit_coef(j * SS_JIT_D + i);
     if (code == kCode21) return i == 0 ? 0x03u : 0x02u;
     if (code == kCode31) return 0x01u;
     if (code == kCode43 || code == kCode42) {

@@ -235,33 +235,246 @@ def test_crossword_distribute_matches_assignment_and_oracle(ctx, oracle, variant
     assert (got[:, total:] == 0x33).all()                               # nothing written past the logs
 
 
-@pytest.mark.gpu
-@pytest.mark.parametrize("d,p,data_len,shard_idx", [(3, 2, 4096, 0), (3, 2, 4096, 4), (3, 2, 18, 1), (3, 2, 1, 2), (4, 3, 1000, 5), (3, 2, 80000, 3)])
-def test_accept_frames_match_host_encoder(ctx, oracle, d, p, data_len, shard_idx):
-    """GPU-built Accept frames == summerset_b200.wire byte for byte, for slots / ballots on every varint boundary."""
-    from summerset_b200 import wire
-    from summerset_b200.api import ReedSolomon, round_up, shard_len
-    rng = np.random.default_rng(8)
-    n = 257
-    rs = ReedSolomon(ctx, d, p)
-    data = wl.payload_uniform(n, data_len, seed_extra=shard_idx)
+SPECIAL = [0, 1, 250, 251, 252, 65535, 65536, (1 << 32) - 1, 1 << 32, (1 << 63) + 5]      # every varint boundary
+
+
+def _slots_ballots(rng, n):
+    slot = np.array([SPECIAL[i % len(SPECIAL)] if i < 40 else int(rng.integers(0, 1 << 40)) for i in range(n)], dtype=np.uint64)
+    ballot = np.array([SPECIAL[(i // 3) % len(SPECIAL)] if i < 60 else int(rng.integers(0, 1 << 20)) for i in range(n)], dtype=np.uint64)
+    return slot, ballot
+
+
+def _shard_planes(oracle, d, p, data, data_len):
+    from summerset_b200.api import round_up, shard_len
+    n = data.shape[0]
     L = shard_len(data_len, d); ds = round_up(L, 16)
     planes = np.zeros((d + p, n, ds), dtype=np.uint8)
     for g in range(n):
         planes[:d, g, :L] = oracle.cw_split(data[g, :data_len].tobytes(), d)
     planes[d:] = oracle.rs_encode_uniform(d, p, data, data_len)
-    special = [0, 1, 250, 251, 252, 65535, 65536, (1 << 32) - 1, 1 << 32, (1 << 63) + 5]
-    slot = np.array([special[i % len(special)] if i < 40 else int(rng.integers(0, 1 << 40)) for i in range(n)], dtype=np.uint64)
-    ballot = np.array([special[(i // 3) % len(special)] if i < 60 else int(rng.integers(0, 1 << 20)) for i in range(n)], dtype=np.uint64)
-    out, off, ln = ctx.frame_accept_batch(torch.from_numpy(planes[shard_idx]).to(DEV), shard_idx, d, p, data_len,
-                                          _t(slot), _t(ballot))
+    return planes, L, ds
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("d,p,data_len,shard_idx", [(3, 2, 4096, 0), (3, 2, 4096, 4), (3, 2, 18, 1), (3, 2, 1, 2), (4, 3, 1000, 5),
+                                                     (3, 2, 80000, 3)])
+def test_accept_frames_single_shard_fast_path_matches_oracle(ctx, oracle, d, p, data_len, shard_idx):
+    """ss_frame_accept_batch_dev (one shard per frame, aligned copy) == the oracle's C encoder (oracle/ss_wire.c) byte for
+    byte, for slots / ballots on every varint boundary; the output buffer is NOT zeroed beforehand."""
+    from summerset_b200 import wire
+    from summerset_b200.api import ReedSolomon
+    rng = np.random.default_rng(8)
+    n = 257
+    data = wl.payload_uniform(n, data_len, seed_extra=shard_idx)
+    planes, L, ds = _shard_planes(oracle, d, p, data, data_len)
+    slot, ballot = _slots_ballots(rng, n)
+    out, off, ln = ctx.frame_accept_batch(torch.from_numpy(planes[shard_idx]).to(DEV), shard_idx, d, p, data_len, _t(slot), _t(ballot))
     torch.cuda.synchronize()
     out = out.cpu().numpy().reshape(-1); off = off.cpu().numpy(); ln = ln.cpu().numpy()
     for g in range(n):
-        want = wire.rspaxos_accept_frame(int(slot[g]), int(ballot[g]), d, p, data_len, shard_idx, planes[shard_idx, g, :L].tobytes())
+        shards = [None] * (d + p)
+        shards[shard_idx] = planes[shard_idx, g, :L].tobytes()
+        want = oracle.frame_accept(2, int(slot[g]), int(ballot[g]), d, p, data_len, shards)
         got = out[int(off[g]):int(off[g]) + int(ln[g])].tobytes()
         assert got == want, (g, int(slot[g]), int(ballot[g]))
-        assert (int(off[g]) + 8 + (len(want) - 8 - L - (d + p - shard_idx))) % 16 == 0     # payload 16-byte aligned
+        assert got == wire.rspaxos_accept_frame(int(slot[g]), int(ballot[g]), d, p, data_len, shard_idx, shards[shard_idx])  # host encoder too
+        assert (int(off[g]) + len(want) - L - (d + p - shard_idx)) % 16 == 0     # shard payload 16-byte aligned
+        dec = oracle.decode_accept(got, 0)                                       # decode(encode(x)) == x
+        assert dec and (dec["slot"], dec["ballot"], dec["d"], dec["p"], dec["data_len"], dec["shard_len"]) == \
+            (int(slot[g]), int(ballot[g]), d, p, data_len, L) and dec["shards"] == shards
+
+
+@pytest.mark.gpu
+def test_accept_frames_many_shards_and_late_shard_index(ctx, oracle):
+    """more than 32 shards (None runs longer than a warp) and a shard index far beyond the old header array."""
+    rng = np.random.default_rng(9)
+    d, p, data_len, n = 40, 30, 4000, 33
+    L = (data_len + d - 1) // d; ds = (L + 15) // 16 * 16
+    for shard_idx in (0, 33, 69):
+        plane = rng.integers(0, 256, (n, ds), dtype=np.uint8)
+        plane[:, L:] = 0
+        slot, ballot = _slots_ballots(rng, n)
+        out, off, ln = ctx.frame_accept_batch(torch.from_numpy(plane).to(DEV), shard_idx, d, p, data_len, _t(slot), _t(ballot))
+        torch.cuda.synchronize()
+        out = out.cpu().numpy().reshape(-1); off = off.cpu().numpy(); ln = ln.cpu().numpy()
+        for g in range(n):
+            shards = [None] * (d + p)
+            shards[shard_idx] = plane[g, :L].tobytes()
+            assert out[int(off[g]):int(off[g]) + int(ln[g])].tobytes() == oracle.frame_accept(2, int(slot[g]), int(ballot[g]), d, p, data_len, shards)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("kind", ["rspaxos_accept", "crossword_accept", "wal_accept_data"])
+@pytest.mark.parametrize("data_len", [1, 100, 4096, 9001])
+def test_general_frame_packer_matches_oracle(ctx, oracle, kind, data_len):
+    """ss_frame_accept_pack_dev: PeerMsg::Accept frames for one peer with the shards of its assignment (one in RSPaxos,
+    spr in Crossword, plus assignment: Vec<Bitmap>) and WalEntry::AcceptData records, byte for byte against the oracle's
+    encoder (rspaxos/mod.rs:212-232,283-288, crossword/mod.rs:356-362, rscoding.rs:43-72, bitmap.rs:20-30)."""
+    rng = np.random.default_rng(len(kind) + data_len)
+    d, p, pop, n = 3, 2, 5, 131
+    T = d + p
+    data = wl.payload_uniform(n, data_len, seed_extra=data_len)
+    planes, L, ds = _shard_planes(oracle, d, p, data, data_len)
+    slot, ballot = _slots_ballots(rng, n)
+    if kind == "crossword_accept":
+        policies = [list(map(int, oracle.cw_brr_assignment(pop, T, spr))) for spr in (1, 2, 3)]
+        policies.append([int(x) for x in rng.integers(0, 1 << T, pop)])           # an unbalanced assignment, possibly empty masks
+        pidx = rng.integers(0, len(policies), n).astype(np.uint8)
+    else:
+        policies = [[1 << r for r in range(pop)]]                                 # replica r holds shard r (rspaxos/request.rs:135-137)
+        pidx = np.zeros(n, dtype=np.uint8)
+    for peer in (0, 3, 4):
+        out, off, ln = ctx.frame_accept_pack(torch.from_numpy(planes).to(DEV), data_len, d, p, policies, torch.from_numpy(pidx).to(DEV),
+                                             peer, _t(slot), _t(ballot), kind=1 if kind == "wal_accept_data" else 0,
+                                             msg_variant=1 if kind == "wal_accept_data" else 2, with_assignment=kind == "crossword_accept")
+        torch.cuda.synchronize()
+        out = out.cpu().numpy().reshape(-1); off = off.cpu().numpy(); ln = ln.cpu().numpy()
+        for g in range(n):
+            mask = policies[int(pidx[g])][peer]
+            shards = [planes[j, g, :L].tobytes() if (mask >> j) & 1 else None for j in range(T)]
+            if not any(s is not None for s in shards):
+                # a peer the assignment gives nothing: every shard None, the codeword still states its geometry
+                got = out[int(off[g]):int(off[g]) + int(ln[g])].tobytes()
+                dec = oracle.decode_accept(got, 0, kind == "crossword_accept")
+                assert dec and dec["shards"] == [None] * T and dec["shard_len"] == L and dec["slot"] == int(slot[g])
+                continue
+            if kind == "wal_accept_data":
+                want = oracle.wal_accept_data(int(slot[g]), int(ballot[g]), d, p, data_len, shards)
+            else:
+                want = oracle.frame_accept(2, int(slot[g]), int(ballot[g]), d, p, data_len, shards,
+                                           policies[int(pidx[g])] if kind == "crossword_accept" else None, T)
+            got = out[int(off[g]):int(off[g]) + int(ln[g])].tobytes()
+            assert got == want, (kind, peer, g)
+            dec = oracle.decode_accept(got, 1 if kind == "wal_accept_data" else 0, kind == "crossword_accept")
+            assert dec and dec["shards"] == shards and dec["ballot"] == int(ballot[g])
+            if kind == "crossword_accept":
+                assert dec["assignment"] == policies[int(pidx[g])] and dec["assign_size"] == T
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("with_size", [False, True])
+def test_accept_reply_parser_feeds_ingest(ctx, oracle, with_size):
+    """AcceptReply frames (rspaxos/mod.rs:290-291; crossword/mod.rs:365-373 with size + reply_ts) interleaved with other
+    messages, a truncated frame and garbage -> records identical to the oracle's parser, window-relative slots, and the
+    records drive ss_ack_ingest_dev to the same planes as the oracle's per-message handler."""
+    rng = np.random.default_rng(21 + with_size)
+    G, R, n = 300, 5, 5000
+    base = rng.integers(0, 1 << 34, G).astype(np.uint64)
+    bal = rng.integers(1, 1 << 33, G).astype(np.uint64)
+    frames, fgroup, fpeer = [], [], []
+    for i in range(n):
+        g = int(rng.integers(0, G)); peer = int(rng.integers(0, R))
+        r = rng.random()
+        slot = int(base[g]) + int(rng.integers(-3, 70))            # below the window, inside, beyond
+        slot = max(slot, 0)
+        ballot = int(bal[g]) if rng.random() < 0.8 else int(rng.integers(1, 1 << 33))
+        if r < 0.8:
+            fr = oracle.frame_accept_reply(3, slot, ballot, with_size, int(rng.integers(0, 1 << 20)))
+            if with_size and rng.random() < 0.3:                    # reply_ts: Some(SystemTime{secs, nanos})
+                body = fr[8:-1] + b"\x01" + oracle.varint(1_700_000_000) + oracle.varint(123456789)
+                fr = len(body).to_bytes(8, "big") + body
+        elif r < 0.9:
+            fr = oracle.frame_accept_reply(6, slot, ballot)         # some other PeerMsg (Heartbeat index): not ours
+        elif r < 0.95:
+            fr = oracle.frame_accept_reply(3, slot, ballot, with_size, 5)[:-2]      # truncated body, stale length
+        else:
+            fr = (9).to_bytes(8, "big") + bytes(rng.integers(251, 256, 9).astype(np.uint8))   # garbage varints
+        frames.append(fr); fgroup.append(g); fpeer.append(peer)
+    offs = np.concatenate([[0], np.cumsum([len(f) for f in frames])]).astype(np.uint64)
+    buf = np.frombuffer(b"".join(frames), dtype=np.uint8)
+    rg, rs_, rp, rb, rk = ctx.accept_reply_parse(torch.from_numpy(buf.copy()).to(DEV), _t(offs[:-1]), _t(np.array(fgroup, dtype=np.uint32)),
+                                                 torch.from_numpy(np.array(fpeer, dtype=np.uint8)).to(DEV), _t(base), 3, with_size)
+    torch.cuda.synchronize()
+    rg, rs_, rp, rb, rk = (x.cpu().numpy() for x in (rg, rs_, rp, rb, rk))
+    n_ok = 0
+    for i in range(n):
+        # the parser only sees the bytes up to the next frame's offset... the oracle gets the same view: the whole rest of the buffer
+        ln, slot, ballot, size, kind = oracle.parse_accept_reply(buf[int(offs[i]):].tobytes()[:4096], 3, with_size)
+        if ln > 0:
+            n_ok += 1
+            assert rk[i] == 3 and int(rb[i]) == ballot
+            rel = slot - int(base[fgroup[i]])
+            assert rs_[i] == (rel if 0 <= rel < 64 else 0xff)
+        elif ln == -2:
+            assert np.uint32(rk[i]) == np.uint32(kind) and rs_[i] == 0xff
+        else:
+            assert np.uint32(rk[i]) == 0xFFFFFFFF and rs_[i] == 0xff
+        assert rg[i] == fgroup[i] and rp[i] == fpeer[i]
+    assert n_ok > 0.6 * n
+    # the records go straight into the ingest kernel
+    inst_bal = np.zeros(G * 64, dtype=np.uint64); accepting = np.full(G, np.uint64(0xFFFFFFFFFFFFFFFF)); status = np.full(G * 64, oracle.ST_ACCEPTING, dtype=np.uint8)
+    acks = np.zeros(G * 64, dtype=np.uint16)
+    planes = torch.zeros((R, G), dtype=torch.int64, device=DEV)
+    ctx.ack_ingest(_t(rg.view(np.uint32)), torch.from_numpy(rs_).to(DEV), torch.from_numpy(rp).to(DEV), _t(rb.view(np.uint64)),
+                   _t(bal), _t(inst_bal), _t(accepting), R, planes)
+    torch.cuda.synchronize()
+    keep = rs_ != 0xff
+    oracle.tally_stream(rg.view(np.uint32)[keep], rs_[keep], rp[keep], rb.view(np.uint64)[keep], 64, R, 99, bal, inst_bal, status, acks)
+    got = planes.cpu().numpy().view(np.uint64)
+    for r in range(R):
+        want_plane = np.packbits(((acks.reshape(G, 64) >> r) & 1).astype(np.uint8), axis=1, bitorder="little").view(np.uint64).reshape(-1)
+        assert (got[r] == want_plane).all()
+
+
+@pytest.mark.gpu
+def test_wal_commit_slot_packer(ctx, oracle):
+    """newly committed instances -> WalEntry::CommitSlot{slot} records (rspaxos/mod.rs:231) with the StorageHub length prefix"""
+    rng = np.random.default_rng(31)
+    G = 4001
+    newly = (rng.integers(0, 1 << 62, G).astype(np.uint64) & rng.integers(0, 1 << 62, G).astype(np.uint64) & rng.integers(0, 1 << 62, G).astype(np.uint64))
+    newly[::7] = 0
+    newly[5] = np.uint64(1 << 63)
+    base = rng.integers(0, 1 << 40, G).astype(np.uint64)
+    base[:4] = [0, 186, 250, 65530]                                 # varint boundaries
+    total = int(sum(bin(int(w)).count("1") for w in newly))
+    entries, eg, el, cnt = ctx.wal_commit_pack(_t(newly), _t(base), total + 10)
+    torch.cuda.synchronize()
+    assert int(cnt) == total
+    entries = entries.cpu().numpy(); eg = eg.cpu().numpy(); el = el.cpu().numpy()
+    got = sorted((int(eg[e]), entries[e, :int(el[e])].tobytes()) for e in range(total))
+    want = sorted((g, oracle.wal_commit_slot(int(base[g]) + s)) for g in range(G) for s in range(64) if (int(newly[g]) >> s) & 1)
+    assert got == want
+    # capacity smaller than needed: counted, nothing written past the end
+    entries2, _, _, cnt2 = ctx.wal_commit_pack(_t(newly), _t(base), 16)
+    torch.cuda.synchronize()
+    assert int(cnt2) == total and entries2.shape[0] == 16
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("T,data_len", [(5, 4096), (5, 18), (7, 1000), (10, 3000)])
+def test_reconstruct_serving_matches_oracle(ctx, oracle, T, data_len):
+    """crossword/messages.rs:577-632: reply shards = held & flip(exclude) for instances at least Accepting, copied out
+    packed; no entry when the status is lower or nothing is left."""
+    from summerset_b200.api import round_up
+    rng = np.random.default_rng(T + data_len)
+    d = T // 2 + 1 if T != 10 else 6
+    n = 500
+    L = (data_len + d - 1) // d; ds = round_up(L, 16)
+    planes = rng.integers(0, 256, (T, n, ds), dtype=np.uint8)
+    planes[:, :, L:] = 0
+    R = 1300
+    req_group = rng.integers(0, n, R).astype(np.uint32)
+    held = rng.integers(0, 1 << T, R).astype(np.uint32)
+    excl = rng.integers(0, 1 << T, R).astype(np.uint32)
+    excl[::11] = (1 << T) - 1                                       # requester already has everything
+    status = rng.integers(0, 5, R).astype(np.uint8)
+    want_mask = np.array([oracle.reconstruct_serve_mask(int(h), int(x), T, int(st)) for h, x, st in zip(held, excl, status)], dtype=np.uint32)
+    cnt = np.array([bin(int(m)).count("1") for m in want_mask], dtype=np.int64)
+    reply_off = np.concatenate([[0], np.cumsum(cnt * ds)[:-1]]).astype(np.uint64)
+    total = int((cnt * ds).sum())
+    mask, out = ctx.reconstruct_serve(torch.from_numpy(planes).to(DEV), L, _t(req_group), _t(held), _t(excl), torch.from_numpy(status).to(DEV),
+                                      _t(reply_off), total + 64)
+    torch.cuda.synchronize()
+    assert (mask.cpu().numpy().view(np.uint32) == want_mask).all()
+    out = out.cpu().numpy()
+    assert (out[total:] == 0x77).all()
+    for i in range(R):
+        o = int(reply_off[i])
+        for j in range(T):
+            if (int(want_mask[i]) >> j) & 1:
+                assert (out[o:o + ds] == planes[j, req_group[i]]).all(), (i, j)      # subset_copy: the shard, bit for bit
+                o += ds
+    assert (want_mask != 0).mean() > 0.3
 
 
 @pytest.mark.gpu
