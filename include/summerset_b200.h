@@ -317,8 +317,9 @@ int ss_ctx_device_status(ss_ctx *ctx, uint32_t *status);
  * local groups (data shards included) is written to shard_planes[j] + g*shard_stride, where each shard_planes[j]
  * is a device pointer into LOCAL memory or into a PEER GPU's memory (ss_ipc_open): the encode kernel itself
  * delivers every replica's shard over NVLink -- no pack pass, no separate collective.  shard_planes is a HOST
- * array of d+p pointers; every target slot is 16-byte aligned with capacity round_up(L,16).  RS(3,2) with
- * 16-byte-aligned uniform payloads only (SS_ERR_UNSUPPORTED otherwise).  sync (may be NULL): the tally waits for
+ * array of d+p pointers; every target slot is 16-byte aligned with capacity round_up(L,16).  Any code with d <= 8
+ * data shards (every Summerset cluster code; others are specialised at run time), 16-byte-aligned uniform payloads of
+ * any length (SS_ERR_UNSUPPORTED otherwise).  sync (may be NULL): the tally waits for
  * sync->wait_flags (the followers' ack flags) and the followers are signalled when every shard has landed. */
 int ss_accept_step_replicate_dev(ss_rs_coder *coder, const uint8_t *data, uint64_t data_stride, uint32_t data_len,
                                  uint64_t n_groups, uint8_t *const *shard_planes, uint64_t shard_stride,

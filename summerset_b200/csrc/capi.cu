@@ -703,19 +703,19 @@ int ss_accept_step_replicate_dev(ss_rs_coder *c, const uint8_t *data, uint64_t d
     if (c == nullptr) return set_error(SS_ERR_INVALID_ARG, "null coder");
     if (n_groups == 0) return SS_OK;
     if (!data || !shard_planes) return set_error(SS_ERR_INVALID_ARG, "null buffer");
-    if (!c->is_rs32) return set_error(SS_ERR_UNSUPPORTED, "replicate step is implemented for RS(3,2) (coder is %d,%d)", c->d, c->p);
-    const uint64_t L = (uint64_t(data_len) + 2) / 3, vpc = (L + 15) / 16;
-    if (data_len == 0 || vpc > 256 || ((reinterpret_cast<uintptr_t>(data) | data_stride | shard_stride) & 15u) ||
-        shard_stride < vpc * 16)
-        return set_error(SS_ERR_UNSUPPORTED, "replicate step needs 16-byte aligned uniform payloads of at most 12 KB");
-    for (int j = 0; j < 5; ++j)
+    const int d = c->d, nsh = c->d + c->p;
+    if (d > 8 || nsh > 16) return set_error(SS_ERR_UNSUPPORTED, "replicate step needs d <= 8 data shards (coder is %d,%d)", c->d, c->p);
+    const uint64_t L = (uint64_t(data_len) + d - 1) / d, vpc = (L + 15) / 16;
+    if (data_len == 0 || ((reinterpret_cast<uintptr_t>(data) | data_stride | shard_stride) & 15u) || shard_stride < vpc * 16)
+        return set_error(SS_ERR_UNSUPPORTED, "replicate step needs 16-byte aligned uniform payloads and padded shard slots");
+    for (int j = 0; j < nsh; ++j)
         if (shard_planes[j] == nullptr || (reinterpret_cast<uintptr_t>(shard_planes[j]) & 15u))
             return set_error(SS_ERR_INVALID_ARG, "shard plane %d is null or not 16-byte aligned", j);
     EncGeom g{};
     g.data = data; g.data_off = nullptr; g.data_stride = data_stride; g.uni_len = data_len;
-    g.parity = shard_planes[3]; g.plane_stride = 16; g.shard_stride = shard_stride; g.n = n_groups;
+    g.parity = shard_planes[d]; g.plane_stride = 16; g.shard_stride = shard_stride; g.n = n_groups;
     g.flags = SS_RS_OUT_PADDED16 | SS_RS_EMIT_DATA;
-    g.planes5 = shard_planes;
+    g.plane_ptrs = shard_planes;
     SS_TRY(make_flag_wait(c->ctx, sync, &g.wait));
     TallyArgs t;
     const bool with_tally = planes != nullptr;
@@ -726,7 +726,7 @@ int ss_accept_step_replicate_dev(ss_rs_coder *c, const uint8_t *data, uint64_t d
         t.commit_bar = commit_bar;
     }
     const int saved = c->variant;
-    if ((c->variant & 15) == 1) c->variant &= ~15;     // the flat kernel has no peer-plane mode
+    if ((c->variant & 15) == 1 || (c->variant & 15) == 5) c->variant &= ~15;     // the flat / bit-plane kernels have no peer-plane mode
     const int rc = launch_rs_encode(c, g, with_tally ? &t : nullptr);
     c->variant = saved;
     if (rc != SS_OK) return rc;

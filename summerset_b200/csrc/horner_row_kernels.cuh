@@ -31,8 +31,11 @@ using dev::msb_mask;
 struct EncRowGen {
     const uint8_t *data;
     uint64_t data_stride;
-    uint8_t *parity;
-    uint64_t plane_stride, shard_stride;
+    uint8_t *plane[16];       // base of shard plane j, j < d + p (local memory, or a peer GPU's memory mapped over NVLink);
+                              // planes 0..d-1 (data shards) are only written when emit_data is set
+    uint64_t shard_stride;
+    uint32_t emit_data;
+    dev::FlagWait wait;       // replicate mode: wait for the followers' ack flags before the tally (flags == nullptr: none)
     uint32_t n, len, L, vpc, fast_cols;
     uint32_t d, p;
     uint32_t pack_m, tail_ctas, ntail;   // packed kernel: codewords per CTA pass, CTAs that do tail columns, tail columns per codeword
@@ -84,9 +87,15 @@ __device__ __forceinline__ int row_load_column(const EncRowGen &P, const uint8_t
     return onv;
 }
 
-// the p parity vectors of one column from its d source vectors x[], stored at out + j*plane_stride + k
+// the p parity vectors of one column from its d source vectors x[], stored at plane[d + j] + out_off (and, with
+// emit_data, the source vectors themselves at plane[i] + out_off: the pack-for-send of subset_copy, rscoding.rs:255-293)
 template <int D, int CODE, bool MASKED>
-__device__ __forceinline__ void parity_rows(const EncRowGen &P, const uint4 (&x)[D], int onv, uint8_t *__restrict__ out, uint32_t k) {
+__device__ __forceinline__ void parity_rows(const EncRowGen &P, const uint4 (&x)[D], int onv, uint64_t out_off) {
+    if (P.emit_data) {        // kernel-uniform; x[] is already masked to the output vector in MASKED columns
+#pragma unroll
+        for (int i = 0; i < D; ++i)
+            if (CODE != kCodeGeneric || static_cast<uint32_t>(i) < P.d) dev::stg128_cs(P.plane[i] + out_off, x[i]);
+    }
     if constexpr (CODE != kCodeGeneric) {
         static_assert(D == static_code_d(CODE), "static code width");
 #pragma unroll
@@ -107,7 +116,7 @@ __device__ __forceinline__ void parity_rows(const EncRowGen &P, const uint4 (&x)
                     }
             }
             if (MASKED) acc = keep_bytes(acc, onv);
-            dev::stg128_cs(out + static_cast<uint64_t>(j) * P.plane_stride + k, acc);
+            dev::stg128_cs(P.plane[D + j] + out_off, acc);
         }
     } else {
         for (uint32_t j = 0; j < P.p; ++j) {
@@ -131,17 +140,16 @@ __device__ __forceinline__ void parity_rows(const EncRowGen &P, const uint4 (&x)
                 }
             }
             if (MASKED) acc = keep_bytes(acc, onv);
-            dev::stg128_cs(out + static_cast<uint64_t>(j) * P.plane_stride + k, acc);
+            dev::stg128_cs(P.plane[P.d + j] + out_off, acc);
         }
     }
 }
 
 template <int D, int CODE, bool MASKED>
-__device__ __forceinline__ void horner_row_column(const EncRowGen &P, const uint8_t *__restrict__ src, uint8_t *__restrict__ out,
-                                                  uint32_t k) {
+__device__ __forceinline__ void horner_row_column(const EncRowGen &P, const uint8_t *__restrict__ src, uint64_t out_off, uint32_t k) {
     uint4 x[D];
     const int onv = row_load_column<D, MASKED, CODE != kCodeGeneric>(P, src, k, x);
-    parity_rows<D, CODE, MASKED>(P, x, onv, out, k);
+    parity_rows<D, CODE, MASKED>(P, x, onv, out_off + k);
 }
 
 // Split load for the software-pipelined packed kernel (complete columns only): issue the aligned 128-bit loads of one
@@ -190,6 +198,7 @@ __device__ __forceinline__ void raw_finish(const EncRowGen &P, const RawColumn<D
 template <int D, int CODE, int MAXT, int MINB>
 __global__ void __launch_bounds__(MAXT, MINB) horner_encode_row_kernel(const __grid_constant__ EncRowGen P) {
     const uint32_t lane = threadIdx.x & 31u, wid = threadIdx.x >> 5, nblk = blockDim.x >> 5;
+    if (P.emit_data) dev::cta_wait_flags(P.wait);       // kernel-uniform; the ack planes tallied below come from peer GPUs
     if (P.planes != nullptr) {
         const uint32_t per = (P.n + gridDim.x - 1) / gridDim.x;
         const uint32_t lo = blockIdx.x * per;
@@ -203,14 +212,17 @@ __global__ void __launch_bounds__(MAXT, MINB) horner_encode_row_kernel(const __g
     uint32_t wb = wid;
 #pragma unroll 1
     for (uint32_t g = blockIdx.x; g < P.n; g += gridDim.x) {
-        const uint32_t v = wb * 32u + lane;
-        const bool masked = wb * 32u + 32u > P.fast_cols;           // warp-uniform
-        wb = (wb + 1u == nblk) ? 0u : wb + 1u;                       // rotate the warp -> block assignment
-        if (v >= P.vpc) continue;
         const uint8_t *src = P.data + static_cast<uint64_t>(g) * P.data_stride;
-        uint8_t *out = P.parity + static_cast<uint64_t>(g) * P.shard_stride;
-        if (!masked) horner_row_column<D, CODE, false>(P, src, out, v * 16u);
-        else horner_row_column<D, CODE, true>(P, src, out, v * 16u);
+        const uint64_t out_off = static_cast<uint64_t>(g) * P.shard_stride;
+        // codewords wider than the CTA are walked in segments of blockDim.x columns (one pass for the usual sizes)
+        for (uint32_t vb = 0; vb < P.vpc; vb += blockDim.x) {
+            const uint32_t v = vb + wb * 32u + lane;
+            const bool masked = vb + wb * 32u + 32u > P.fast_cols;       // warp-uniform
+            if (v >= P.vpc) continue;
+            if (!masked) horner_row_column<D, CODE, false>(P, src, out_off, v * 16u);
+            else horner_row_column<D, CODE, true>(P, src, out_off, v * 16u);
+        }
+        wb = (wb + 1u == nblk) ? 0u : wb + 1u;                       // rotate the warp -> block assignment
     }
 }
 
@@ -231,6 +243,7 @@ SSB_HD constexpr int packed_min_blocks() {
 
 template <int D, int CODE, bool ALIGNED, bool PIPE>
 __global__ void __launch_bounds__(256, packed_min_blocks<D, ALIGNED, PIPE>()) horner_encode_packed_kernel(const __grid_constant__ EncRowGen P) {
+    if (P.emit_data) dev::cta_wait_flags(P.wait);
     if (P.planes != nullptr) {
         const uint32_t per = (P.n + gridDim.x - 1) / gridDim.x;
         const uint32_t lo = blockIdx.x * per;
@@ -246,7 +259,7 @@ __global__ void __launch_bounds__(256, packed_min_blocks<D, ALIGNED, PIPE>()) ho
         const uint64_t g = P.ntail == 1u ? item : item / P.ntail;
         if (g >= P.n) return;
         const uint32_t col = P.fast_cols + static_cast<uint32_t>(item - g * P.ntail);
-        horner_row_column<D, CODE, true>(P, P.data + g * P.data_stride, P.parity + g * P.shard_stride, col * 16u);
+        horner_row_column<D, CODE, true>(P, P.data + g * P.data_stride, g * P.shard_stride, col * 16u);
         return;
     }
     const uint32_t cg = threadIdx.x / P.fast_cols;               // fast_cols >= 1 whenever main CTAs exist
@@ -258,7 +271,7 @@ __global__ void __launch_bounds__(256, packed_min_blocks<D, ALIGNED, PIPE>()) ho
     if constexpr (!PIPE) {
 #pragma unroll 1
         for (; g < P.n; g += step)
-            horner_row_column<D, CODE, false>(P, P.data + g * P.data_stride, P.parity + g * P.shard_stride, k);
+            horner_row_column<D, CODE, false>(P, P.data + g * P.data_stride, g * P.shard_stride, k);
         return;
     }
     // software pipeline: the loads of this thread's next column are in flight while the current one is computed
@@ -270,7 +283,7 @@ __global__ void __launch_bounds__(256, packed_min_blocks<D, ALIGNED, PIPE>()) ho
         raw_finish<D, ALIGNED, CODE != kCodeGeneric>(P, raw, x);
         const uint64_t gn = g + step;
         if (gn < P.n) raw_issue<D, ALIGNED, CODE != kCodeGeneric>(P, P.data + gn * P.data_stride, k, raw);
-        parity_rows<D, CODE, false>(P, x, 16, P.parity + g * P.shard_stride, k);
+        parity_rows<D, CODE, false>(P, x, 16, g * P.shard_stride + k);
         if (gn >= P.n) break;
         g = gn;
     }

@@ -287,7 +287,7 @@ __device__ __forceinline__ void rs32_row_pair(const uint8_t *__restrict__ src, u
     }
 }
 
-template <bool EMIT, int MAXT, int MINB>
+template <bool EMIT, int MAXT, int MINB, bool SEG = false>
 __global__ void __launch_bounds__(MAXT, MINB) rs32_encode_row_kernel(const __grid_constant__ Enc32Row P) {
     const uint32_t lane = threadIdx.x & 31u, wid = threadIdx.x >> 5, nblk = blockDim.x >> 5;
     const uint32_t s1 = P.s1, s2 = P.s2;
@@ -313,6 +313,35 @@ __global__ void __launch_bounds__(MAXT, MINB) rs32_encode_row_kernel(const __gri
     // critical path and the other warps idle at the end (measured: 10 % of the whole kernel).  So the assignment
     // ROTATES: on its i-th codeword warp w takes block (w + i) mod nblk, and every warp does every block type
     // equally often.
+    if constexpr (SEG) {
+        // Codewords wider than the CTA (more than 256 columns: payloads above 12 KB, up to one multi-megabyte codeword):
+        // the work items are (codeword, 256-column segment) pairs, so that a single large codeword still fills the GPU
+        // (benches/rse_bench.rs sizes 16 KB .. 4 MB).
+        const uint32_t nseg = (P.vpc + blockDim.x - 1u) / blockDim.x;
+        const uint64_t items = static_cast<uint64_t>(P.n) * nseg;
+#pragma unroll 1
+        for (uint64_t it = blockIdx.x; it < items; it += gridDim.x) {
+            const uint32_t g = static_cast<uint32_t>(it / nseg), seg = static_cast<uint32_t>(it - static_cast<uint64_t>(g) * nseg);
+            const uint32_t vb = seg * blockDim.x + wid * 32u;
+            const uint32_t v = vb + lane, k = v * 16u;
+            if (v >= P.vpc) continue;
+            const bool masked = vb + 32u > P.fast_cols;                 // warp-uniform
+            const uint32_t o1 = P.L + k - s1, o2 = 2u * P.L + k - s2;
+            const uint64_t so = static_cast<uint64_t>(g) * P.shard_stride;
+            uint8_t *const out[5] = {EMIT ? P.plane[0] + so : nullptr, EMIT ? P.plane[1] + so : nullptr,
+                                     EMIT ? P.plane[2] + so : nullptr, P.plane[3] + so, P.plane[4] + so};
+            const uint8_t *src = P.data + static_cast<uint64_t>(g) * P.data_stride;
+            if (!masked) {
+                rs32_row_column<EMIT, false>(src, out, k, o1, o2, 0u, s1, s2, 16, 16, 16, 16, P.st_mode);
+            } else {
+                rs32_row_column<EMIT, true>(src, out, k, o1, o2, 0u, s1, s2, clamp16(static_cast<int64_t>(P.len) - k),
+                                            clamp16(static_cast<int64_t>(P.len) - P.L - k),
+                                            clamp16(static_cast<int64_t>(P.len) - 2ll * P.L - k),
+                                            clamp16(static_cast<int64_t>(P.L) - k), P.st_mode);
+            }
+        }
+        return;
+    }
     const uint32_t g_begin = P.chunk ? blockIdx.x * P.chunk : blockIdx.x;
     const uint32_t g_step = P.chunk ? 1u : gridDim.x;
     const uint32_t g_end = P.chunk ? (g_begin + P.chunk < P.n ? g_begin + P.chunk : P.n) : P.n;
@@ -1234,27 +1263,40 @@ int launch_rs_encode(ss_rs_coder *coder, const EncGeom &g, const TallyArgs *tall
                              (unsigned long long)g.shard_stride, vpc * 16u);
 
         // ---- RS(3,2) row kernel: aligned uniform geometry, codewords up to 256 columns ----
-        if (use_rs32 && (coder->variant & 15) != 1 && padded && vpc >= 1 && vpc <= 256 && g.n <= 0xffffffffull &&
+        if (use_rs32 && (coder->variant & 15) != 1 && padded && vpc >= 1 && g.n <= 0xffffffffull &&
             ((reinterpret_cast<uintptr_t>(g.data) | g.data_stride) & 15u) == 0u &&
             (tally == nullptr || tally->planes == nullptr || tally->G == g.n)) {
             Enc32Row Rw;
             Rw.data = g.data; Rw.data_stride = g.data_stride; Rw.shard_stride = g.shard_stride;
             for (int j = 0; j < 5; ++j) {
-                if (g.planes5 != nullptr) Rw.plane[j] = g.planes5[j];
+                if (g.plane_ptrs != nullptr) Rw.plane[j] = g.plane_ptrs[j];
                 else Rw.plane[j] = g.parity + (static_cast<int64_t>(j) - 3) * static_cast<int64_t>(g.plane_stride);
             }
             Rw.n = static_cast<uint32_t>(g.n); Rw.len = len; Rw.L = L; Rw.vpc = vpc;
             const uint32_t lim = (len - 2u * L) < L ? (len - 2u * L) : L;     // bytes of shard 2 inside the payload
             Rw.fast_cols = len >= 2u * L ? lim / 16u : 0u;
             Rw.s1 = L & 15u; Rw.s2 = (2u * L) & 15u;
-            Rw.emit_data = ((g.flags & SS_RS_EMIT_DATA) || g.planes5 != nullptr) ? 1u : 0u;
+            Rw.emit_data = ((g.flags & SS_RS_EMIT_DATA) || g.plane_ptrs != nullptr) ? 1u : 0u;
             Rw.planes = nullptr; Rw.R = 0; Rw.threshold = 0; Rw.committed = nullptr; Rw.commit_bar = nullptr;
             if (tally != nullptr && tally->planes != nullptr) {
                 Rw.planes = tally->planes; Rw.R = tally->R; Rw.threshold = tally->threshold;
                 Rw.committed = tally->committed; Rw.commit_bar = tally->commit_bar;
             }
             Rw.wait = g.wait;
-            const uint32_t threads = (vpc + 31u) & ~31u;
+            const uint32_t threads = vpc > 256u ? 256u : ((vpc + 31u) & ~31u);
+            if (vpc > 256u) {
+                // wide codewords: (codeword, 256-column segment) work items
+                const uint64_t items = g.n * ((vpc + 255u) / 256u);
+                uint64_t ctas = static_cast<uint64_t>(ctx->sm_count) * 8ull * 16ull;
+                if (ctas > items) ctas = items;
+                Rw.chunk = 0; Rw.st_mode = static_cast<uint32_t>((coder->variant >> 8) & 3); Rw.rotate = 0;
+                if (Rw.emit_data) rs32_encode_row_kernel<true, 256, 4, true><<<static_cast<uint32_t>(ctas), 256, 0, st>>>(Rw);
+                else rs32_encode_row_kernel<false, 256, 4, true><<<static_cast<uint32_t>(ctas), 256, 0, st>>>(Rw);
+                coder->last_kernel = Rw.planes ? "rs32_encode_row_kernel<segmented>+tally" : "rs32_encode_row_kernel<segmented>";
+                SS_CUDA(cudaGetLastError());
+                ctx->launches++;
+                return SS_OK;
+            }
             // resident CTAs per SM (2048 threads, 32 CTAs) x a few waves; every CTA strides over codewords
             uint32_t per_sm = 2048u / threads; if (per_sm > 32u) per_sm = 32u;
             const int vr = coder->variant & 15, vchunk = (coder->variant >> 4) & 1, vw = (coder->variant >> 5) & 7;
@@ -1287,11 +1329,18 @@ int launch_rs_encode(ss_rs_coder *coder, const EncGeom &g, const TallyArgs *tall
 
         // ---- generic row kernel: any code with d <= 8, aligned uniform geometry, codewords up to 256 columns ----
         if (!use_rs32 && d <= 8 && coder->enc_hmT8 != nullptr && (coder->variant & 15) != 5 && (coder->variant & 15) != 1 &&
-            padded && !(g.flags & SS_RS_EMIT_DATA) && vpc >= 1 && vpc <= 256 && g.n <= 0xffffffffull &&
+            padded && vpc >= 1 && g.n <= 0xffffffffull &&
             ((reinterpret_cast<uintptr_t>(g.data) | g.data_stride) & 15u) == 0u &&
             (tally == nullptr || tally->planes == nullptr || tally->G == g.n)) {
             EncRowGen Rg;
-            Rg.data = g.data; Rg.data_stride = g.data_stride; Rg.parity = g.parity; Rg.plane_stride = g.plane_stride;
+            Rg.data = g.data; Rg.data_stride = g.data_stride;
+            for (int j = 0; j < 16; ++j) {
+                if (j >= d + p) Rg.plane[j] = nullptr;
+                else if (g.plane_ptrs != nullptr) Rg.plane[j] = g.plane_ptrs[j];
+                else Rg.plane[j] = g.parity + (static_cast<int64_t>(j) - d) * static_cast<int64_t>(g.plane_stride);
+            }
+            Rg.emit_data = ((g.flags & SS_RS_EMIT_DATA) || g.plane_ptrs != nullptr) ? 1u : 0u;
+            Rg.wait = g.wait;
             Rg.shard_stride = g.shard_stride; Rg.n = static_cast<uint32_t>(g.n); Rg.len = len; Rg.L = L; Rg.vpc = vpc;
             // columns whose every source window lies inside the payload and whose output vector is complete
             const uint64_t last_shard_bytes = static_cast<uint64_t>(len) >= static_cast<uint64_t>(d - 1) * L
@@ -1317,8 +1366,8 @@ int launch_rs_encode(ss_rs_coder *coder, const EncGeom &g, const TallyArgs *tall
             // Packed flavour when the one-codeword-per-pass layout would idle or mask a good part of the lanes
             // (bit 13 forces it off, bit 14 forces it on).
             const uint32_t fc = Rg.fast_cols;
-            const uint32_t row_threads = (vpc + 31u) & ~31u;
-            bool packed = fc != vpc || row_threads != vpc;
+            const uint32_t row_threads = vpc > 256u ? 256u : ((vpc + 31u) & ~31u);    // wider codewords: 256-column segments
+            bool packed = (fc != vpc || row_threads != vpc) && vpc <= 256u;
             if ((coder->variant >> 13) & 1) packed = false;
             if ((coder->variant >> 14) & 1) packed = true;
             // software-pipelined main loop: always when every shard is 16-byte aligned; bit 15 selects it for unaligned too

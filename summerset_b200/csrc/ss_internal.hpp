@@ -140,7 +140,7 @@ struct EncGeom {
     uint64_t shard_stride;      // uniform
     uint64_t n;
     uint32_t flags;
-    uint8_t *const *planes5 = nullptr;   // RS(3,2) replicate mode: 5 explicit plane bases (local or peer memory)
+    uint8_t *const *plane_ptrs = nullptr;   // replicate mode: d+p explicit plane bases (local or peer memory)
     dev::FlagWait wait = {nullptr, 0, 0, 0, nullptr};   // replicate mode: flags to wait for before the tally
 };
 

@@ -34,19 +34,25 @@ def _want_planes(oracle, data, data_len, d, p):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("data_len", [1, 17, 4096, 12288])
+@pytest.mark.parametrize("d,p", [(3, 2), (4, 3), (2, 1), (6, 4)])
+@pytest.mark.parametrize("data_len", [1, 17, 4096, 12288, 30000])
 @pytest.mark.parametrize("with_tally", [False, True])
-def test_replicate_five_local_buffers(ctx, oracle, data_len, with_tally):
+def test_replicate_separate_local_buffers(ctx, oracle, d, p, data_len, with_tally):
+    """d+p distinct buffers as the replicas' logs: every plane of every group, guard bands, padding, fused tally.  RS(3,2)
+    takes its hand-specialised row kernel (segmented for payloads above 12 KB); the other codes the generalised row /
+    packed kernels (compile-time cluster codes, or specialised by NVRTC), which also walk codewords wider than one CTA."""
+    from summerset_b200._lib import SummersetError
     from summerset_b200.api import ReedSolomon, round_up, shard_len
-    rs = ReedSolomon(ctx, 3, 2)
+    rs = ReedSolomon(ctx, d, p)
     n = 1531
+    T = d + p
     stride = round_up(max(data_len, 16), 16)
     data = wl.payload_uniform(n, stride, seed_extra=data_len)
-    L = shard_len(data_len, 3); ds = round_up(L, 16)
-    # five separate allocations, each with a guard band that must stay untouched
-    bufs = [torch.full((n * ds + 64,), 0xC3, dtype=torch.uint8, device=DEV) for _ in range(5)]
+    L = shard_len(data_len, d); ds = round_up(L, 16)
+    # separate allocations, each with a guard band that must stay untouched
+    bufs = [torch.full((n * ds + 64,), 0xC3, dtype=torch.uint8, device=DEV) for _ in range(T)]
     ptrs = [b.data_ptr() + 32 for b in bufs]
-    assert all(p % 16 == 0 for p in ptrs)
+    assert all(q % 16 == 0 for q in ptrs)
     planes = wl.cfg2_planes(n, 5, 0.9, seed_extra=3)
     pl = torch.from_numpy(planes.view(np.int64)).to(DEV)
     committed = torch.zeros(n, dtype=torch.int64, device=DEV)
@@ -54,9 +60,9 @@ def test_replicate_five_local_buffers(ctx, oracle, data_len, with_tally):
     rs.accept_step_replicate(torch.from_numpy(data).to(DEV), data_len, ptrs, ds, pl if with_tally else None, 4,
                              committed if with_tally else None, bar if with_tally else None)
     torch.cuda.synchronize()
-    assert rs.last_kernel().startswith("rs32_encode_row_kernel")
-    want = _want_planes(oracle, data, data_len, 3, 2)
-    for j in range(5):
+    assert rs.last_kernel().startswith("rs32_encode_row_kernel" if (d, p) == (3, 2) else "horner_encode_")
+    want = _want_planes(oracle, data, data_len, d, p)
+    for j in range(T):
         got = bufs[j].cpu().numpy()
         assert (got[:32] == 0xC3).all() and (got[32 + n * ds:] == 0xC3).all(), f"plane {j}: guard band written"
         body = got[32:32 + n * ds].reshape(n, ds)

@@ -193,7 +193,8 @@ def test_row_kernel_emit_data_and_wide_codewords(ctx, oracle):
     """SS_RS_EMIT_DATA (all d+p planes in one pass) on the row kernel and the general kernels; codewords wider
     than the row kernel's 256-column limit fall back to the flat kernel"""
     from summerset_b200._lib import check
-    for d, p, data_len, n in [(3, 2, 4096, 1000), (3, 2, 20000, 64), (3, 2, 5, 40), (4, 3, 1000, 100)]:
+    for d, p, data_len, n in [(3, 2, 4096, 1000), (3, 2, 20000, 64), (3, 2, 5, 40), (4, 3, 1000, 100), (4, 3, 4096, 300),
+                              (4, 3, 40000, 37), (5, 4, 30001, 21), (6, 4, 4096, 100), (6, 4, 50000, 9), (2, 1, 9000, 50)]:
         rs = ReedSolomon(ctx, d, p)
         data = wl.payload_uniform(n, data_len, seed_extra=3)
         L, ds, ps = rs.parity_layout(data_len, n)
@@ -445,22 +446,26 @@ def test_generic_row_kernel_fused_step(ctx, oracle, d, p, data_len, n):
     torch.cuda.synchronize()
     assert ctx.launches == before + 1
     static = (d, p) in [(2, 1), (4, 3), (5, 4), (4, 2), (3, 1)]      # population 3/7/9/6/4 cluster codes
-    tag = "<static code>" if static else ""
+    tag = "<static code>" if static else "<nvrtc>"                  # any other code: specialised at run time (jit.cu)
+    if not static:
+        status = ctx.lib.ss_rs_jit_status(rs.h).decode()
+        assert status.startswith("specialised by NVRTC"), status
     vpc = -(-L // 16)
     last = max(0, data_len - (d - 1) * L)
     packed = (min(L, last) // 16 != vpc) or vpc % 32 != 0          # some lanes would idle or be masked: packed layout
     assert rs.last_kernel() == ("horner_encode_packed_kernel" if packed else "horner_encode_row_kernel") + tag + "+tally"
     want = oracle.rs_encode_uniform(d, p, data, data_len)
     assert (par.cpu().numpy() == want).all()
-    # run-time masks; forced one-codeword-per-pass layout; forced packed layout; pipelined packed loop
-    for v in (1 << 11, 1 << 13, 1 << 14, (1 << 14) | (1 << 11), (1 << 14) | (1 << 15), (1 << 13) | (1 << 11)):
+    # run-time masks; forced one-codeword-per-pass layout; forced packed layout; pipelined packed loop; no NVRTC
+    for v in (1 << 11, 1 << 13, 1 << 14, (1 << 14) | (1 << 11), (1 << 14) | (1 << 15), (1 << 13) | (1 << 11), 1 << 17, (1 << 17) | (1 << 14)):
         rs.set_variant(v)
         par3 = rs.encode_uniform(torch.from_numpy(data).to(DEV), data_len)
         torch.cuda.synchronize()
         is_packed = (packed or (v >> 14) & 1) and not (v >> 13) & 1
         is_static = static and not (v >> 11) & 1
+        is_jit = not static and not (v >> 11) & 1 and not (v >> 17) & 1
         assert rs.last_kernel() == ("horner_encode_packed_kernel" if is_packed else "horner_encode_row_kernel") + \
-            ("<static code>" if is_static else ""), (v, rs.last_kernel())
+            ("<static code>" if is_static else "<nvrtc>" if is_jit else ""), (v, rs.last_kernel())
         assert (par3.cpu().numpy() == want).all(), v
     c_want, b_want = oracle.tally_planes(planes, thr)
     assert (committed.cpu().numpy().view(np.uint64) == c_want).all()

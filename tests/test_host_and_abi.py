@@ -165,3 +165,15 @@ def test_crossword_brr_assignment_matches_oracle(oracle):
     for n, T in [(5, 5), (3, 3), (7, 7), (5, 10), (9, 9), (4, 8)]:
         for spr in range(1, T + 1):
             assert [int(x) for x in oracle.cw_brr_assignment(n, T, spr)] == crossword_brr_assignment(n, T, spr)
+
+
+def test_nvrtc_specialisation_compiles_without_a_gpu():
+    """jit.cu: the row / packed encode kernels compile under NVRTC for a code that has no compile-time table (Crossword's
+    RS(6,4)), offline -- the same source, options and name expressions a coder uses on the GPU box."""
+    import ctypes as C
+    from summerset_b200 import _lib
+    lib = _lib.load()
+    log = C.create_string_buffer(16384)
+    n = lib.ss_jit_selftest(6, 4, log, 16384)
+    assert n > 50000, (n, log.value.decode())
+    assert lib.ss_jit_selftest(9, 3, log, 16384) < 0 and b"d <= 8" in log.value      # outside the specialised range
