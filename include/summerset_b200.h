@@ -343,15 +343,16 @@ int ss_accept_step_fused(ss_rs_coder *coder, const uint8_t *data, uint64_t data_
 int ss_follower_ack_dev(ss_ctx *ctx, const uint64_t *ack_src, uint64_t *const *ack_dst, uint32_t n_replicas,
                         uint64_t n_groups, const ss_step_sync *sync);
 
-/* Crossword encode + distribute (BASELINE config 4; crossword/request.rs:82-87,137-185): RS(3,2)-encodes a
- * ragged batch and writes, for every codeword g, the spr[g] shards the balanced round-robin assignment gives
- * replica r -- shards {(r + k) mod 5 : k < spr[g]} (crossword/mod.rs:866-888 with n = T = 5) -- into
- * replica_logs[r] at rep_off[g] + k*round_up(L_g,16), k = 0..spr-1 (bytes past L_g zero).  replica_logs is a
- * HOST array of 5 device pointers, local or peer (ss_ipc_open): the kernel's stores are the shard transfer.
- * Per codeword (n-1)*spr*L_g bytes cross to other replicas, as in the reference.  n = 5 / RS(3,2) only. */
+/* Crossword encode + distribute (BASELINE config 4; crossword/request.rs:82-87,137-185): RS-encodes a ragged batch with
+ * the coder's (d, T-d) code and writes, for every codeword g, the spr[g] shards the balanced round-robin assignment gives
+ * replica r -- shards {(r*dj + k) mod T : k < spr[g]}, dj = T / n_replicas (crossword/mod.rs:866-888) -- into
+ * replica_logs[r] at rep_off[g] + k*round_up(L_g,16), k = 0..spr-1 (bytes past L_g zero).  replica_logs is a HOST array
+ * of n_replicas device pointers, local or peer (ss_ipc_open): the kernel's stores are the shard transfer.  Per codeword
+ * (n-1)*spr*L_g bytes cross to other replicas, as in the reference.  Any code with d <= 8 and T a multiple of
+ * n_replicas <= 16 (crossword/mod.rs:805-830); n = 5 with RS(3,2) runs the hand-specialised kernel. */
 int ss_crossword_distribute_dev(ss_rs_coder *coder, const uint8_t *data, const uint64_t *data_off,
                                 const uint32_t *data_len, const uint8_t *spr, const uint64_t *rep_off,
-                                uint64_t n, uint8_t *const *replica_logs);
+                                uint64_t n, uint8_t *const *replica_logs, uint32_t n_replicas);
 
 /* Accept-frame packer (the step after the path): for n uniform codewords, builds the byte frames an
  * unmodified Summerset peer reads off its TCP connection -- 8-byte big-endian body length (utils/safetcp.rs:30-88)
@@ -535,6 +536,8 @@ int ss_engine_raft_ingest(ss_engine *engine, const uint32_t *rec_group, const ui
  *   bits 5-7  row kernel waves of CTAs per resident set: {64 (default), 1, 32, 4, 16, 256, 128, 8}
  *   bits 8-9  cache operator of the plane stores in replicate mode: .cs (default), write-back, .cg, .wt
  *   bit 10    row kernel: fixed instead of rotating warp -> column-block assignment
+ *   ss_crossword_distribute_dev, bits 0-3: 1 = one column per pass, 3 = cooperative CTA per long codeword, 4 = the general
+ *             (any code) kernel also for RS(3,2) / n = 5
  *   d <= 8 codes other than RS(3,2) (horner_encode_row_kernel / horner_encode_packed_kernel):
  *   bits 0-3  1 = flat kernel; 2 / 3 / 4 = 48 / 64 / 80-register builds of the row layout (default by width)
  *   bit 11    run-time coefficient masks even when the matrix is one of the compile-time cluster codes

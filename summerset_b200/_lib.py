@@ -82,7 +82,7 @@ SIGNATURES = {
     "ss_ack_ingest_dev": (_i, [_vp, _vp, _vp, _vp, _vp, _u64, _vp, _vp, _vp, _u32, _u64, _vp]),
     "ss_tally_crossword_dev": (_i, [_vp, _vp, _u32, _vp, _u64, _vp, _u32, _u32, _u32, _u32, _u32, _u32, _i, _vp]),
     "ss_raft_commit_scan_dev": (_i, [_vp, _vp, _u32, _u64, _vp, _vp, _vp, _vp, _u32, _u32, _vp, _vp]),
-    "ss_crossword_distribute_dev": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _u64, C.POINTER(_vp)]),
+    "ss_crossword_distribute_dev": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _u64, C.POINTER(_vp), _u32]),
     "ss_frame_accept_batch_dev": (_i, [_vp, _vp, _u64, _u32, _u32, _u32, _u32, _u32, _vp, _vp, _u64, _vp, _u64, _vp, _vp]),
     "ss_gossip_plan_dev": (_i, [_vp, _u32, _u32, _u32, _vp, _vp, _vp, _vp, _u32, _u32, _u64, _vp, _vp]),
     "ss_raft_kth_match_dev": (_i, [_vp, _vp, _u32, _u64, _u32, _vp]),

@@ -507,11 +507,12 @@ class ReedSolomon:
 
     def crossword_distribute(self, data: torch.Tensor, data_off: torch.Tensor, data_len: torch.Tensor, spr: torch.Tensor,
                              rep_off: torch.Tensor, replica_logs: Sequence[int]) -> None:
-        """Crossword (n = 5): encode the ragged batch and write replica r's spr[g] shards into replica_logs[r]."""
+        """Crossword: encode the ragged batch and write replica r's spr[g] shards {(r*dj + k) mod T} into replica_logs[r]
+        (len(replica_logs) = population; T = d + p must be a multiple of it)."""
         assert data_off.dtype == torch.int64 and data_len.dtype == torch.int32 and spr.dtype == torch.uint8 and rep_off.dtype == torch.int64
-        arr = (C.c_void_p * 5)(*replica_logs)
+        arr = (C.c_void_p * len(replica_logs))(*replica_logs)
         check(self.lib.ss_crossword_distribute_dev(self.h, _ptr(data), _ptr(data_off), _ptr(data_len), _ptr(spr),
-                                                   _ptr(rep_off), data_len.numel(), arr))
+                                                   _ptr(rep_off), data_len.numel(), arr, len(replica_logs)))
 
     def accept_step_fused_host(self, data: np.ndarray, data_len: int, parity: np.ndarray, planes: np.ndarray,
                                threshold: int, committed: np.ndarray, commit_bar: Optional[np.ndarray]) -> None:

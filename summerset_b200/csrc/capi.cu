@@ -917,11 +917,12 @@ int ss_raft_commit_scan_dev(ss_ctx *ctx, const uint32_t *match, uint32_t n_peers
 }
 
 int ss_crossword_distribute_dev(ss_rs_coder *c, const uint8_t *data, const uint64_t *data_off, const uint32_t *data_len,
-                                const uint8_t *spr, const uint64_t *rep_off, uint64_t n, uint8_t *const *replica_logs) {
+                                const uint8_t *spr, const uint64_t *rep_off, uint64_t n, uint8_t *const *replica_logs,
+                                uint32_t n_replicas) {
     if (c == nullptr) return set_error(SS_ERR_INVALID_ARG, "null coder");
     if (n == 0) return SS_OK;
     if (!data || !data_off || !data_len || !spr || !rep_off || !replica_logs) return set_error(SS_ERR_INVALID_ARG, "null buffer");
-    return launch_crossword_distribute(c, data, data_off, data_len, spr, rep_off, n, replica_logs);
+    return launch_crossword_distribute(c, data, data_off, data_len, spr, rep_off, n, replica_logs, n_replicas);
 }
 
 int ss_frame_accept_batch_dev(ss_ctx *ctx, const uint8_t *shard_plane, uint64_t shard_stride, uint32_t shard_idx, uint32_t d,

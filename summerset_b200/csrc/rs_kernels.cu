@@ -1197,20 +1197,113 @@ __global__ void __launch_bounds__(kThreads, 5) rs32_crossword_distribute_coop_ke
     }
 }
 
+// General Crossword distribute: any code with d <= 8, p <= 8 and any population n with T = d + p a multiple of n
+// (crossword/mod.rs:805-830).  Replica r holds shards {(r*dj + k) mod T : k < spr}, dj = T / n (balanced round-robin,
+// crossword/mod.rs:866-888).  A warp per codeword; every column's T shards live in registers (d source vectors, p Horner
+// rows with the coder's run-time masks) and each is stored into the slot of every replica that holds it.
+struct CwDistributeGen {
+    const uint8_t *data;
+    const uint64_t *data_off;
+    const uint32_t *data_len;
+    const uint8_t *spr;
+    const uint64_t *rep_off;
+    uint8_t *rep[16];
+    uint64_t n;
+    uint32_t d, p, n_rep, dj;
+    const uint32_t *prog;      // encode program: ProgHeader + splats + Horner masks
+};
+
+template <int D>
+__global__ void __launch_bounds__(kThreads, 2) crossword_distribute_generic_kernel(const __grid_constant__ CwDistributeGen P) {
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint64_t warp = (static_cast<uint64_t>(blockIdx.x) * kThreads + threadIdx.x) >> 5;
+    const uint64_t nwarps = (static_cast<uint64_t>(gridDim.x) * kThreads) >> 5;
+    const int d = static_cast<int>(P.d), p = static_cast<int>(P.p);
+    const uint32_t T = P.d + P.p;
+    const ProgHeader *hdr = reinterpret_cast<const ProgHeader *>(P.prog);
+    const uint32_t *hmask = P.prog + sizeof(ProgHeader) / 4 + p * d * 8;
+    for (uint64_t g = warp; g < P.n; g += nwarps) {
+        const uint32_t len = __ldg(P.data_len + g);
+        if (len == 0u) continue;
+        const uint32_t spr = __ldg(P.spr + g);
+        const uint32_t L = (len + P.d - 1u) / P.d, vpc = (L + 15u) >> 4, Lpad = vpc * 16u;
+        const uint8_t *src = P.data + __ldg(P.data_off + g);
+        const uint64_t ro = __ldg(P.rep_off + g);
+        for (uint32_t v = lane; v < vpc; v += 32u) {
+            const uint32_t k = v * 16u;
+            const int onv = static_cast<int>(L - k) > 16 ? 16 : static_cast<int>(L - k);
+            uint4 x[D], par[kMaxP];
+            dev::Raw16 raw[D];
+#pragma unroll
+            for (int i = 0; i < D; ++i) {
+                raw[i].lo = make_uint4(0u, 0u, 0u, 0u); raw[i].hi = raw[i].lo; raw[i].s = 0u;
+                if (i < d) {
+                    const int64_t rem = static_cast<int64_t>(len) - (static_cast<int64_t>(i) * L + k);
+                    const int nv = rem > onv ? onv : (rem < 0 ? 0 : static_cast<int>(rem));
+                    raw[i] = dev::raw16_issue(src + static_cast<uint64_t>(i) * L + k, nv);
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < D; ++i) {
+                const int64_t rem = static_cast<int64_t>(len) - (static_cast<int64_t>(i) * L + k);
+                const int nv = rem > onv ? onv : (rem < 0 ? 0 : static_cast<int>(rem));
+                x[i] = i < d ? dev::raw16_finish(raw[i], nv) : make_uint4(0u, 0u, 0u, 0u);
+            }
+#pragma unroll
+            for (int j = 0; j < kMaxP; ++j)
+                par[j] = j < p ? keep_bytes(horner_row<D>(x, d, hmask + j * d * 8, hdr->top[j]), onv) : make_uint4(0u, 0u, 0u, 0u);
+            // shard js goes to replica r's slot kk when (js - r*dj) mod T = kk < spr
+            auto place = [&](uint32_t js, const uint4 &val) {
+                for (uint32_t r = 0; r < P.n_rep; ++r) {
+                    const uint32_t kk = (js + T - (r * P.dj) % T) % T;
+                    if (kk < spr) dev::stg128_cs(P.rep[r] + ro + static_cast<uint64_t>(kk) * Lpad + k, val);
+                }
+            };
+#pragma unroll
+            for (int i = 0; i < D; ++i)
+                if (i < d) place(static_cast<uint32_t>(i), x[i]);
+#pragma unroll
+            for (int j = 0; j < kMaxP; ++j)
+                if (j < p) place(P.d + static_cast<uint32_t>(j), par[j]);
+        }
+    }
+}
+
 int launch_crossword_distribute(ss_rs_coder *coder, const uint8_t *data, const uint64_t *data_off,
                                 const uint32_t *data_len, const uint8_t *spr, const uint64_t *rep_off, uint64_t n,
-                                uint8_t *const *replica_logs) {
+                                uint8_t *const *replica_logs, uint32_t n_replicas) {
     ss_ctx *ctx = coder->ctx;
     SS_TRY(ctx_bind(ctx));
-    if (!coder->is_rs32) return set_error(SS_ERR_UNSUPPORTED, "crossword distribute is implemented for n = 5, RS(3,2)");
+    const uint32_t T = static_cast<uint32_t>(coder->d + coder->p);
+    // crossword/mod.rs:805-830: rs_total_shards must be a multiple of the population
+    if (n_replicas == 0 || n_replicas > 16 || T % n_replicas != 0)
+        return set_error(SS_ERR_INVALID_ARG, "total shards (%u) must be a multiple of the population (%u <= 16)", T, n_replicas);
     if (n == 0) return SS_OK;
+    for (uint32_t r = 0; r < n_replicas; ++r)
+        if (replica_logs[r] == nullptr || (reinterpret_cast<uintptr_t>(replica_logs[r]) & 15u))
+            return set_error(SS_ERR_INVALID_ARG, "replica log %u is null or not 16-byte aligned", r);
+    if (!(coder->is_rs32 && n_replicas == 5) || (coder->variant & 15) == 4) {
+        // any other (T, d, n): the general kernel (variant 4 forces it for RS(3,2) / n = 5 as well)
+        if (coder->d > 8 || !coder->batch_ok)
+            return set_error(SS_ERR_UNSUPPORTED, "crossword distribute needs d <= 8 data shards (coder is %d,%d)", coder->d, coder->p);
+        CwDistributeGen Gp;
+        Gp.data = data; Gp.data_off = data_off; Gp.data_len = data_len; Gp.spr = spr; Gp.rep_off = rep_off; Gp.n = n;
+        Gp.d = static_cast<uint32_t>(coder->d); Gp.p = static_cast<uint32_t>(coder->p); Gp.n_rep = n_replicas; Gp.dj = T / n_replicas;
+        Gp.prog = static_cast<const uint32_t *>(coder->enc_prog);
+        for (uint32_t r = 0; r < 16; ++r) Gp.rep[r] = r < n_replicas ? replica_logs[r] : nullptr;
+        const uint32_t grid = ragged_grid(ctx, n);
+        SS_TRY(dispatch_d(coder->d, [&](auto DC) {
+            crossword_distribute_generic_kernel<decltype(DC)::value><<<grid, kThreads, 0, ctx->stream>>>(Gp);
+            return SS_OK;
+        }));
+        coder->last_kernel = "crossword_distribute_generic_kernel";
+        SS_CUDA(cudaGetLastError());
+        ctx->launches++;
+        return SS_OK;
+    }
     CwDistribute P;
     P.data = data; P.data_off = data_off; P.data_len = data_len; P.spr = spr; P.rep_off = rep_off; P.n = n;
-    for (int r = 0; r < 5; ++r) {
-        if (replica_logs[r] == nullptr || (reinterpret_cast<uintptr_t>(replica_logs[r]) & 15u))
-            return set_error(SS_ERR_INVALID_ARG, "replica log %d is null or not 16-byte aligned", r);
-        P.rep[r] = replica_logs[r];
-    }
+    for (int r = 0; r < 5; ++r) P.rep[r] = replica_logs[r];
     // variant bits 0-3 (tuning; measured in profiles/r02_distribute_variants.txt): 0 = warp per codeword, two columns per
     // pass (default: 13.0 ms on the cfg-4 mix), 1 = one column per pass at 5 CTAs/SM (14.1 ms), 3 = cooperative CTA per long
     // codeword (18.7 ms: more DRAM traffic, lower DRAM efficiency)

@@ -201,7 +201,7 @@ int launch_prepare_merge(ss_ctx *ctx, const uint64_t *vote_bal, const uint32_t *
 
 int launch_crossword_distribute(ss_rs_coder *coder, const uint8_t *data, const uint64_t *data_off,
                                 const uint32_t *data_len, const uint8_t *spr, const uint64_t *rep_off, uint64_t n,
-                                uint8_t *const *replica_logs);
+                                uint8_t *const *replica_logs, uint32_t n_replicas);
 
 int launch_frame_accept(ss_ctx *ctx, const uint8_t *plane, uint64_t shard_stride, uint32_t shard_idx, uint32_t d, uint32_t p,
                         uint32_t data_len, uint32_t msg_variant, const uint64_t *slot, const uint64_t *ballot, uint64_t n,

@@ -235,6 +235,56 @@ def test_crossword_distribute_matches_assignment_and_oracle(ctx, oracle, variant
     assert (got[:, total:] == 0x33).all()                               # nothing written past the logs
 
 
+@pytest.mark.gpu
+@pytest.mark.parametrize("n_rep,T,d,variant", [(5, 5, 3, 4), (5, 10, 6, 0), (7, 7, 4, 0), (3, 3, 2, 0), (3, 6, 4, 0), (4, 8, 5, 0), (9, 9, 5, 0)])
+def test_crossword_distribute_general_codes(ctx, oracle, n_rep, T, d, variant):
+    """ss_crossword_distribute_dev for any (T, d, n) with T % n == 0 (crossword/mod.rs:805-830): replica r's log holds
+    shards {(r*dj + k) mod T : k < spr} (crossword/mod.rs:866-888), bytes equal to the oracle's encode.  variant 4 runs
+    the general kernel on the RS(3,2) / n = 5 case too, so the two kernels are checked against the same oracle."""
+    from summerset_b200.api import ReedSolomon
+    rng = np.random.default_rng(T * 10 + n_rep)
+    p = T - d
+    dj = T // n_rep
+    rs = ReedSolomon(ctx, d, p)
+    rs.set_variant(variant)
+    lens = np.concatenate([rng.integers(1, 3000, 150), [0, 1, 2, 16, 48, 4096, 9001, 20000]]).astype(np.uint32)
+    rng.shuffle(lens)
+    n = len(lens)
+    choices = np.arange(dj, d + 1, dj)                                   # the spr values the assignment policy can pick
+    spr = choices[rng.integers(0, len(choices), n)].astype(np.uint8)
+    lay = wl.ragged_layout(lens, d)
+    arena = rng.integers(0, 256, lay["data_bytes"] + 64, dtype=np.uint8)
+    L = lay["L"].astype(np.int64)
+    Lpad = (L + 15) // 16 * 16
+    slot_bytes = spr.astype(np.int64) * Lpad
+    rep_off = np.concatenate([[0], np.cumsum(slot_bytes)[:-1]]).astype(np.int64)
+    total = int(slot_bytes.sum())
+    logs = torch.full((n_rep, total + 64), 0x33, dtype=torch.uint8, device=DEV)
+    rs.crossword_distribute(torch.from_numpy(arena).to(DEV), torch.from_numpy(lay["data_off"].astype(np.int64)).to(DEV),
+                            torch.from_numpy(lens.astype(np.int32)).to(DEV), torch.from_numpy(spr).to(DEV),
+                            torch.from_numpy(rep_off).to(DEV), [logs[r].data_ptr() for r in range(n_rep)])
+    torch.cuda.synchronize()
+    assert rs.last_kernel() == "crossword_distribute_generic_kernel"
+    got = logs.cpu().numpy()
+    par = np.zeros((p, lay["plane_bytes"]), dtype=np.uint8)
+    oracle.rs_encode_batch(d, p, arena, lay["data_off"], lens, par.reshape(-1), lay["plane_bytes"], lay["par_off"])
+    for g in range(n):
+        if lens[g] == 0:
+            continue
+        Lg = int(L[g]); lp = int(Lpad[g])
+        shards = list(oracle.cw_split(arena[int(lay["data_off"][g]):int(lay["data_off"][g]) + int(lens[g])].tobytes(), d))
+        shards += [par[j, int(lay["par_off"][g]):int(lay["par_off"][g]) + Lg] for j in range(p)]
+        asg = oracle.cw_brr_assignment(n_rep, T, int(spr[g]))
+        for r in range(n_rep):
+            held = [(r * dj + k) % T for k in range(int(spr[g]))]
+            assert sum(1 << j for j in held) == int(asg[r])              # the reference's assignment, bit for bit
+            for k, j in enumerate(held):
+                o = int(rep_off[g]) + k * lp
+                assert (got[r, o:o + Lg] == shards[j]).all(), (g, r, k, j)
+                assert (got[r, o + Lg:o + lp] == 0).all()
+    assert (got[:, total:] == 0x33).all()
+
+
 SPECIAL = [0, 1, 250, 251, 252, 65535, 65536, (1 << 32) - 1, 1 << 32, (1 << 63) + 5]      # every varint boundary
 
 
