@@ -61,7 +61,9 @@ def parse_args():
     ap.add_argument("--groups", type=int, default=G_PER_GPU, help="groups per GPU")
     ap.add_argument("--variant", type=int, default=0, help="encode kernel variant (tuning)")
     ap.add_argument("--replicas", type=int, default=5, help="cfg3 variant: population n (RS(majority, n-majority), f=(n//2)//2)")
-    ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"], help="N>1: how shard planes reach the simulated peers")
+    ap.add_argument("--exchange", default="ce", choices=["ce", "p2p", "nccl"],
+                    help="N>1: how shard planes reach the simulated peers: ce = encode into local staging + copy-engine push overlapped "
+                         "with the next step's encode; p2p = the encode kernel stores into the peers' HBM itself; nccl = all-to-all baseline")
     ap.add_argument("--lag", type=int, default=2, choices=[1, 2], help="N>1: the tally of step k reads the acks of step k-lag")
     ap.add_argument("--timeline", default="", help="N>1: write per-rank per-step CUDA-event timings to this JSON file")
     ap.add_argument("--no-tally", action="store_true", help="tuning: time the encode alone")
@@ -307,8 +309,8 @@ def config_dict(args, world):
     return {"workload": txt,
             "groups_per_gpu": args.groups, "data_len": DATA_LEN, "rs": [D, P], "shard_len": L, "replicas": R,
             "sharding": f"groups x{world} (independent shards)" + ("" if world == 1 else
-                        " + shard planes written to the simulated peers' GPUs over NVLink by the encode kernel; followers' ack planes "
-                        "stored back by a follower kernel; ordering by step flags in device memory (no host sync, NCCL or memcpy per step)"),
+                        f" + shard planes delivered to the simulated peers' GPUs over NVLink (exchange = {args.exchange}); followers' ack planes "
+                        "stored back by a follower kernel; ordering by step flags in device memory (no host sync or NCCL per step)"),
             "l2": "inputs (4 GiB payload + 2.9 GB parity per GPU) exceed the 126 MB L2; no flush needed"}
 
 
@@ -394,14 +396,15 @@ def run_ours(args):
     nccl = None                                      # NCCL all-to-all baseline state
     if world == 1:
         parity = torch.empty((P, n, ds), dtype=torch.uint8, device=dev)
-    elif args.exchange == "p2p":
+    elif args.exchange in ("p2p", "ce"):
         from summerset_b200.replicate import ReplicatedAcceptStep
 
         def exchange_handles(obj):
             out = [None] * world
             dist.all_gather_object(out, obj)
             return out
-        rep = ReplicatedAcceptStep(ctx, rs, n, DATA_LEN, R, world, rank, exchange_handles, lag=args.lag)
+        rep = ReplicatedAcceptStep(ctx, rs, n, DATA_LEN, R, world, rank, exchange_handles, lag=2 if args.exchange == "ce" else args.lag,
+                                   mode=args.exchange)
         rep.fill_acks(planes)
         dist.barrier()
     else:
@@ -453,7 +456,7 @@ def run_ours(args):
         step()
     barrier()
     sampler = ClockSampler(local) if rank == 0 else None
-    launches0 = ctx.launches
+    launches0 = ctx.launches + (rep.comm.launches if rep is not None and rep.mode == "ce" else 0)
     tl = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)] if (args.timeline and world > 1) else None
     t_start = torch.cuda.Event(enable_timing=True); t_end = torch.cuda.Event(enable_timing=True)
     t_start.record()
@@ -461,12 +464,14 @@ def run_ours(args):
         if tl is not None:
             tl[i].record()
         step()
+    if rep is not None:
+        rep.drain()                                  # the copy stream's tail belongs to the timed region
     if tl is not None:
         tl[args.steps].record()
     t_end.record()
     barrier()
     total_ms = t_start.elapsed_time(t_end)
-    launches = ctx.launches - launches0
+    launches = ctx.launches + (rep.comm.launches if rep is not None and rep.mode == "ce" else 0) - launches0
     clocks = sampler.stop() if sampler else None
     status = ctx.device_status()
     assert status == 0, f"device status {status}: a step-flag wait timed out"
@@ -558,12 +563,14 @@ def run_ours(args):
         nv_bytes = remote * n * L
         nv_ms = nv_bytes / (NVLINK_REF_GBS * 1e9) * 1e3
         hbm_ms = (alg + D * L) * n / (peak * 1e9) * 1e3          # replicate mode also writes the data-shard planes
-        roofline["comm"] = {"exchange": "p2p stores by the encode kernel + step flags" if rep is not None else "nccl all-to-all baseline",
+        roofline["comm"] = {"exchange": ("copy-engine push of staged planes overlapped with the next encode + step flags" if args.exchange == "ce"
+                                         else "p2p stores by the encode kernel + step flags") if rep is not None else "nccl all-to-all baseline",
                             "lag": args.lag if rep is not None else None,
                             "remote_planes_per_rank": remote, "nvlink_bytes_per_rank_per_step": nv_bytes,
                             "nvlink_ref_gbs": NVLINK_REF_GBS, "nvlink_bound_ms": nv_ms, "hbm_bound_ms": hbm_ms,
                             "step_ms": ms_per_step, "kernel_ms": kernel_ms,
-                            "nvlink_gbs_in_kernel": nv_bytes / (kernel_ms * 1e-3) / 1e9,
+                            "nvlink_gbs_per_step": nv_bytes / (ms_per_step * 1e-3) / 1e9,
+                            "nvlink_gbs_in_kernel": nv_bytes / (kernel_ms * 1e-3) / 1e9 if args.exchange == "p2p" else None,
                             "frac_of_slower_bound": max(nv_ms, hbm_ms) / ms_per_step,
                             "note": "target time = slower of HBM bytes / measured copy bandwidth and NVLink bytes / 770 GB/s "
                                     "(measured peer-copy reference, B200_PROFILING.md)"}

@@ -309,6 +309,16 @@ typedef struct ss_step_sync {
     uint32_t n_signal;
     uint64_t signal_value;
 } ss_step_sync;
+/* the two halves of an ss_step_sync as stand-alone stream operations (one-warp kernels on the context's stream) */
+int ss_flags_wait_dev(ss_ctx *ctx, const ss_step_sync *sync);
+int ss_flags_signal_dev(ss_ctx *ctx, const ss_step_sync *sync);
+/* Stream-ordering between TWO contexts of one process (e.g. a compute context and a copy context whose
+ * ss_copy_d2d pushes run on the copy engines while the next step computes): an event recorded on one context's stream
+ * can be waited for by another's (cudaEventRecord / cudaStreamWaitEvent). */
+int ss_event_create(ss_ctx *ctx, void **event);
+int ss_event_destroy(ss_ctx *ctx, void *event);
+int ss_event_record(ss_ctx *ctx, void *event);
+int ss_event_wait(ss_ctx *ctx, void *event);
 /* reads (and clears) the context's device status word; synchronises the context's stream */
 #define SS_DEV_STATUS_FLAG_TIMEOUT 1u
 int ss_ctx_device_status(ss_ctx *ctx, uint32_t *status);

@@ -61,6 +61,12 @@ SIGNATURES = {
     "ss_accept_step_replicate_dev": (_i, [_vp, _vp, _u64, _u32, _u64, C.POINTER(_vp), _u64, _vp, _u32, _u32, _vp, _vp, _vp]),
     "ss_follower_ack_dev": (_i, [_vp, _vp, C.POINTER(_vp), _u32, _u64, _vp]),
     "ss_ctx_device_status": (_i, [_vp, C.POINTER(_u32)]),
+    "ss_flags_wait_dev": (_i, [_vp, _vp]),
+    "ss_flags_signal_dev": (_i, [_vp, _vp]),
+    "ss_event_create": (_i, [_vp, C.POINTER(_vp)]),
+    "ss_event_destroy": (_i, [_vp, _vp]),
+    "ss_event_record": (_i, [_vp, _vp]),
+    "ss_event_wait": (_i, [_vp, _vp]),
     "ss_rs_coder_create": (_i, [_vp, _i, _i, C.POINTER(_vp)]),
     "ss_rs_coder_destroy": (_i, [_vp]),
     "ss_rs_data_shard_count": (_i, [_vp]),

@@ -98,6 +98,26 @@ class Context:
     def copy_d2d(self, dst_ptr: int, src_ptr: int, nbytes: int) -> None:
         check(self.lib.ss_copy_d2d(self.h, dst_ptr, src_ptr, nbytes))
 
+    def flags_signal(self, sync: "StepSync") -> None:
+        check(self.lib.ss_flags_signal_dev(self.h, C.byref(sync.c)))
+
+    def flags_wait(self, sync: "StepSync") -> None:
+        check(self.lib.ss_flags_wait_dev(self.h, C.byref(sync.c)))
+
+    def event_create(self) -> int:
+        ev = C.c_void_p()
+        check(self.lib.ss_event_create(self.h, C.byref(ev)))
+        return ev.value
+
+    def event_destroy(self, ev: int) -> None:
+        check(self.lib.ss_event_destroy(self.h, ev))
+
+    def event_record(self, ev: int) -> None:
+        check(self.lib.ss_event_record(self.h, ev))
+
+    def event_wait(self, ev: int) -> None:
+        check(self.lib.ss_event_wait(self.h, ev))
+
     def device_status(self) -> int:
         """Reads and clears the device status word (bit 0: a step-flag wait timed out); synchronises the stream."""
         st = C.c_uint32(0)

@@ -744,6 +744,44 @@ int ss_follower_ack_dev(ss_ctx *ctx, const uint64_t *ack_src, uint64_t *const *a
     return launch_flag_signal(ctx, sync);
 }
 
+int ss_flags_signal_dev(ss_ctx *ctx, const ss_step_sync *sync) {
+    if (ctx == nullptr) return set_error(SS_ERR_INVALID_ARG, "null context");
+    dev::FlagWait w;
+    SS_TRY(make_flag_wait(ctx, sync, &w));        // validates both halves
+    return launch_flag_signal(ctx, sync);
+}
+
+int ss_flags_wait_dev(ss_ctx *ctx, const ss_step_sync *sync) {
+    if (ctx == nullptr) return set_error(SS_ERR_INVALID_ARG, "null context");
+    dev::FlagWait w;
+    SS_TRY(make_flag_wait(ctx, sync, &w));
+    return launch_flag_wait(ctx, w);
+}
+
+int ss_event_create(ss_ctx *ctx, void **event) {
+    SS_TRY(ctx_bind(ctx));
+    if (event == nullptr) return set_error(SS_ERR_INVALID_ARG, "null out pointer");
+    cudaEvent_t ev;
+    SS_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    *event = ev;
+    return SS_OK;
+}
+int ss_event_destroy(ss_ctx *ctx, void *event) {
+    SS_TRY(ctx_bind(ctx));
+    SS_CUDA(cudaEventDestroy(static_cast<cudaEvent_t>(event)));
+    return SS_OK;
+}
+int ss_event_record(ss_ctx *ctx, void *event) {
+    SS_TRY(ctx_bind(ctx));
+    SS_CUDA(cudaEventRecord(static_cast<cudaEvent_t>(event), ctx->stream));
+    return SS_OK;
+}
+int ss_event_wait(ss_ctx *ctx, void *event) {
+    SS_TRY(ctx_bind(ctx));
+    SS_CUDA(cudaStreamWaitEvent(ctx->stream, static_cast<cudaEvent_t>(event), 0));
+    return SS_OK;
+}
+
 int ss_ctx_device_status(ss_ctx *ctx, uint32_t *status) {
     SS_TRY(ctx_bind(ctx));
     if (status == nullptr) return set_error(SS_ERR_INVALID_ARG, "null status pointer");

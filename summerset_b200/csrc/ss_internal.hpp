@@ -191,6 +191,7 @@ void jit_release(ss_rs_coder *coder);
 // multi-GPU step flags
 int make_flag_wait(ss_ctx *ctx, const ss_step_sync *sync, dev::FlagWait *out);
 int launch_flag_signal(ss_ctx *ctx, const ss_step_sync *sync);
+int launch_flag_wait(ss_ctx *ctx, const dev::FlagWait &w);
 int launch_follower_ack(ss_ctx *ctx, const uint64_t *ack_src, uint64_t *const *ack_dst, uint32_t R, uint64_t G,
                         const dev::FlagWait &wait);
 

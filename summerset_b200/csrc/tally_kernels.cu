@@ -516,6 +516,9 @@ __global__ void flag_signal_kernel(const __grid_constant__ SignalArgs A) {
     }
 }
 
+// stand-alone wait: one warp polls the flags; later work on the stream starts when they are all there
+__global__ void flag_wait_kernel(const __grid_constant__ dev::FlagWait W) { dev::cta_wait_flags(W); }
+
 struct AckArgs {
     const uint64_t *src;      // [R][G] local
     uint64_t *dst[16];        // per replica: G words in the leader GPU's memory (local or peer), or nullptr
@@ -551,6 +554,15 @@ int launch_flag_signal(ss_ctx *ctx, const ss_step_sync *sync) {
         if (A.flag[i] == nullptr || (reinterpret_cast<uintptr_t>(A.flag[i]) & 7u))
             return set_error(SS_ERR_INVALID_ARG, "signal flag %u is null or not 8-byte aligned", i);
     flag_signal_kernel<<<1, 32, 0, ctx->stream>>>(A);
+    SS_CUDA(cudaGetLastError());
+    ctx->launches++;
+    return SS_OK;
+}
+
+int launch_flag_wait(ss_ctx *ctx, const dev::FlagWait &w) {
+    if (w.flags == nullptr) return SS_OK;
+    SS_TRY(ctx_bind(ctx));
+    flag_wait_kernel<<<1, 32, 0, ctx->stream>>>(w);
     SS_CUDA(cudaGetLastError());
     ctx->launches++;
     return SS_OK;

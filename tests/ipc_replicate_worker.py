@@ -34,8 +34,8 @@ def main():
     ctx = Context(local)
     rs = ReedSolomon(ctx, 3, 2)
     n, data_len, R, steps = 4098, 4096, 5, 5
-    for lag in (1, 2):
-        st = ReplicatedAcceptStep(ctx, rs, n, data_len, R, world, rank, exchange, lag=lag)
+    for lag, mode in ((1, "p2p"), (2, "p2p"), (2, "ce")):
+        st = ReplicatedAcceptStep(ctx, rs, n, data_len, R, world, rank, exchange, lag=lag, mode=mode)
         assert st.remote_planes() == (2 if world == 2 else 0)
         empty = np.zeros((R, n), dtype=np.uint64)
         st.fill_acks(torch.from_numpy(empty.view(np.int64)).to(dev))
@@ -49,17 +49,20 @@ def main():
                 pl[r] = wl.cfg2_planes(n, R, 0.8, seed_extra=1000 * st.leader_of[r] + k)[r]
             return pl
         data = None
+        keep = []          # the copy-engine mode reads the ack planes on a second stream: the tensors must outlive the call
         for k in range(1, steps + 1):
             data = wl.payload_uniform(n, data_len, seed_extra=10 * rank + k)
-            st.step(torch.from_numpy(data).to(dev), torch.from_numpy(follower_acks(k).view(np.int64)).to(dev), 4, committed, bar)
+            keep.append((torch.from_numpy(data).to(dev), torch.from_numpy(follower_acks(k).view(np.int64)).to(dev)))
+            st.step(keep[-1][0], keep[-1][1], 4, committed, bar)
             # NO synchronisation between steps: the flags order everything
+        st.drain()
         torch.cuda.synchronize()
         dist.barrier()
         assert ctx.device_status() == 0, "a flag wait timed out"
         # tally of the last step = acks my followers sent at step (steps - lag), seeded by MY rank
         src = wl.cfg2_planes(n, R, 0.8, seed_extra=1000 * rank + (steps - lag))
         cw, bw = oracle.tally_planes(src, 4)
-        assert (committed.cpu().numpy().view(np.uint64) == cw).all(), f"rank {rank} lag {lag}: commit words"
+        assert (committed.cpu().numpy().view(np.uint64) == cw).all(), f"rank {rank} lag {lag} {mode}: commit words"
         assert (bar.cpu().numpy().view(np.uint32) == bw).all()
         # every plane of every group of the last step, wherever it lives
         L = st.L
@@ -70,7 +73,7 @@ def main():
                 want = np.stack([oracle.cw_split(data[g, :data_len].tobytes(), 3)[r] for g in range(n)])
             else:
                 want = want_par[r - 3][:, :L]
-            assert (got[:, :L] == want).all(), f"rank {rank} lag {lag}: plane {r}"
+            assert (got[:, :L] == want).all(), f"rank {rank} lag {lag} {mode}: plane {r}"
             assert (got[:, L:] == 0).all()
         # ss_copy_d2d into peer memory: overwrite the peer's ack buffer 0 plane 0 and read it back
         peer = (rank + 1) % world

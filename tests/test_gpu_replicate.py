@@ -124,23 +124,26 @@ def test_flag_wait_times_out_instead_of_hanging(ctx):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("lag", [1, 2])
-def test_replicated_step_protocol_single_gpu(ctx, oracle, lag):
+@pytest.mark.parametrize("lag,mode", [(1, "p2p"), (2, "p2p"), (2, "ce")])
+def test_replicated_step_protocol_single_gpu(ctx, oracle, lag, mode):
     """The whole E_k / A_k flag protocol with world = 1 (every replica hosted locally): shards of the last step in
     every plane, tally of step k == oracle tally of the acks delivered at step k - lag."""
     from summerset_b200.api import ReedSolomon
     from summerset_b200.replicate import ReplicatedAcceptStep
     n, data_len, R = 2050, 4096, 5
     rs = ReedSolomon(ctx, 3, 2)
-    st = ReplicatedAcceptStep(ctx, rs, n, data_len, R, 1, 0, lambda o: [o], lag=lag)
+    st = ReplicatedAcceptStep(ctx, rs, n, data_len, R, 1, 0, lambda o: [o], lag=lag, mode=mode)
     committed = torch.zeros(n, dtype=torch.int64, device=DEV)
     bar = torch.zeros(n, dtype=torch.int32, device=DEV)
     empty = np.zeros((R, n), dtype=np.uint64)
     st.fill_acks(torch.from_numpy(empty.view(np.int64)).to(DEV))
     datas = [wl.payload_uniform(n, data_len, seed_extra=100 + k) for k in range(4)]
     ackss = [wl.cfg2_planes(n, R, 0.8, seed_extra=200 + k) for k in range(4)]
+    keep = []              # the copy-engine mode reads the ack planes on a second stream: keep the tensors alive
     for k in range(1, 5):
-        st.step(torch.from_numpy(datas[k - 1]).to(DEV), torch.from_numpy(ackss[k - 1].view(np.int64)).to(DEV), 4, committed, bar)
+        keep.append((torch.from_numpy(datas[k - 1]).to(DEV), torch.from_numpy(ackss[k - 1].view(np.int64)).to(DEV)))
+        st.step(keep[-1][0], keep[-1][1], 4, committed, bar)
+        st.drain()
         torch.cuda.synchronize()
         src = ackss[k - lag - 1] if k - lag >= 1 else empty
         cw, bw = oracle.tally_planes(src, 4)
