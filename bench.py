@@ -61,6 +61,8 @@ def parse_args():
     ap.add_argument("--groups", type=int, default=G_PER_GPU, help="groups per GPU")
     ap.add_argument("--variant", type=int, default=0, help="encode kernel variant (tuning)")
     ap.add_argument("--replicas", type=int, default=5, help="cfg3 variant: population n (RS(majority, n-majority), f=(n//2)//2)")
+    ap.add_argument("--rs", default="", help="cfg3 variant: an arbitrary code 'd,p' (n = d+p replicas), e.g. 6,4 -- codes without a "
+                                             "compile-time table are specialised at run time by NVRTC (variant bit 17 turns that off)")
     ap.add_argument("--exchange", default="ce", choices=["ce", "p2p", "nccl"],
                     help="N>1: how shard planes reach the simulated peers: ce = encode into local staging + copy-engine push overlapped "
                          "with the next step's encode; p2p = the encode kernel stores into the peers' HBM itself; nccl = all-to-all baseline")
@@ -304,7 +306,7 @@ WORKLOAD_TEXT = {
 def config_dict(args, world):
     L = (DATA_LEN + D - 1) // D
     txt = WORKLOAD_TEXT[args.workload]
-    if args.workload == "cfg3" and R != 5:
+    if args.workload == "cfg3" and (R != 5 or D != 3):
         txt = f"cfg3 variant: RSPaxos ({D},{R}) fused RS({D},{P}) encode + quorum tally ({THRESH_RSPAXOS} of {R}), 2^20 groups x 4096 B per GPU"
     return {"workload": txt,
             "groups_per_gpu": args.groups, "data_len": DATA_LEN, "rs": [D, P], "shard_len": L, "replicas": R,
@@ -904,6 +906,11 @@ def main():
         P = R - D
         THRESH_MULTIPAXOS = D
         THRESH_RSPAXOS = D + (R // 2) // 2
+    if args.rs:
+        D, P = (int(x) for x in args.rs.split(","))
+        R = D + P
+        THRESH_MULTIPAXOS = R // 2 + 1
+        THRESH_RSPAXOS = min(R, R // 2 + 1 + (R // 2) // 2)
     if args.impl == "reference":
         run_reference(args)
     else:

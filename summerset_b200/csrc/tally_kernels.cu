@@ -301,6 +301,44 @@ raft_scan_kernel(const uint32_t *__restrict__ match, uint32_t n_peers, uint64_t 
             const uint32_t o = upper - lc - 1u;
             if (o < W && __ldg(terms + g * W + (ring ? (upper & (W - 1u)) : o)) == ct) { result = upper; any = false; }
         }
+        // ---- the rest: the last slot in (lc, upper) whose term equals curr_term (raft/messages.rs:261-263,271-274: last one
+        //      wins).  Each lane walks ITS OWN group's window from the top, four terms per 128-bit load (the window rows are
+        //      16-byte aligned when W % 4 == 0): a dozen instructions per step instead of a warp-wide ballot per 32 entries
+        //      and group -- the scan was issue-bound, not bandwidth-bound (profiles/r02_ncu_raft_before.txt).  Windows whose
+        //      size is not a multiple of four, or unaligned term arrays, take the cooperative walk below. ----
+        const bool vec_ok = (W & 3u) == 0u && (reinterpret_cast<uintptr_t>(terms) & 15u) == 0u;
+        if (vec_ok) {
+            if (live && any) {
+                // positions: ring -> absolute slot numbers, else window offsets; candidates are lo_p .. hi_p
+                const uint32_t span = upper - lc;                                  // offsets 0 .. span-1; span-1 was the probe
+                const uint32_t lim = span < W ? span : W;
+                if (lim >= 2u || (lim == 1u && span > W)) {
+                    const uint32_t top_o = (span <= W) ? lim - 2u : lim - 1u;       // highest offset not probed yet
+                    const uint32_t base_p = ring ? lc + 1u : 0u;                    // position of offset 0
+                    const uint32_t *row = terms + g * W;
+                    int64_t p = static_cast<int64_t>(base_p) + top_o;
+                    const int64_t lo_p = base_p;
+                    bool found = false;
+                    while (p >= lo_p && !found) {
+                        const uint32_t pb = static_cast<uint32_t>(p) & ~3u;         // chunk of four positions
+                        const uint32_t idx = ring ? (pb & (W - 1u)) : pb;
+                        const uint4 t4 = __ldg(reinterpret_cast<const uint4 *>(row + idx));
+                        const uint32_t tv[4] = {t4.x, t4.y, t4.z, t4.w};
+#pragma unroll
+                        for (int e = 3; e >= 0; --e) {
+                            const int64_t pe = static_cast<int64_t>(pb) + e;
+                            if (!found && pe <= p && pe >= lo_p && tv[e] == ct) {
+                                result = lc + 1u + static_cast<uint32_t>(pe - lo_p);
+                                found = true;
+                            }
+                        }
+                        p = static_cast<int64_t>(pb) - 1;
+                    }
+                }
+            }
+            if (live) new_commit[g] = result;
+            continue;
+        }
         // ---- cooperative part: for each remaining group of the batch, find the last slot in (lc, upper]
         //      whose term equals curr_term (raft/messages.rs:261-263,271-274: last one wins) ----
         const uint32_t todo = __ballot_sync(0xffffffffu, live && any);

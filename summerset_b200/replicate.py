@@ -38,10 +38,6 @@ from .sharding import replica_rank
 FLAG_SLOTS = 16        # u64 counters per flag array (>= replicas)
 
 
-def _follower_ack(ctx: Context, ack_src: torch.Tensor, ack_dst: Sequence[int], sync: StepSync) -> None:
-    ctx.follower_ack(ack_src, ack_dst, sync)
-
-
 class ReplicatedAcceptStep:
     """Per-rank state of the multi-GPU accept step.
 
@@ -108,7 +104,10 @@ class ReplicatedAcceptStep:
             self.ev_copied = [ctx.event_create() for _ in range(self.nbuf)]
             self.ev_done = ctx.event_create()
             # E_k raises only the flags of the replicas hosted here; the copy stream raises the remote ones behind the copies
-            self.sync_e_local = StepSync(self.flags.ptr + FLAG_SLOTS * 8, R, 0, [self.flags.ptr + r * 8 for r in self.local], 0)
+            self.sync_e_local = StepSync(0, 0, 0, [self.flags.ptr + r * 8 for r in self.local], 0)
+            self.sync_w = StepSync(self.flags.ptr + FLAG_SLOTS * 8, R, 0, [], 0)       # stand-alone wait on my ack flags
+            self.sync_aw = StepSync(self.flags.ptr, R, 0, [], 0)                        # stand-alone wait on my shard flags
+            self.sync_a_sig = StepSync(0, 0, 0, [self.peer_flags[self.leader_of[r]].ptr + (FLAG_SLOTS + r) * 8 for r in range(R)], 0)
             self.sync_c = StepSync(0, 0, 0, [self.peer_flags[self.follower_of[r]].ptr + r * 8 for r in self.remote], 0)
 
     def remote_planes(self) -> int:
@@ -140,7 +139,11 @@ class ReplicatedAcceptStep:
         ctx, comm, R = self.ctx, self.comm, self.R
         if k > self.nbuf:
             ctx.event_wait(self.ev_copied[b])              # staging[b] was last read by the copies of step k - nbuf
-        self.sync_e_local.c.wait_value = max(0, k - self.lag)
+        # The flags E_k waits for are raised by follower kernels, one of which runs on THIS GPU's copy stream: a grid-filling
+        # kernel must not spin on them (its CTAs could occupy every SM slot the producer needs).  So the wait is a one-warp
+        # kernel ahead of E_k on the compute stream, and E_k itself starts without polling.
+        self.sync_w.c.wait_value = max(0, k - self.lag)
+        ctx.flags_wait(self.sync_w)
         self.sync_e_local.c.signal_value = k
         # E_k: tally (acks of step k - lag), encode; local replicas' planes into my log, remote ones into staging[b]
         self.rs.accept_step_replicate(data, self.data_len, self.enc_ptrs[b], self.ds, self.acks_view[(k - self.lag) % self.nbuf],
@@ -154,10 +157,11 @@ class ReplicatedAcceptStep:
         self.sync_c.c.signal_value = k
         comm.flags_signal(self.sync_c)                     # shard flags of the remote followers, behind the copies
         comm.event_record(self.ev_copied[b])
-        # A_k on the copy stream: it waits for the shards that land HERE, and must not hold up E_{k+1}
-        self.sync_a.c.wait_value = k
-        self.sync_a.c.signal_value = k
-        _follower_ack(comm, follower_acks, self.ack_dst[b], self.sync_a)
+        # A_k on the copy stream (it must not hold up E_{k+1}): one-warp wait for the shards that land HERE, then the ack kernel
+        self.sync_aw.c.wait_value = k
+        comm.flags_wait(self.sync_aw)
+        self.sync_a_sig.c.signal_value = k
+        comm.follower_ack(follower_acks, self.ack_dst[b], self.sync_a_sig)
         return k
 
     def drain(self) -> None:
