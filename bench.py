@@ -486,6 +486,7 @@ def run_ours(args):
     kernel_ms = sum(a.elapsed_time(b) for a, b in k_evs) / len(k_evs)
     total_ms, kernel_ms = _max_over_ranks(torch, dist, dev, world, total_ms, kernel_ms)
     ms_per_step = total_ms / args.steps
+    timed_kernel = rs.last_kernel() if args.workload != "cfg2" else "tally_planes_x2_kernel"     # before the checks launch other kernels
     if tl is not None:
         mine = [tl[i].elapsed_time(tl[i + 1]) for i in range(args.steps)]
         allt = [None] * world
@@ -551,7 +552,12 @@ def run_ours(args):
         value = alg_rs * n * world / (ms_per_step * 1e-3) / 1e9
         unit = "GB/s"
     tkey = args.workload if R == 5 else f"{args.workload}_r{R}"
-    roofline = roofline_obj(alg * n, kernel_ms, peak, peak_src, rs.last_kernel() if args.workload != "cfg2" else "tally_planes_x2_kernel", tkey)
+    # N > 1: the step also writes the d data-shard planes (every replica's log is a separate buffer), SURVEY 8d "state which"
+    alg_kernel = alg + (D * L if (world > 1 and args.workload == "cfg3") else 0)
+    roofline = roofline_obj(alg_kernel * n, kernel_ms, peak, peak_src, timed_kernel, tkey)
+    if world > 1 and args.workload == "cfg3":
+        roofline["note"] = ("kernel = the encode + tally launch alone; in exchange mode ce it writes all five planes to local HBM "
+                            "(algorithmic bytes include the three data-shard planes), in mode p2p its stores cross NVLink")
     if world > 1 and args.workload == "cfg3":
         # the same fused kernel WITHOUT the replicate stores (parity to local HBM only): per-GPU compute is flat in N
         lp = torch.empty((P, n, ds), dtype=torch.uint8, device=dev)
@@ -564,7 +570,7 @@ def run_ours(args):
         remote = sum(1 for r in range(R) if sharding.replica_rank(rank, r, world) != rank)
         nv_bytes = remote * n * L
         nv_ms = nv_bytes / (NVLINK_REF_GBS * 1e9) * 1e3
-        hbm_ms = (alg + D * L) * n / (peak * 1e9) * 1e3          # replicate mode also writes the data-shard planes
+        hbm_ms = alg_kernel * n / (peak * 1e9) * 1e3
         roofline["comm"] = {"exchange": ("copy-engine push of staged planes overlapped with the next encode + step flags" if args.exchange == "ce"
                                          else "p2p stores by the encode kernel + step flags") if rep is not None else "nccl all-to-all baseline",
                             "lag": args.lag if rep is not None else None,
