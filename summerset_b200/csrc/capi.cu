@@ -60,6 +60,23 @@ int ctx_scratch(ss_ctx *ctx, size_t bytes, void **out) {
     return SS_OK;
 }
 
+// grow-only pinned host staging for the single-codeword calls: the caller's shard slices are pageable memory, and one
+// pinned H2D + one pinned D2H cost far less than d + p pageable copies (each of which the driver stages anyway)
+static int ctx_pinned(ss_ctx *ctx, size_t bytes, uint8_t **out) {
+    if (bytes > ctx->pinned_bytes) {
+        SS_CUDA(cudaStreamSynchronize(ctx->stream));
+        if (ctx->pinned) SS_CUDA(cudaFreeHost(ctx->pinned));
+        ctx->pinned = nullptr;
+        ctx->pinned_bytes = 0;
+        size_t want = bytes < (1u << 20) ? (1u << 20) : bytes;
+        SS_CUDA(cudaHostAlloc(&ctx->pinned, want, cudaHostAllocDefault));
+        ctx->pinned_bytes = want;
+    }
+    *out = static_cast<uint8_t *>(ctx->pinned);
+    return SS_OK;
+}
+constexpr size_t kStagedCallLimit = size_t(8) << 20;    // larger codewords copy straight from the caller's slices
+
 static int pipeline_init(ss_ctx *ctx) {
     if (ctx->pipeline_ready) return SS_OK;
     SS_CUDA(cudaStreamCreateWithFlags(&ctx->h2d_stream, cudaStreamNonBlocking));
@@ -232,6 +249,7 @@ static void ctx_teardown(ss_ctx *ctx) {
         if (ctx->stage_out[i]) cudaFree(ctx->stage_out[i]);
     }
     if (ctx->scratch) cudaFree(ctx->scratch);
+    if (ctx->pinned) cudaFreeHost(ctx->pinned);
     if (ctx->dev_status) cudaFree(ctx->dev_status);
     if (ctx->owns_stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
@@ -559,14 +577,29 @@ int ss_rs_encode(ss_rs_coder *c, uint8_t *const *shards, size_t n_shards, size_t
     SS_TRY(ctx_scratch(ctx, par_at + size_t(p) * ds, &scr));
     uint8_t *d_data = static_cast<uint8_t *>(scr);
     uint8_t *d_par = d_data + par_at;
-    for (int i = 0; i < d; ++i)
-        SS_CUDA(cudaMemcpyAsync(d_data + size_t(i) * L, shards[i], L, cudaMemcpyHostToDevice, ctx->stream));
+    const bool staged = size_t(d) * L + size_t(p) * ds <= kStagedCallLimit;
+    uint8_t *pin = nullptr;
+    if (staged) {
+        SS_TRY(ctx_pinned(ctx, size_t(d) * L + size_t(p) * ds, &pin));
+        for (int i = 0; i < d; ++i) memcpy(pin + size_t(i) * L, shards[i], L);
+        SS_CUDA(cudaMemcpyAsync(d_data, pin, size_t(d) * L, cudaMemcpyHostToDevice, ctx->stream));
+    } else {
+        for (int i = 0; i < d; ++i)
+            SS_CUDA(cudaMemcpyAsync(d_data + size_t(i) * L, shards[i], L, cudaMemcpyHostToDevice, ctx->stream));
+    }
     EncGeom g{};
     g.data = d_data; g.data_off = nullptr; g.data_len = nullptr; g.data_stride = size_t(d) * L;
     g.uni_len = static_cast<uint32_t>(size_t(d) * L);
     g.parity = d_par; g.plane_stride = ds; g.par_off = nullptr; g.shard_stride = ds; g.n = 1;
     g.flags = SS_RS_OUT_PADDED16;
     SS_TRY(launch_rs_encode(c, g, nullptr));
+    if (staged) {
+        uint8_t *pout = pin + size_t(d) * L;
+        SS_CUDA(cudaMemcpyAsync(pout, d_par, size_t(p) * ds, cudaMemcpyDeviceToHost, ctx->stream));
+        SS_CUDA(cudaStreamSynchronize(ctx->stream));
+        for (int j = 0; j < p; ++j) memcpy(shards[d + j], pout + size_t(j) * ds, L);
+        return SS_OK;
+    }
     for (int j = 0; j < p; ++j)
         SS_CUDA(cudaMemcpyAsync(shards[d + j], d_par + size_t(j) * ds, L, cudaMemcpyDeviceToHost, ctx->stream));
     SS_CUDA(cudaStreamSynchronize(ctx->stream));
@@ -595,20 +628,39 @@ static int reconstruct_one(ss_rs_coder *c, uint8_t *const *shards, uint8_t *pres
     uint32_t pat = 0;
     for (int i = 0; i < t; ++i)
         if (present[i]) pat |= 1u << i;
-    struct { uint64_t off; uint32_t len; uint32_t pat; int32_t status; } h = {0, static_cast<uint32_t>(size_t(d) * L), pat, 0};
-    SS_CUDA(cudaMemcpyAsync(d_meta, &h, sizeof(h), cudaMemcpyHostToDevice, ctx->stream));
-    for (int i = 0; i < t; ++i)
-        if (present[i])
-            SS_CUDA(cudaMemcpyAsync(d_sh + size_t(i) * ds, shards[i], L, cudaMemcpyHostToDevice, ctx->stream));
+    struct Meta { uint64_t off; uint32_t len; uint32_t pat; int32_t status; } h = {0, static_cast<uint32_t>(size_t(d) * L), pat, 0};
+    const int upto = data_only ? d : t;
+    const bool staged = meta + size_t(t) * ds <= kStagedCallLimit;
+    uint8_t *pin = nullptr;
+    if (staged) {
+        // one pinned image of the metadata block + all shard slots up, one image down
+        SS_TRY(ctx_pinned(ctx, meta + size_t(t) * ds, &pin));
+        memset(pin, 0, meta);
+        memcpy(pin, &h, sizeof(h));
+        for (int i = 0; i < t; ++i)
+            if (present[i]) memcpy(pin + meta + size_t(i) * ds, shards[i], L);
+        SS_CUDA(cudaMemcpyAsync(d_meta, pin, meta + size_t(t) * ds, cudaMemcpyHostToDevice, ctx->stream));
+    } else {
+        SS_CUDA(cudaMemcpyAsync(d_meta, &h, sizeof(h), cudaMemcpyHostToDevice, ctx->stream));
+        for (int i = 0; i < t; ++i)
+            if (present[i])
+                SS_CUDA(cudaMemcpyAsync(d_sh + size_t(i) * ds, shards[i], L, cudaMemcpyHostToDevice, ctx->stream));
+    }
     SS_TRY(launch_rs_reconstruct(c, d_sh, ds, reinterpret_cast<const uint64_t *>(d_meta),
                                  reinterpret_cast<const uint32_t *>(d_meta + 8),
                                  reinterpret_cast<const uint32_t *>(d_meta + 12), 1, data_only,
                                  reinterpret_cast<int32_t *>(d_meta + 16), SS_RS_OUT_PADDED16));
-    const int upto = data_only ? d : t;
-    for (int i = 0; i < upto; ++i)
-        if (!present[i])
-            SS_CUDA(cudaMemcpyAsync(shards[i], d_sh + size_t(i) * ds, L, cudaMemcpyDeviceToHost, ctx->stream));
-    SS_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (staged) {
+        SS_CUDA(cudaMemcpyAsync(pin + meta, d_sh, size_t(t) * ds, cudaMemcpyDeviceToHost, ctx->stream));
+        SS_CUDA(cudaStreamSynchronize(ctx->stream));
+        for (int i = 0; i < upto; ++i)
+            if (!present[i]) memcpy(shards[i], pin + meta + size_t(i) * ds, L);
+    } else {
+        for (int i = 0; i < upto; ++i)
+            if (!present[i])
+                SS_CUDA(cudaMemcpyAsync(shards[i], d_sh + size_t(i) * ds, L, cudaMemcpyDeviceToHost, ctx->stream));
+        SS_CUDA(cudaStreamSynchronize(ctx->stream));
+    }
     for (int i = 0; i < upto; ++i) present[i] = 1;
     return SS_OK;
 }

@@ -85,6 +85,9 @@ struct ss_ctx {
     void *stage_in[kStages] = {};
     void *stage_out[kStages] = {};
     size_t stage_in_bytes = 0, stage_out_bytes = 0;
+    // pinned host staging of the single-codeword host-slice calls (grow-only)
+    void *pinned = nullptr;
+    size_t pinned_bytes = 0;
     // device status word (bit 0: a step-flag wait timed out), allocated with the context
     uint32_t *dev_status = nullptr;
 };
