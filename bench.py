@@ -454,10 +454,16 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    # The clock sampler is started BEFORE the warm-up: forking nvidia-smi takes rank 0's host thread tens of ms, and at N > 1
+    # the other ranks' first timed steps would wait that long for rank 0's first launch (profiles/r02_timeline_n8_*_serial*:
+    # one 70-100 ms interval at the start of the timed region on every rank but 0 -- the "5 ms/step outside the kernel" of
+    # round 1's N = 8 run).
+    sampler = ClockSampler(local) if rank == 0 else None
     for _ in range(max(3, args.warmup)):
         step()
+    if rep is not None:
+        rep.drain()
     barrier()
-    sampler = ClockSampler(local) if rank == 0 else None
     launches0 = ctx.launches + (rep.comm.launches if rep is not None and rep.mode == "ce" else 0)
     tl = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)] if (args.timeline and world > 1) else None
     t_start = torch.cuda.Event(enable_timing=True); t_end = torch.cuda.Event(enable_timing=True)
