@@ -321,6 +321,7 @@ int ss_event_record(ss_ctx *ctx, void *event);
 int ss_event_wait(ss_ctx *ctx, void *event);
 /* reads (and clears) the context's device status word; synchronises the context's stream */
 #define SS_DEV_STATUS_FLAG_TIMEOUT 1u
+#define SS_DEV_STATUS_FRAME_OVERFLOW 4u   /* ss_frame_accept_pack_dev: a frame did not fit frame_stride */
 int ss_ctx_device_status(ss_ctx *ctx, uint32_t *status);
 
 /* Fused encode + tally + REPLICATE (the multi-GPU accept step): as ss_accept_step_fused_dev, but shard j of the
@@ -392,7 +393,8 @@ int ss_frame_accept_batch_dev(ss_ctx *ctx, const uint8_t *shard_plane, uint64_t 
  * utils/rscoding.rs:43-72; with_assignment appends assignment: Vec<Bitmap> = that policy row (utils/bitmap.rs:20-30).
  * policies: DEVICE array [n_policies][population] of shard bitmasks; policy_idx: device [n] or NULL (policy 0).
  * Frame g is written inside out[g*frame_stride ..) at frame_off[g] (placed so that its first shard's bytes are 16-byte
- * aligned) and is frame_len[g] bytes long; frame_stride >= ss_frame_accept_max_len(spec, max shards per frame).
+ * aligned) and is frame_len[g] bytes long; frame_stride >= ss_frame_accept_max_len(spec, max shards per frame) -- a
+ * frame that would not fit its slot is not written: frame_len[g] = 0 and bit 2 of ss_ctx_device_status is set.
  * bincode layout from knowledge of the crate: unpinned against the reference; tested byte for byte against the oracle's
  * independent C encoder (oracle/ss_wire.c), and decode(encode(x)) == x. */
 #define SS_FRAME_PEER_ACCEPT 0u

@@ -264,7 +264,8 @@ def _ctx_extras():
 
     def frame_accept_pack(self, shard_planes: torch.Tensor, data_len: int, d: int, p: int, policies: Sequence[Sequence[int]],
                           policy_idx: Optional[torch.Tensor], peer: int, slot: torch.Tensor, ballot: torch.Tensor, kind: int = 0,
-                          msg_variant: int = 2, with_assignment: bool = False, max_shards: Optional[int] = None):
+                          msg_variant: int = 2, with_assignment: bool = False, max_shards: Optional[int] = None,
+                          frame_stride: Optional[int] = None):
         """General Accept / WAL AcceptData packer.  shard_planes uint8 [d+p, n, shard_stride]; policies [K][population] shard
         bitmasks.  Returns (out uint8 [n, frame_stride], frame_off int64 [n], frame_len int32 [n])."""
         T, n, ss = shard_planes.shape
@@ -273,7 +274,7 @@ def _ctx_extras():
         dev = shard_planes.device
         pol_dev = torch.from_numpy(pol.view(np.int32)).to(dev)
         spec = _lib.FrameSpec(kind, msg_variant, d, p, data_len, pol.shape[1], 1 if with_assignment else 0, T)
-        stride = int(self.lib.ss_frame_accept_max_len(C.byref(spec), max_shards if max_shards is not None else T))
+        stride = frame_stride or int(self.lib.ss_frame_accept_max_len(C.byref(spec), max_shards if max_shards is not None else T))
         out = torch.full((n, stride), 0xA5, dtype=torch.uint8, device=dev)       # the C ABI does not require a zeroed buffer
         off = torch.empty(n, dtype=torch.int64, device=dev)
         ln = torch.empty(n, dtype=torch.int32, device=dev)

@@ -78,6 +78,7 @@ struct PackArgs {
     uint64_t frame_stride;
     uint64_t *frame_off;
     uint32_t *frame_len;
+    uint32_t *status;               // context's device status word
 };
 
 __global__ void __launch_bounds__(kWireThreads) frame_pack_kernel(const __grid_constant__ PackArgs A) {
@@ -107,6 +108,25 @@ __global__ void __launch_bounds__(kWireThreads) frame_pack_kernel(const __grid_c
         const uint32_t first = mask ? static_cast<uint32_t>(__ffs(mask) - 1) : T;
         const uint32_t pre = 8u + static_cast<uint32_t>(h) + first + (mask ? some_len : 0u);
         const uint32_t pad = (16u - (pre & 15u)) & 15u;
+        // the frame must fit its slot: its length is known before a byte is written
+        uint32_t asg_len = 0;
+        if (A.with_assignment) {
+            const uint32_t nblocks = (A.assign_size + 63u) / 64u;
+            asg_len = static_cast<uint32_t>(wv_len(A.population));
+            for (uint32_t r = 0; r < A.population; ++r)
+                asg_len += static_cast<uint32_t>(wv_len(A.assign_size) + wv_len(nblocks) + wv_len(pol[r])) + (nblocks > 1u ? nblocks - 1u : 0u);
+        }
+        const uint32_t carried = static_cast<uint32_t>(__popc(mask));
+        const uint64_t need = static_cast<uint64_t>(pad) + 8u + static_cast<uint32_t>(h) + (T - carried) +
+                              static_cast<uint64_t>(carried) * (some_len + A.L) + 1u + asg_len;
+        if (need > A.frame_stride) {
+            if (lane == 0u) {
+                A.frame_off[g] = g * A.frame_stride;
+                A.frame_len[g] = 0;                                              // nothing written for this codeword
+                atomicOr(A.status, 4u);                                          // SS_DEV_STATUS_FRAME_OVERFLOW
+            }
+            continue;
+        }
         uint8_t *f = A.out + g * A.frame_stride + pad;
         for (uint32_t i = lane; i < static_cast<uint32_t>(h); i += 32u) f[8u + i] = hdr[i];
         uint32_t at = 8u + static_cast<uint32_t>(h);                             // running offset inside the frame
@@ -323,9 +343,8 @@ int ss_frame_accept_pack_dev(ss_ctx *ctx, const ss_frame_spec *s, const uint8_t 
     if (s->with_assignment && (s->assign_size == 0 || s->assign_size > 64)) return set_error(SS_ERR_INVALID_ARG, "assignment bitmaps must have 1..64 bits");
     if ((frame_stride & 15u) || ((reinterpret_cast<uintptr_t>(out) | reinterpret_cast<uintptr_t>(shard_planes) | plane_stride | shard_stride) & 15u))
         return set_error(SS_ERR_INVALID_ARG, "frame_stride, buffers and strides must be 16-byte aligned");
-    if (frame_stride < ss_frame_accept_max_len(s, T))
-        ;   // the caller may know a tighter bound on the shards per frame; per-frame overflow cannot be checked without the masks
     PackArgs A;
+    A.status = ctx->dev_status;     // a frame that does not fit frame_stride is skipped (frame_len 0) and reported there
     A.planes = shard_planes; A.plane_stride = plane_stride; A.shard_stride = shard_stride;
     A.d = s->data_shards; A.p = s->parity_shards; A.data_len = s->data_len; A.L = (s->data_len + s->data_shards - 1) / s->data_shards;
     A.kind = s->kind; A.variant = s->msg_variant; A.policies = policies; A.policy_idx = policy_idx; A.n_policies = n_policies;

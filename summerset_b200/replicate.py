@@ -32,7 +32,7 @@ from typing import Callable, List, Optional, Sequence
 
 import torch
 
-from .api import Context, DevBuffer, ReedSolomon, StepSync, round_up, shard_len
+from .api import Context, ReedSolomon, StepSync, round_up, shard_len
 from .sharding import replica_rank
 
 FLAG_SLOTS = 16        # u64 counters per flag array (>= replicas)

@@ -402,6 +402,25 @@ def test_general_frame_packer_matches_oracle(ctx, oracle, kind, data_len):
 
 
 @pytest.mark.gpu
+def test_frame_packer_refuses_frames_that_do_not_fit(ctx, oracle):
+    """a slot too small for its frame: nothing is written for that codeword, frame_len = 0, status bit 2"""
+    d, p, pop, n, data_len = 3, 2, 5, 40, 4096
+    data = wl.payload_uniform(n, data_len, seed_extra=5)
+    planes, L, ds = _shard_planes(oracle, d, p, data, data_len)
+    slot = np.arange(n, dtype=np.uint64); ballot = np.full(n, 7, dtype=np.uint64)
+    policies = [[0b00111, 0b01110, 0b11100, 0b11001, 0b10011]]                       # three shards per peer
+    small = ((L + 128) + 15) // 16 * 16                                              # room for one shard only
+    out, off, ln = ctx.frame_accept_pack(torch.from_numpy(planes).to(DEV), data_len, d, p, policies, None, 0, _t(slot), _t(ballot),
+                                         frame_stride=small)
+    torch.cuda.synchronize()
+    assert int(ln.abs().sum()) == 0 and (out.cpu().numpy() == 0xA5).all()
+    assert ctx.device_status() == 4
+    out, off, ln = ctx.frame_accept_pack(torch.from_numpy(planes).to(DEV), data_len, d, p, policies, None, 0, _t(slot), _t(ballot))
+    torch.cuda.synchronize()
+    assert (ln.cpu().numpy() > 3 * L).all() and ctx.device_status() == 0
+
+
+@pytest.mark.gpu
 @pytest.mark.parametrize("with_size", [False, True])
 def test_accept_reply_parser_feeds_ingest(ctx, oracle, with_size):
     """AcceptReply frames (rspaxos/mod.rs:290-291; crossword/mod.rs:365-373 with size + reply_ts) interleaved with other
