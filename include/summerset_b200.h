@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define SS_VERSION 100 /* 0.1.0 */
+#define SS_VERSION 200 /* 0.2.0: engine, step flags, wire formats, uniform reconstruct; several round-1 signatures gained a parameter */
 
 /* ---- error codes ---------------------------------------------------------------------------
  * -1..-13: reed_solomon_erasure::Error variants in declaration order. */

@@ -23,7 +23,7 @@ def test_library_exports_every_declared_symbol():
     for name in sorted(declared):
         assert hasattr(lib, name), f"{name} declared in the header but not exported"
     assert declared == set(_lib.SIGNATURES), "ctypes table and header disagree"
-    assert lib.ss_version() == 100
+    assert lib.ss_version() == 200
     assert b"no CPU fallback" in lib.ss_strerror(_lib.SS_ERR_NO_DEVICE)
 
 
