@@ -841,7 +841,7 @@ def bench_cfg4(env, steps, warmup):
     torch, dist, ctx, rs, dev, world, rank, peak, args = (env[k] for k in ("torch", "dist", "ctx", "rs", "dev", "world", "rank", "peak", "args"))
     from oracle import pyoracle as oracle
     from summerset_b200 import sharding, workloads as wl
-    from summerset_b200.api import crossword_brr_assignment
+    from summerset_b200.api import crossword_brr_assignment, cw_slot_pitch
     n = args.groups
     lens, spr = wl.cfg4_lengths(n, seed_extra=0)      # same sizes on every rank (payload bytes differ by rank)
     lay = wl.ragged_layout(lens, D)
@@ -855,7 +855,7 @@ def bench_cfg4(env, steps, warmup):
     pidx = torch.from_numpy((spr - 1).astype(np.uint8)).to(dev)
     policies = [crossword_brr_assignment(5, 5, s) for s in (1, 2, 3)]
     # replica logs for the distribute step: replica r of my groups lives on rank (rank + r) % world
-    Lp = (lay["L"].astype(np.int64) + 15) // 16 * 16
+    Lp = cw_slot_pitch(lay["L"].astype(np.int64))
     slot_bytes = spr.astype(np.int64) * Lp
     rep_off_np = np.concatenate([[0], np.cumsum(slot_bytes)[:-1]]).astype(np.int64)
     region = int(slot_bytes.sum() + 255) // 256 * 256

@@ -357,10 +357,13 @@ int ss_follower_ack_dev(ss_ctx *ctx, const uint64_t *ack_src, uint64_t *const *a
 /* Crossword encode + distribute (BASELINE config 4; crossword/request.rs:82-87,137-185): RS-encodes a ragged batch with
  * the coder's (d, T-d) code and writes, for every codeword g, the spr[g] shards the balanced round-robin assignment gives
  * replica r -- shards {(r*dj + k) mod T : k < spr[g]}, dj = T / n_replicas (crossword/mod.rs:866-888) -- into
- * replica_logs[r] at rep_off[g] + k*round_up(L_g,16), k = 0..spr-1 (bytes past L_g zero).  replica_logs is a HOST array
+ * replica_logs[r] at rep_off[g] + k*SS_CW_SLOT_PITCH(L_g), k = 0..spr-1 (bytes past L_g zero; the pitch is L_g rounded up
+ * to 32 bytes so that every slot of a log built from 32-byte aligned offsets starts on a DRAM sector: with a 16-byte
+ * pitch the same kernel is 7 % slower, profiles/r02_distribute_variants.txt).  replica_logs is a HOST array
  * of n_replicas device pointers, local or peer (ss_ipc_open): the kernel's stores are the shard transfer.  Per codeword
  * (n-1)*spr*L_g bytes cross to other replicas, as in the reference.  Any code with d <= 8 and T a multiple of
  * n_replicas <= 16 (crossword/mod.rs:805-830); n = 5 with RS(3,2) runs the hand-specialised kernel. */
+#define SS_CW_SLOT_PITCH(L) ((((uint64_t)(L)) + 31u) & ~(uint64_t)31u)
 int ss_crossword_distribute_dev(ss_rs_coder *coder, const uint8_t *data, const uint64_t *data_off,
                                 const uint32_t *data_len, const uint8_t *spr, const uint64_t *rep_off,
                                 uint64_t n, uint8_t *const *replica_logs, uint32_t n_replicas);

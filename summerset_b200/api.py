@@ -33,6 +33,12 @@ def round_up(x: int, a: int) -> int:
     return (x + a - 1) // a * a
 
 
+def cw_slot_pitch(L):
+    """SS_CW_SLOT_PITCH of include/summerset_b200.h: bytes between the slots of one codeword in a Crossword replica log
+    (shard length rounded up to 32; works on ints and numpy arrays)."""
+    return (L + 31) // 32 * 32
+
+
 def shard_len(data_len: int, d: int) -> int:
     """rscoding.rs:177-181"""
     return data_len // d if data_len % d == 0 else data_len // d + 1
@@ -529,7 +535,7 @@ class ReedSolomon:
     def crossword_distribute(self, data: torch.Tensor, data_off: torch.Tensor, data_len: torch.Tensor, spr: torch.Tensor,
                              rep_off: torch.Tensor, replica_logs: Sequence[int]) -> None:
         """Crossword: encode the ragged batch and write replica r's spr[g] shards {(r*dj + k) mod T} into replica_logs[r]
-        (len(replica_logs) = population; T = d + p must be a multiple of it)."""
+        (len(replica_logs) = population; T = d + p must be a multiple of it) at rep_off[g] + k * cw_slot_pitch(L_g)."""
         assert data_off.dtype == torch.int64 and data_len.dtype == torch.int32 and spr.dtype == torch.uint8 and rep_off.dtype == torch.int64
         arr = (C.c_void_p * len(replica_logs))(*replica_logs)
         check(self.lib.ss_crossword_distribute_dev(self.h, _ptr(data), _ptr(data_off), _ptr(data_len), _ptr(spr),

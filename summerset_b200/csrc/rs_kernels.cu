@@ -996,7 +996,7 @@ static int dispatch_p(int p, F &&f) {
 // Crossword distribute (BASELINE config 4, n = 5 replicas, RS(3,2), T = 5 total shards, dj = 1):
 // encode a ragged batch and write, for every codeword g, the spr[g] shards of replica r --
 // shards {(r + k) mod 5 : k < spr} (balanced round-robin assignment, crossword/mod.rs:866-888) -- into
-// replica r's log at rep_off[g] + k * round_up(L_g,16).  The five log bases may be local memory or peer
+// replica r's log at rep_off[g] + k * round_up(L_g,32).  The five log bases may be local memory or peer
 // GPUs' HBM (CUDA IPC): this is crossword/request.rs:137-185 (subset_copy per peer + send_msg) for a
 // whole batch, with the NVLink transfer done by the encode kernel's own stores.
 // ------------------------------------------------------------------------------------------------
@@ -1008,6 +1008,7 @@ struct CwDistribute {
     const uint64_t *rep_off;   // byte offset of codeword g's slots inside every replica log
     uint8_t *rep[5];           // replica log bases
     uint64_t n;
+    unsigned long long *next_cw;   // dynamic kernels: the next codeword nobody has taken yet (zeroed before the launch)
 };
 
 // raw aligned vectors covering one unmasked column of the three data shards
@@ -1045,81 +1046,6 @@ __device__ __forceinline__ void distribute_store(const CwDistribute &P, uint64_t
     }
 }
 
-template <bool PAIR>
-__global__ void __launch_bounds__(kThreads, PAIR ? 3 : 5) rs32_crossword_distribute_kernel(const __grid_constant__ CwDistribute P) {
-    const uint32_t lane = threadIdx.x & 31u;
-    const uint64_t warp = (static_cast<uint64_t>(blockIdx.x) * kThreads + threadIdx.x) >> 5;
-    const uint64_t nwarps = (static_cast<uint64_t>(gridDim.x) * kThreads) >> 5;
-    auto clamp16 = [](int64_t r) { return r > 16 ? 16 : (r < 0 ? 0 : static_cast<int>(r)); };
-    for (uint64_t g = warp; g < P.n; g += nwarps) {
-        const uint32_t len = __ldg(P.data_len + g);
-        if (len == 0u) continue;
-        const uint32_t spr = __ldg(P.spr + g);
-        const uint32_t L = (len + 2u) / 3u;
-        const uint32_t vpc = (L + 15u) >> 4;
-        const uint32_t Lpad = vpc * 16u;
-        const uint8_t *pay = P.data + __ldg(P.data_off + g);
-        const uint64_t ro = __ldg(P.rep_off + g);
-        const uint32_t s0 = static_cast<uint32_t>(reinterpret_cast<uintptr_t>(pay)) & 15u;
-        const uint8_t *src = pay - s0;
-        const uint32_t s1 = (s0 + L) & 15u, s2 = (s0 + 2u * L) & 15u;
-        const uint32_t fast_cols = len >= 2u * L ? (((len - 2u * L) < L ? (len - 2u * L) : L) / 16u) : 0u;
-        uint32_t v0 = 0;
-        // interior columns, two per lane per iteration: all loads in flight before any compute
-        if constexpr (PAIR) {
-            for (; v0 + 64u <= fast_cols; v0 += 64u) {
-                const uint32_t k = (v0 + lane) * 16u, k2 = k + 512u;
-                Raw6 r1, r2;
-                rs32_issue_loads(src, k, s0 + L + k - s1, s0 + 2u * L + k - s2, s0, s1, s2, r1);
-                rs32_issue_loads(src, k2, s0 + L + k2 - s1, s0 + 2u * L + k2 - s2, s0, s1, s2, r2);
-                uint4 sh[5];
-                rs32_shards_from_raw(r1, s0, s1, s2, sh);
-                distribute_store(P, ro, k, Lpad, spr, sh);
-                rs32_shards_from_raw(r2, s0, s1, s2, sh);
-                distribute_store(P, ro, k2, Lpad, spr, sh);
-            }
-        }
-        for (; v0 < vpc; v0 += 32u) {
-            const uint32_t v = v0 + lane;
-            if (v >= vpc) break;
-            const uint32_t k = v * 16u;
-            const uint32_t o1 = s0 + L + k - s1, o2 = s0 + 2u * L + k - s2;
-            uint4 sh[5];
-            if (v0 + 32u <= fast_cols) {
-                Raw6 r1;
-                rs32_issue_loads(src, k, o1, o2, s0, s1, s2, r1);
-                rs32_shards_from_raw(r1, s0, s1, s2, sh);
-            } else {
-                // masked column: zero-padded payload tail / partial last vector; windows in the padding are not read
-                const int nva = clamp16(static_cast<int64_t>(len) - k);
-                const int nvb = clamp16(static_cast<int64_t>(len) - L - k);
-                const int nvc = clamp16(static_cast<int64_t>(len) - 2ll * L - k);
-                const int onv = clamp16(static_cast<int64_t>(L) - k);
-                const uint4 a0 = dev::ldg128(src + k);
-                uint4 a1 = make_uint4(0u, 0u, 0u, 0u);
-                if (s0 != 0u && static_cast<int>(s0) + nva > 16) a1 = dev::ldg128(src + k + 16u);
-                uint4 b0 = make_uint4(0u, 0u, 0u, 0u), c0 = make_uint4(0u, 0u, 0u, 0u);
-                if (nvb > 0) b0 = dev::ldg128(src + o1);
-                uint4 b1 = make_uint4(0u, 0u, 0u, 0u);
-                if (s1 != 0u && static_cast<int>(s1) + nvb > 16) b1 = dev::ldg128(src + o1 + 16u);
-                if (nvc > 0) c0 = dev::ldg128(src + o2);
-                uint4 c1 = make_uint4(0u, 0u, 0u, 0u);
-                if (s2 != 0u && static_cast<int>(s2) + nvc > 16) c1 = dev::ldg128(src + o2 + 16u);
-                sh[0] = keep_bytes(s0 != 0u ? funnel16(a0, a1, s0) : a0, nva < onv ? nva : onv);
-                sh[1] = keep_bytes(s1 != 0u ? funnel16(b0, b1, s1) : b0, nvb < onv ? nvb : onv);
-                sh[2] = keep_bytes(s2 != 0u ? funnel16(c0, c1, s2) : c0, nvc < onv ? nvc : onv);
-                rs32_word_fast(sh[0].x, sh[1].x, sh[2].x, sh[3].x, sh[4].x);
-                rs32_word_fast(sh[0].y, sh[1].y, sh[2].y, sh[3].y, sh[4].y);
-                rs32_word_fast(sh[0].z, sh[1].z, sh[2].z, sh[3].z, sh[4].z);
-                rs32_word_fast(sh[0].w, sh[1].w, sh[2].w, sh[3].w, sh[4].w);
-                sh[3] = keep_bytes(sh[3], onv);
-                sh[4] = keep_bytes(sh[4], onv);
-            }
-            distribute_store(P, ro, k, Lpad, spr, sh);
-        }
-    }
-}
-
 // one column (masked when it touches the payload tail / the last partial vector) of codeword geometry (len, L, s0)
 __device__ __forceinline__ void cw_column(const CwDistribute &P, const uint8_t *__restrict__ src, uint32_t len, uint32_t L, uint32_t v,
                                           uint32_t s0, uint32_t s1, uint32_t s2, bool fast, uint64_t ro, uint32_t Lpad, uint32_t spr) {
@@ -1136,8 +1062,8 @@ __device__ __forceinline__ void cw_column(const CwDistribute &P, const uint8_t *
         const int nvb = clamp16(static_cast<int64_t>(len) - L - k);
         const int nvc = clamp16(static_cast<int64_t>(len) - 2ll * L - k);
         const int onv = clamp16(static_cast<int64_t>(L) - k);
-        const uint4 a0 = dev::ldg128(src + k);
-        uint4 a1 = make_uint4(0u, 0u, 0u, 0u);
+        uint4 a0 = make_uint4(0u, 0u, 0u, 0u), a1 = a0;    // the all-padding column of an odd-length slot reads nothing
+        if (nva > 0) a0 = dev::ldg128(src + k);
         if (s0 != 0u && static_cast<int>(s0) + nva > 16) a1 = dev::ldg128(src + k + 16u);
         uint4 b0 = make_uint4(0u, 0u, 0u, 0u), c0 = make_uint4(0u, 0u, 0u, 0u);
         if (nvb > 0) b0 = dev::ldg128(src + o1);
@@ -1159,39 +1085,107 @@ __device__ __forceinline__ void cw_column(const CwDistribute &P, const uint8_t *
     distribute_store(P, ro, k, Lpad, spr, sh);
 }
 
-// Cooperative flavour: a CTA of 8 warps takes 8 consecutive codewords at a time.  Short codewords (up to 64 columns, i.e.
-// payloads up to 3 KB) go one per warp; every longer one is walked by ALL eight warps together, 32-column blocks dealt round
-// robin -- so the long codewords, which carry almost all of the bytes of a mixed-size batch, are streamed by 256 threads with
-// one column each (high memory-level parallelism at 40 registers) and every destination slot is written in 4 KB runs.
-__global__ void __launch_bounds__(kThreads, 5) rs32_crossword_distribute_coop_kernel(const __grid_constant__ CwDistribute P) {
-    const uint32_t lane = threadIdx.x & 31u, wid = threadIdx.x >> 5;
-    constexpr uint32_t kBatch = kThreads / 32;
-    const uint64_t nbatches = (P.n + kBatch - 1) / kBatch;
-    for (uint64_t b = blockIdx.x; b < nbatches; b += gridDim.x) {
-        // lanes 0..7 fetch the batch's metadata; everyone gets it by shuffle
-        const uint64_t gm = b * kBatch + (lane & (kBatch - 1u));
-        uint32_t m_len = 0, m_spr = 0; uint64_t m_off = 0, m_ro = 0;
-        if (gm < P.n) { m_len = __ldg(P.data_len + gm); m_spr = __ldg(P.spr + gm); m_off = __ldg(P.data_off + gm); m_ro = __ldg(P.rep_off + gm); }
+// A warp takes a RUN of codewords (RUN consecutive ones from a shared counter when DYN, else one at a fixed stride) and
+// walks it in two phases:
+//   A  every codeword of 64 unmasked columns or more (payloads from 3 KB): its interior in blocks of 64 columns, two
+//      columns per lane, all loads in flight before any compute, then its own trailing columns;
+//   B  the SHORT codewords of the run, pooled into one column sequence dealt 32 lanes at a time, each lane looking up
+//      which codeword its column is in (lane j of the warp holds the geometry of codeword j of the run).
+// Why the pooling: walked alone, a payload of 256 B costs a full pass of ~400 warp instructions for 6 useful lanes; a batch
+// of such payloads runs 3.3x faster pooled (0.30 ms vs 0.97 ms per 2^20).  In the cfg-4 mix the short codewords carry 3 % of
+// the bytes and the pooling does not pay for the coarser unit of work, so RUN = 1 stays the default there
+// (profiles/r02_distribute_variants.txt).
+// The next run is fetched one run ahead, so the counter's latency hides behind the current run.
+template <int RUN, bool DYN>
+__global__ void __launch_bounds__(kThreads, 3) rs32_crossword_distribute_kernel(const __grid_constant__ CwDistribute P) {
+    static_assert(RUN >= 1 && RUN <= 32, "a lane per codeword of the run");
+    constexpr uint32_t kFull = 0xffffffffu;
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint64_t warp = (static_cast<uint64_t>(blockIdx.x) * kThreads + threadIdx.x) >> 5;
+    const uint64_t nwarps = (static_cast<uint64_t>(gridDim.x) * kThreads) >> 5;
+    auto take = [&]() -> uint64_t {
+        unsigned long long v = 0;
+        if (lane == 0u) v = atomicAdd(P.next_cw, static_cast<unsigned long long>(RUN));
+        return __shfl_sync(kFull, v, 0);
+    };
+    auto shfl64 = [&](uint64_t v, uint32_t from) -> uint64_t {
+        const uint32_t lo = __shfl_sync(kFull, static_cast<uint32_t>(v), from), hi = __shfl_sync(kFull, static_cast<uint32_t>(v >> 32), from);
+        return (static_cast<uint64_t>(hi) << 32) | lo;
+    };
+    // column bookkeeping of a codeword of `len` bytes: shard length, columns, unmasked columns, columns phase A covers
+    auto cols_of = [](uint32_t len, uint32_t &L, uint32_t &vpc, uint32_t &fast_cols, uint32_t &done) {
+        L = (len + 2u) / 3u;
+        vpc = ((L + 31u) >> 5) << 1;                       // 16-byte columns of a slot: the slot pitch is round_up(L, 32)
+        fast_cols = len >= 2u * L ? (((len - 2u * L) < L ? (len - 2u * L) : L) / 16u) : 0u;
+        done = fast_cols & ~63u;
+    };
+    uint64_t base = DYN ? take() : warp * RUN, ahead = DYN ? take() : (warp + nwarps) * RUN;
+    while (base < P.n) {
+        const uint64_t rb = base;
+        base = ahead;
+        ahead = DYN ? take() : ahead + nwarps * RUN;
+        // lane j < RUN holds codeword rb + j: one gather of the four geometry arrays per run
+        uint32_t m_len = 0, m_spr = 0;
+        uint64_t m_off = 0, m_ro = 0;
+        if (lane < static_cast<uint32_t>(RUN) && rb + lane < P.n) {
+            m_len = __ldg(P.data_len + rb + lane); m_spr = __ldg(P.spr + rb + lane);
+            m_off = __ldg(P.data_off + rb + lane); m_ro = __ldg(P.rep_off + rb + lane);
+        }
+        uint32_t mL, mvpc, mfast, mdone;
+        cols_of(m_len, mL, mvpc, mfast, mdone);
+        uint32_t pool_end = mdone == 0u ? mvpc : 0u;       // inclusive prefix sum of the pooled column counts over the run
+#pragma unroll
+        for (uint32_t d = 1; d < static_cast<uint32_t>(RUN); d <<= 1) {
+            const uint32_t up = __shfl_up_sync(kFull, pool_end, d);
+            if (lane >= d) pool_end += up;
+        }
+        const uint32_t pool_total = __shfl_sync(kFull, pool_end, RUN - 1);
+        // ---- phase A ----
 #pragma unroll 1
-        for (uint32_t i = 0; i < kBatch; ++i) {
-            const uint32_t len = __shfl_sync(0xffffffffu, m_len, i);
-            if (len == 0u) continue;                                   // null codeword or past the end
-            const uint32_t L = (len + 2u) / 3u, vpc = (L + 15u) >> 4;
-            const bool shortcw = vpc <= 64u;
-            if (shortcw && i != wid) continue;                         // short: warp i alone
-            const uint32_t spr = __shfl_sync(0xffffffffu, m_spr, i);
-            const uint64_t off = __shfl_sync(0xffffffffu, m_off, i), ro = __shfl_sync(0xffffffffu, m_ro, i);
-            const uint8_t *pay = P.data + off;
+        for (uint32_t j = 0; j < static_cast<uint32_t>(RUN); ++j) {
+            const uint32_t len = __shfl_sync(kFull, m_len, j);
+            uint32_t L, vpc, fast_cols, done;
+            cols_of(len, L, vpc, fast_cols, done);
+            if (done == 0u) continue;                      // uniform: every lane sees the same len
+            const uint32_t spr = __shfl_sync(kFull, m_spr, j);
+            const uint8_t *pay = P.data + shfl64(m_off, j);
+            const uint64_t ro = shfl64(m_ro, j);
+            const uint32_t Lpad = vpc * 16u;
             const uint32_t s0 = static_cast<uint32_t>(reinterpret_cast<uintptr_t>(pay)) & 15u;
             const uint8_t *src = pay - s0;
             const uint32_t s1 = (s0 + L) & 15u, s2 = (s0 + 2u * L) & 15u;
-            const uint32_t fast_cols = len >= 2u * L ? (((len - 2u * L) < L ? (len - 2u * L) : L) / 16u) : 0u;
-            const uint32_t Lpad = vpc * 16u;
-            const uint32_t first = shortcw ? 0u : wid * 32u, step = shortcw ? 32u : kThreads;
-            for (uint32_t v0 = first; v0 < vpc; v0 += step) {
-                const uint32_t v = v0 + lane;
-                if (v >= vpc) break;
-                cw_column(P, src, len, L, v, s0, s1, s2, v0 + 32u <= fast_cols, ro, Lpad, spr);
+            for (uint32_t v0 = 0; v0 < done; v0 += 64u) {
+                const uint32_t k = (v0 + lane) * 16u, k2 = k + 512u;
+                Raw6 r1, r2;
+                rs32_issue_loads(src, k, s0 + L + k - s1, s0 + 2u * L + k - s2, s0, s1, s2, r1);
+                rs32_issue_loads(src, k2, s0 + L + k2 - s1, s0 + 2u * L + k2 - s2, s0, s1, s2, r2);
+                uint4 sh[5];
+                rs32_shards_from_raw(r1, s0, s1, s2, sh);
+                distribute_store(P, ro, k, Lpad, spr, sh);
+                rs32_shards_from_raw(r2, s0, s1, s2, sh);
+                distribute_store(P, ro, k2, Lpad, spr, sh);
+            }
+            // its own < 64 + 2 trailing columns: whole passes are unmasked or masked together
+            for (uint32_t v0 = done; v0 < vpc; v0 += 32u)
+                if (v0 + lane < vpc) cw_column(P, src, len, L, v0 + lane, s0, s1, s2, v0 + 32u <= fast_cols, ro, Lpad, spr);
+        }
+        // ---- phase B ----
+#pragma unroll 1
+        for (uint32_t t0 = 0; t0 < pool_total; t0 += 32u) {
+            const uint32_t t = t0 + lane;
+            uint32_t mine = 0;                             // how many codewords of the run end at or before pooled column t
+#pragma unroll
+            for (uint32_t j = 0; j + 1 < static_cast<uint32_t>(RUN); ++j) mine += __shfl_sync(kFull, pool_end, j) <= t ? 1u : 0u;
+            const uint32_t len = __shfl_sync(kFull, m_len, mine), spr = __shfl_sync(kFull, m_spr, mine);
+            const uint32_t end = __shfl_sync(kFull, pool_end, mine);
+            const uint64_t off = shfl64(m_off, mine), ro = shfl64(m_ro, mine);
+            if (t < pool_total) {
+                uint32_t L, vpc, fast_cols, done;
+                cols_of(len, L, vpc, fast_cols, done);
+                const uint32_t v = vpc - (end - t);        // column of codeword `mine`, all of whose columns are pooled
+                const uint8_t *pay = P.data + off;
+                const uint32_t s0 = static_cast<uint32_t>(reinterpret_cast<uintptr_t>(pay)) & 15u;
+                cw_column(P, pay - s0, len, L, v, s0, (s0 + L) & 15u, (s0 + 2u * L) & 15u, v < fast_cols, ro, vpc * 16u, spr);
             }
         }
     }
@@ -1226,12 +1220,12 @@ __global__ void __launch_bounds__(kThreads, 2) crossword_distribute_generic_kern
         const uint32_t len = __ldg(P.data_len + g);
         if (len == 0u) continue;
         const uint32_t spr = __ldg(P.spr + g);
-        const uint32_t L = (len + P.d - 1u) / P.d, vpc = (L + 15u) >> 4, Lpad = vpc * 16u;
+        const uint32_t L = (len + P.d - 1u) / P.d, vpc = ((L + 31u) >> 5) << 1, Lpad = vpc * 16u;   // slot pitch round_up(L, 32)
         const uint8_t *src = P.data + __ldg(P.data_off + g);
         const uint64_t ro = __ldg(P.rep_off + g);
         for (uint32_t v = lane; v < vpc; v += 32u) {
             const uint32_t k = v * 16u;
-            const int onv = static_cast<int>(L - k) > 16 ? 16 : static_cast<int>(L - k);
+            const int onv = k >= L ? 0 : (L - k > 16u ? 16 : static_cast<int>(L - k));      // 0: the padding column of an odd-length slot
             uint4 x[D], par[kMaxP];
             dev::Raw16 raw[D];
 #pragma unroll
@@ -1304,23 +1298,25 @@ int launch_crossword_distribute(ss_rs_coder *coder, const uint8_t *data, const u
     CwDistribute P;
     P.data = data; P.data_off = data_off; P.data_len = data_len; P.spr = spr; P.rep_off = rep_off; P.n = n;
     for (int r = 0; r < 5; ++r) P.rep[r] = replica_logs[r];
-    // variant bits 0-3 (tuning; measured in profiles/r02_distribute_variants.txt): 0 = warp per codeword, two columns per
-    // pass (default: 13.0 ms on the cfg-4 mix), 1 = one column per pass at 5 CTAs/SM (14.1 ms), 3 = cooperative CTA per long
-    // codeword (18.7 ms: more DRAM traffic, lower DRAM efficiency)
+    // variant bits 0-3 (tuning; profiles/r02_distribute_variants.txt): default = a codeword per warp at a fixed stride (12.16 ms
+    // on the cfg-4 mix); 6 / 7 = runs of 8 / 4 codewords from a shared counter with the short ones pooled -- 1-2 % slower on
+    // the mix (a run of long codewords is a coarse unit of work) but 3.3x faster on batches of payloads under 1 KB, for
+    // callers that know their batch is like that
     const int vk = coder->variant & 15;
-    if (vk != 1 && vk != 3) {
-        rs32_crossword_distribute_kernel<true><<<ragged_grid(ctx, n), kThreads, 0, ctx->stream>>>(P);
-        coder->last_kernel = "rs32_crossword_distribute_kernel<pair>";
-    } else if (vk == 1) {
-        const uint64_t cap = static_cast<uint64_t>(ctx->sm_count) * 5ull * 8ull;
-        uint64_t ctas = (n + 7) / 8; if (ctas > cap) ctas = cap;
-        rs32_crossword_distribute_kernel<false><<<static_cast<uint32_t>(ctas), kThreads, 0, ctx->stream>>>(P);
-        coder->last_kernel = "rs32_crossword_distribute_kernel";
+    P.next_cw = reinterpret_cast<unsigned long long *>(ctx->dev_status + 32);
+    if (vk != 6 && vk != 7) {
+        rs32_crossword_distribute_kernel<1, false><<<ragged_grid(ctx, n), kThreads, 0, ctx->stream>>>(P);
+        coder->last_kernel = "rs32_crossword_distribute_kernel<1>";
     } else {
-        const uint64_t cap = static_cast<uint64_t>(ctx->sm_count) * 5ull * 16ull;
-        uint64_t ctas = (n + 7) / 8; if (ctas > cap) ctas = cap;
-        rs32_crossword_distribute_coop_kernel<<<static_cast<uint32_t>(ctas), kThreads, 0, ctx->stream>>>(P);
-        coder->last_kernel = "rs32_crossword_distribute_coop_kernel";
+        // one CTA per resident slot (3 per SM at 80 registers), never more warps than runs
+        SS_CUDA(cudaMemsetAsync(P.next_cw, 0, sizeof(unsigned long long), ctx->stream));
+        const uint64_t run = vk == 7 ? 4 : 8;
+        uint64_t ctas = static_cast<uint64_t>(ctx->sm_count) * 3ull;
+        const uint64_t need = (n + run * (kThreads / 32) - 1) / (run * (kThreads / 32));
+        if (ctas > need) ctas = need;
+        if (vk == 7) rs32_crossword_distribute_kernel<4, true><<<static_cast<uint32_t>(ctas), kThreads, 0, ctx->stream>>>(P);
+        else rs32_crossword_distribute_kernel<8, true><<<static_cast<uint32_t>(ctas), kThreads, 0, ctx->stream>>>(P);
+        coder->last_kernel = vk == 7 ? "rs32_crossword_distribute_kernel<4,dynamic>" : "rs32_crossword_distribute_kernel<8,dynamic>";
     }
     SS_CUDA(cudaGetLastError());
     ctx->launches++;

@@ -188,12 +188,12 @@ def test_prepare_merge_on_gpu_and_recovery_roundtrip(ctx, oracle):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("variant,kernel", [(0, "rs32_crossword_distribute_kernel<pair>"), (1, "rs32_crossword_distribute_kernel"),
-                                            (3, "rs32_crossword_distribute_coop_kernel")])
+@pytest.mark.parametrize("variant,kernel", [(0, "rs32_crossword_distribute_kernel<1>"), (6, "rs32_crossword_distribute_kernel<8,dynamic>"),
+                                            (7, "rs32_crossword_distribute_kernel<4,dynamic>")])
 def test_crossword_distribute_matches_assignment_and_oracle(ctx, oracle, variant, kernel):
     """config 4 distribute (crossword/request.rs:137-185): every replica's log holds exactly the shards the balanced
     round-robin assignment gives it (crossword/mod.rs:866-888), bytes equal to the oracle's encode."""
-    from summerset_b200.api import ReedSolomon
+    from summerset_b200.api import ReedSolomon, cw_slot_pitch
     rng = np.random.default_rng(6)
     d, p, n_rep = 3, 2, 5
     rs = ReedSolomon(ctx, d, p)
@@ -205,7 +205,7 @@ def test_crossword_distribute_matches_assignment_and_oracle(ctx, oracle, variant
     lay = wl.ragged_layout(lens, d)
     arena = rng.integers(0, 256, lay["data_bytes"] + 64, dtype=np.uint8)
     L = lay["L"].astype(np.int64)
-    Lpad = (L + 15) // 16 * 16
+    Lpad = cw_slot_pitch(L)
     slot_bytes = spr.astype(np.int64) * Lpad
     rep_off = np.concatenate([[0], np.cumsum(slot_bytes)[:-1]]).astype(np.int64)
     total = int(slot_bytes.sum())
@@ -241,7 +241,7 @@ def test_crossword_distribute_general_codes(ctx, oracle, n_rep, T, d, variant):
     """ss_crossword_distribute_dev for any (T, d, n) with T % n == 0 (crossword/mod.rs:805-830): replica r's log holds
     shards {(r*dj + k) mod T : k < spr} (crossword/mod.rs:866-888), bytes equal to the oracle's encode.  variant 4 runs
     the general kernel on the RS(3,2) / n = 5 case too, so the two kernels are checked against the same oracle."""
-    from summerset_b200.api import ReedSolomon
+    from summerset_b200.api import ReedSolomon, cw_slot_pitch
     rng = np.random.default_rng(T * 10 + n_rep)
     p = T - d
     dj = T // n_rep
@@ -255,7 +255,7 @@ def test_crossword_distribute_general_codes(ctx, oracle, n_rep, T, d, variant):
     lay = wl.ragged_layout(lens, d)
     arena = rng.integers(0, 256, lay["data_bytes"] + 64, dtype=np.uint8)
     L = lay["L"].astype(np.int64)
-    Lpad = (L + 15) // 16 * 16
+    Lpad = cw_slot_pitch(L)
     slot_bytes = spr.astype(np.int64) * Lpad
     rep_off = np.concatenate([[0], np.cumsum(slot_bytes)[:-1]]).astype(np.int64)
     total = int(slot_bytes.sum())
