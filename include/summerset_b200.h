@@ -554,8 +554,9 @@ int ss_engine_raft_ingest(ss_engine *engine, const uint32_t *rec_group, const ui
  *   bits 5-7  row kernel waves of CTAs per resident set: {64 (default), 1, 32, 4, 16, 256, 128, 8}
  *   bits 8-9  cache operator of the plane stores in replicate mode: .cs (default), write-back, .cg, .wt
  *   bit 10    row kernel: fixed instead of rotating warp -> column-block assignment
- *   ss_crossword_distribute_dev, bits 0-3: 1 = one column per pass, 3 = cooperative CTA per long codeword, 4 = the general
- *             (any code) kernel also for RS(3,2) / n = 5
+ *   ss_crossword_distribute_dev, bits 0-3: 6 / 7 = a warp takes runs of 8 / 4 codewords from a shared counter and pools the
+ *             short ones into shared passes (3.3x on batches of sub-KB payloads, 1-2 % behind on mixed sizes), 4 = the
+ *             general (any code) kernel also for RS(3,2) / n = 5
  *   d <= 8 codes other than RS(3,2) (horner_encode_row_kernel / horner_encode_packed_kernel):
  *   bits 0-3  1 = flat kernel; 2 / 3 / 4 = 48 / 64 / 80-register builds of the row layout (default by width)
  *   bit 11    run-time coefficient masks even when the matrix is one of the compile-time cluster codes
