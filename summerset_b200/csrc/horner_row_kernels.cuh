@@ -87,6 +87,28 @@ __device__ __forceinline__ int row_load_column(const EncRowGen &P, const uint8_t
     return onv;
 }
 
+// parity row j of a compile-time code from the column's source vectors: Horner over the coefficient bits, fully unrolled
+template <int CODE, int J, int D>
+__device__ __forceinline__ uint4 static_parity_row(const uint4 (&x)[D]) {
+    static_assert(D == static_code_d(CODE), "static code width");
+    constexpr int top = static_code_top(CODE, J);
+    uint4 acc = make_uint4(0u, 0u, 0u, 0u);
+#pragma unroll
+    for (int kk = 7; kk >= 0; --kk) {
+        if (kk > top) continue;
+        if (kk != top) {
+            acc.x = xtime_word(acc.x); acc.y = xtime_word(acc.y);
+            acc.z = xtime_word(acc.z); acc.w = xtime_word(acc.w);
+        }
+#pragma unroll
+        for (int i = 0; i < D; ++i)
+            if ((static_code_coef(CODE, J, i) >> kk) & 1u) {
+                acc.x ^= x[i].x; acc.y ^= x[i].y; acc.z ^= x[i].z; acc.w ^= x[i].w;
+            }
+    }
+    return acc;
+}
+
 // the p parity vectors of one column from its d source vectors x[], stored at plane[d + j] + out_off (and, with
 // emit_data, the source vectors themselves at plane[i] + out_off: the pack-for-send of subset_copy, rscoding.rs:255-293)
 template <int D, int CODE, bool MASKED>

@@ -1207,7 +1207,14 @@ struct CwDistributeGen {
     const uint32_t *prog;      // encode program: ProgHeader + splats + Horner masks
 };
 
-template <int D>
+template <int CODE, int D, int... Js>
+__device__ __forceinline__ void static_parity_all(const uint4 (&x)[D], uint4 (&par)[kMaxP], int onv, std::integer_sequence<int, Js...>) {
+    ((par[Js] = keep_bytes(static_parity_row<CODE, Js, D>(x), onv)), ...);
+}
+
+// CODE != kCodeGeneric: the coder's matrix is one of the compile-time cluster codes (RS(2,1), (4,3), (5,4), (4,2), (3,1) --
+// the 3-, 7- and 9-replica deployments), parity rows are unrolled from the table instead of read from the mask program
+template <int D, int CODE>
 __global__ void __launch_bounds__(kThreads, 2) crossword_distribute_generic_kernel(const __grid_constant__ CwDistributeGen P) {
     const uint32_t lane = threadIdx.x & 31u;
     const uint64_t warp = (static_cast<uint64_t>(blockIdx.x) * kThreads + threadIdx.x) >> 5;
@@ -1243,13 +1250,19 @@ __global__ void __launch_bounds__(kThreads, 2) crossword_distribute_generic_kern
                 const int nv = rem > onv ? onv : (rem < 0 ? 0 : static_cast<int>(rem));
                 x[i] = i < d ? dev::raw16_finish(raw[i], nv) : make_uint4(0u, 0u, 0u, 0u);
             }
+            if constexpr (CODE != kCodeGeneric) {
+                static_parity_all<CODE>(x, par, onv, std::make_integer_sequence<int, static_code_p(CODE)>{});
+            } else {
 #pragma unroll
-            for (int j = 0; j < kMaxP; ++j)
-                par[j] = j < p ? keep_bytes(horner_row<D>(x, d, hmask + j * d * 8, hdr->top[j]), onv) : make_uint4(0u, 0u, 0u, 0u);
+                for (int j = 0; j < kMaxP; ++j)
+                    par[j] = j < p ? keep_bytes(horner_row<D>(x, d, hmask + j * d * 8, hdr->top[j]), onv) : make_uint4(0u, 0u, 0u, 0u);
+            }
             // shard js goes to replica r's slot kk when (js - r*dj) mod T = kk < spr
             auto place = [&](uint32_t js, const uint4 &val) {
-                for (uint32_t r = 0; r < P.n_rep; ++r) {
-                    const uint32_t kk = (js + T - (r * P.dj) % T) % T;
+                // kk = (js - r*dj) mod T without a division: js < T and r*dj < T
+                uint32_t first = 0;                                   // r * dj
+                for (uint32_t r = 0; r < P.n_rep; ++r, first += P.dj) {
+                    const uint32_t kk = js >= first ? js - first : js + T - first;
                     if (kk < spr) dev::stg128_cs(P.rep[r] + ro + static_cast<uint64_t>(kk) * Lpad + k, val);
                 }
             };
@@ -1286,11 +1299,25 @@ int launch_crossword_distribute(ss_rs_coder *coder, const uint8_t *data, const u
         Gp.prog = static_cast<const uint32_t *>(coder->enc_prog);
         for (uint32_t r = 0; r < 16; ++r) Gp.rep[r] = r < n_replicas ? replica_logs[r] : nullptr;
         const uint32_t grid = ragged_grid(ctx, n);
-        SS_TRY(dispatch_d(coder->d, [&](auto DC) {
-            crossword_distribute_generic_kernel<decltype(DC)::value><<<grid, kThreads, 0, ctx->stream>>>(Gp);
-            return SS_OK;
-        }));
-        coder->last_kernel = "crossword_distribute_generic_kernel";
+        const int sc = ((coder->variant >> 11) & 1) ? kCodeGeneric : coder->static_code;
+        auto go_static = [&](auto CC) {
+            constexpr int C = decltype(CC)::value;
+            crossword_distribute_generic_kernel<static_code_d(C), C><<<grid, kThreads, 0, ctx->stream>>>(Gp);
+            coder->last_kernel = "crossword_distribute_generic_kernel<static>";
+        };
+        switch (sc) {
+            case kCode21: go_static(std::integral_constant<int, kCode21>{}); break;
+            case kCode43: go_static(std::integral_constant<int, kCode43>{}); break;
+            case kCode54: go_static(std::integral_constant<int, kCode54>{}); break;
+            case kCode42: go_static(std::integral_constant<int, kCode42>{}); break;
+            case kCode31: go_static(std::integral_constant<int, kCode31>{}); break;
+            default:
+                SS_TRY(dispatch_d(coder->d, [&](auto DC) {
+                    crossword_distribute_generic_kernel<decltype(DC)::value, kCodeGeneric><<<grid, kThreads, 0, ctx->stream>>>(Gp);
+                    return SS_OK;
+                }));
+                coder->last_kernel = "crossword_distribute_generic_kernel";
+        }
         SS_CUDA(cudaGetLastError());
         ctx->launches++;
         return SS_OK;

@@ -236,7 +236,8 @@ def test_crossword_distribute_matches_assignment_and_oracle(ctx, oracle, variant
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("n_rep,T,d,variant", [(5, 5, 3, 4), (5, 10, 6, 0), (7, 7, 4, 0), (3, 3, 2, 0), (3, 6, 4, 0), (4, 8, 5, 0), (9, 9, 5, 0)])
+@pytest.mark.parametrize("n_rep,T,d,variant", [(5, 5, 3, 4), (5, 10, 6, 0), (7, 7, 4, 0), (3, 3, 2, 0), (3, 6, 4, 0), (4, 8, 5, 0), (9, 9, 5, 0),
+                                               (7, 7, 4, 1 << 11), (9, 9, 5, 1 << 11), (3, 3, 2, 1 << 11)])
 def test_crossword_distribute_general_codes(ctx, oracle, n_rep, T, d, variant):
     """ss_crossword_distribute_dev for any (T, d, n) with T % n == 0 (crossword/mod.rs:805-830): replica r's log holds
     shards {(r*dj + k) mod T : k < spr} (crossword/mod.rs:866-888), bytes equal to the oracle's encode.  variant 4 runs
@@ -264,7 +265,9 @@ def test_crossword_distribute_general_codes(ctx, oracle, n_rep, T, d, variant):
                             torch.from_numpy(lens.astype(np.int32)).to(DEV), torch.from_numpy(spr).to(DEV),
                             torch.from_numpy(rep_off).to(DEV), [logs[r].data_ptr() for r in range(n_rep)])
     torch.cuda.synchronize()
-    assert rs.last_kernel() == "crossword_distribute_generic_kernel"
+    # the cluster codes (RS(2,1), (4,3), (5,4), (4,2)) have compile-time tables; variant bit 11 forces the run-time masks
+    static = (d, T - d) in ((2, 1), (4, 3), (5, 4), (4, 2), (3, 1)) and not (variant >> 11) & 1
+    assert rs.last_kernel() == ("crossword_distribute_generic_kernel<static>" if static else "crossword_distribute_generic_kernel")
     got = logs.cpu().numpy()
     par = np.zeros((p, lay["plane_bytes"]), dtype=np.uint8)
     oracle.rs_encode_batch(d, p, arena, lay["data_off"], lens, par.reshape(-1), lay["plane_bytes"], lay["par_off"])
