@@ -255,9 +255,11 @@ static void ctx_teardown(ss_ctx *ctx) {
     delete ctx;
 }
 
+// The context holds one reference to itself (dropped by ss_ctx_destroy) and every coder / engine one more: whoever drops
+// the last one tears it down, so destroy and the handles' destroy calls may come in any order and from any threads.
 void ctx_retain(ss_ctx *ctx) { ctx->live_handles.fetch_add(1); }
 void ctx_release(ss_ctx *ctx) {
-    if (ctx->live_handles.fetch_sub(1) == 1 && ctx->closing.load()) ctx_teardown(ctx);
+    if (ctx->live_handles.fetch_sub(1) == 1) ctx_teardown(ctx);
 }
 
 
@@ -347,13 +349,10 @@ int ss_ctx_create_on_stream(int device, void *cuda_stream, ss_ctx **out) {
 // and the last handle's destroy call tears it down (either order is safe, e.g. Python garbage collection).
 int ss_ctx_destroy(ss_ctx *ctx) {
     if (ctx == nullptr) return SS_OK;
-    if (ctx->live_handles.load() > 0) {
-        cudaSetDevice(ctx->device);
-        cudaStreamSynchronize(ctx->stream);
-        ctx->closing.store(true);
-        return SS_OK;
-    }
-    ctx_teardown(ctx);
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    if (ctx->closing.exchange(true)) return SS_OK;     // a second destroy while handles keep the context alive
+    ctx_release(ctx);                                  // the context's own reference
     return SS_OK;
 }
 

@@ -72,7 +72,7 @@ struct ss_ctx {
     int sm_count = 0;
     uint64_t launches = 0;
     // coders / engines created on this context hold a reference; ss_ctx_destroy defers the teardown to the last of them
-    std::atomic<int> live_handles{0};
+    std::atomic<int> live_handles{1};   // 1 = the context's own reference (ss_ctx_destroy drops it), + 1 per coder / engine
     std::atomic<bool> closing{false};
     // grow-only device scratch (scan temporaries, LUTs)
     void *scratch = nullptr;

@@ -539,3 +539,40 @@ def test_full_size_encode_erase_decode_roundtrip(ctx, oracle):
     torch.cuda.synchronize()
     assert int(st.abs().sum()) == 0
     assert torch.equal(sh, keep)
+
+
+@pytest.mark.gpu
+def test_context_and_handles_may_be_destroyed_in_any_order(oracle):
+    """ss_ctx_destroy before / after the coders and engines created on it (header: 'either order is safe'): the context
+    holds one reference to itself and every handle one more; a coder that outlives its context refuses work but can still
+    be destroyed, and a fresh context works afterwards."""
+    from summerset_b200._lib import SummersetError
+    from summerset_b200.api import Context, ReedSolomon
+    from summerset_b200.engine import LeaderEngine
+    rng = np.random.default_rng(11)
+    data = [rng.integers(0, 256, 64, dtype=np.uint8) for _ in range(3)]
+    want = [d.copy() for d in data] + [np.zeros(64, dtype=np.uint8) for _ in range(2)]
+    assert oracle.rs_encode(3, 2, want) == 0
+
+    def fresh():
+        return [d.copy() for d in data] + [np.zeros(64, dtype=np.uint8) for _ in range(2)]
+
+    for order in ("handles_first", "context_first"):
+        c = Context(0, own_stream=True)
+        rs1, rs2 = ReedSolomon(c, 3, 2), ReedSolomon(c, 4, 3)
+        eng = LeaderEngine(c, "multipaxos", 128, 5)
+        shards = fresh()
+        rs1.encode(shards)
+        assert all((a == b).all() for a, b in zip(shards, want))
+        if order == "handles_first":
+            rs1.close(); eng.close(); rs2.close(); c.close()
+        else:
+            c.close()
+            with pytest.raises(SummersetError):
+                rs1.encode(fresh())                     # the context is closed: calls fail loudly, nothing dangles
+            rs2.close(); eng.close(); rs1.close()       # the last one frees the context
+    c = Context(0, own_stream=True)
+    rs = ReedSolomon(c, 3, 2)
+    shards = fresh()
+    rs.encode(shards)
+    assert all((a == b).all() for a, b in zip(shards, want)) and rs.verify(shards)
