@@ -9,7 +9,8 @@
 //!   4. `cargo test -p summerset verify_b200_golden`.
 //!
 //! What a green run pins (every vector below was produced by oracle/ss_oracle.c + oracle/ss_wire.c, i.e. by this
-//! repository's CPU restatement, NOT by the reference):
+//! repository's CPU restatement, NOT by the reference; "reqbatch_put" starts from a real ReqBatch whose bincode bytes
+//! tests/golden/make_golden.py writes out by hand):
 //!   * parity bytes of reed_solomon_erasure::galois_8::ReedSolomon for RS(3,2), (4,3), (5,4), (2,1), (6,4)
 //!     -> DESIGN.md section 4 "parity unpinned" becomes "pinned";
 //!   * RSCodeword::from_data's split (shard_len, zero padding) -- src/utils/rscoding.rs:165-243;
@@ -73,16 +74,42 @@ fn bitmap_bincode_matches() {
 fn frames_match() {
     let v = vectors();
     let f = &v["frames"];
-    // reqs_cw: RS(3,2) codeword of a 20-byte payload holding only shard 1 = bytes 00..06, data_copy None.
-    // Build it the way rspaxos/request.rs:127-142 does: from_data on a 20-byte value whose shard 1 is 00..06, then
-    // subset_copy(&Bitmap::from((5, vec![1])), false).  (Use a ReqBatch / test type whose bincode encoding is those 20 bytes.)
-    let cw: RSCodeword<ReqBatch> = unimplemented!("construct as described above");
-    let accept = PeerMessage::Msg { msg: PeerMsg::Accept { slot: 300, ballot: 70000, reqs_cw: cw.clone() } };
-    assert_eq!(hex::encode(framed(&accept)), f["rspaxos_accept_slot300_ballot70000_d3_p2_len20_shard1"].as_str().unwrap());
     let reply = PeerMessage::Msg { msg: PeerMsg::AcceptReply { slot: 300, ballot: 70000 } };
     assert_eq!(hex::encode(framed(&reply)), f["rspaxos_accept_reply_slot300_ballot70000"].as_str().unwrap());
-    let wal = WalEntry::AcceptData { slot: 300, ballot: 70000, reqs_cw: cw };
-    assert_eq!(hex::encode(framed(&wal)), f["rspaxos_wal_accept_data_slot300_ballot70000"].as_str().unwrap());
     let commit = WalEntry::CommitSlot { slot: 300 };
     assert_eq!(hex::encode(framed(&commit)), f["rspaxos_wal_commit_slot300"].as_str().unwrap());
+}
+
+/// A real request batch end to end: bincode of the batch, RSCodeword::from_data's split, compute_parity's bytes, the
+/// single-shard subset_copy a follower is sent (rspaxos/request.rs:127-142), its Accept frame and its WAL record.
+#[test]
+fn real_request_batch_matches() -> Result<(), SummersetError> {
+    use crate::server::{ApiRequest, Command};
+    let v = vectors();
+    let g = &v["reqbatch_put"];
+    let batch: ReqBatch = vec![(7, ApiRequest::Req { id: 1, cmd: Command::Put { key: "k1".into(), value: "value-0123456789abcdef".into() } })];
+    let bytes = bincode::encode_to_vec(&batch, bincode::config::standard()).unwrap();
+    assert_eq!(hex::encode(&bytes), g["bincode"].as_str().unwrap(), "bincode of the batch");
+
+    let rs = ReedSolomon::new(3, 2).unwrap();
+    let mut cw = RSCodeword::<ReqBatch>::from_data(batch, 3, 2)?;
+    assert_eq!(cw.data_len() as u64, g["data_len"].as_u64().unwrap());
+    assert_eq!(cw.shard_len() as u64, g["shard_len"].as_u64().unwrap());
+    cw.compute_parity(Some(&rs))?;
+    // every shard, through the single-shard copies the leader sends (the only public view of the shard bytes)
+    for j in 0..5u8 {
+        let one = cw.subset_copy(&Bitmap::from((5, vec![j])), false)?;
+        let enc = bincode::encode_to_vec(&one, bincode::config::standard()).unwrap();
+        let want = hex::decode(g["shards"][j as usize].as_str().unwrap()).unwrap();
+        assert!(enc.windows(want.len()).any(|w| w == &want[..]), "shard {} bytes inside the encoded subset copy", j);
+    }
+    let sub = cw.subset_copy(&Bitmap::from((5, vec![1])), false)?;
+    let accept = PeerMessage::Msg { msg: PeerMsg::Accept { slot: 300, ballot: 70000, reqs_cw: sub.clone() } };
+    assert_eq!(hex::encode(framed(&accept)), g["accept_frame_shard1_slot300_ballot70000"].as_str().unwrap());
+    let wal = WalEntry::AcceptData { slot: 300, ballot: 70000, reqs_cw: sub };
+    assert_eq!(hex::encode(framed(&wal)), g["wal_accept_data_shard1_slot300_ballot70000"].as_str().unwrap());
+    // the Crossword vector (g["crossword_accept_frame_shards12_..."]) is the same check inside crossword/mod.rs with
+    // PeerMsg::Accept { slot, ballot, reqs_cw: cw.subset_copy(&Bitmap::from((5, vec![1, 2])), false)?,
+    //                   assignment: vec![Bitmap::from((5, vec![0,1])), (5,[1,2]), (5,[2,3]), (5,[3,4]), (5,[4,0])] }
+    Ok(())
 }

@@ -223,3 +223,40 @@ def test_oracle_reproduces_committed_golden_fixtures(oracle):
     nc = oracle.raft_scan_batch(t["raft_match"], t["raft_last_commit"], t["raft_log_end"], t["raft_curr_term"],
                                 t["raft_terms"], int(t["raft_threshold"]))
     assert (nc == t["raft_new_commit"]).all()
+
+
+def test_cargo_vectors_file_is_what_the_oracle_produces(oracle):
+    """tests/golden/rs_vectors.json is the input of tests/golden/verify_with_cargo.rs (the pin a maintainer with Rust can
+    run).  Guard it against drift: every vector must be what the oracle produces today, the hand-written bincode of the
+    real request batch must decode back to its fields, and its frames must parse to the same codeword."""
+    import json
+    from pathlib import Path
+    vec = json.loads((Path(__file__).parent / "golden" / "rs_vectors.json").read_text())
+    for case in vec["rs"]:
+        d, p, dl = case["d"], case["p"], case["data_len"]
+        payload = bytes.fromhex(case["payload"])
+        assert len(payload) == dl
+        L = oracle.cw_shard_len(dl, d)
+        row = np.zeros((1, (dl + 15) // 16 * 16), dtype=np.uint8)
+        row[0, :dl] = np.frombuffer(payload, dtype=np.uint8)
+        par = oracle.rs_encode_uniform(d, p, row, dl)
+        assert [bytes(s).hex() for s in oracle.cw_split(payload, d)] == case["data_shards"]
+        assert [par[j, 0, :L].tobytes().hex() for j in range(p)] == case["parity_shards"]
+    for case in vec["bitmap"]:
+        bits = sum(1 << i for i in case["ones"])
+        assert oracle.bitmap_encode(case["size"], bits).hex() == case["bincode"]
+    g = vec["reqbatch_put"]
+    b = bytes.fromhex(g["bincode"])
+    # bincode 2 standard(): Vec len, ClientId, variant Req, id, variant Put, key, value -- all below 251, one byte each
+    assert b[:5] == bytes([1, 7, 0, 1, 1]) and b[5] == 2 and b[6:8] == b"k1" and b[8] == 22 and b[9:] == b"value-0123456789abcdef"
+    assert g["data_len"] == len(b) == 31 and g["shard_len"] == 11
+    shards = [bytes.fromhex(s) for s in g["shards"]]
+    assert b"".join(shards[:3]) == b + bytes(2)                       # contiguous split, zero-padded tail
+    full = [np.frombuffer(s, dtype=np.uint8).copy() for s in shards]
+    assert oracle.rs_verify(3, 2, full) == (0, True)
+    for key, kind in (("accept_frame_shard1_slot300_ballot70000", 0), ("wal_accept_data_shard1_slot300_ballot70000", 1)):
+        dec = oracle.decode_accept(bytes.fromhex(g[key]), kind)
+        assert dec is not None and (dec["slot"], dec["ballot"], dec["d"], dec["p"], dec["data_len"], dec["shard_len"]) == (300, 70000, 3, 2, 31, 11)
+        assert [s is not None for s in dec["shards"]] == [False, True, False, False, False] and dec["shards"][1] == shards[1]
+    dec = oracle.decode_accept(bytes.fromhex(g["crossword_accept_frame_shards12_slot300_ballot70000_assignment_spr2"]), 0, with_assignment=True)
+    assert dec["shards"][1] == shards[1] and dec["shards"][2] == shards[2] and dec["assignment"] == [3, 6, 12, 24, 17] and dec["assign_size"] == 5
