@@ -177,3 +177,19 @@ def test_nvrtc_specialisation_compiles_without_a_gpu():
     n = lib.ss_jit_selftest(6, 4, log, 16384)
     assert n > 50000, (n, log.value.decode())
     assert lib.ss_jit_selftest(9, 3, log, 16384) < 0 and b"d <= 8" in log.value      # outside the specialised range
+
+
+def test_crossword_slot_pitch_matches_the_header():
+    """api.cw_slot_pitch is SS_CW_SLOT_PITCH of include/summerset_b200.h: the shard length rounded up to 32 bytes (DRAM
+    sector), for ints and arrays; the macro text is checked so the two cannot drift apart silently."""
+    import re
+    from pathlib import Path
+    import numpy as np
+    from summerset_b200.api import cw_slot_pitch
+    hdr = (Path(__file__).resolve().parent.parent / "include" / "summerset_b200.h").read_text()
+    m = re.search(r"#define SS_CW_SLOT_PITCH\(L\) \(\(\(\(uint64_t\)\(L\)\) \+ (\d+)u\) & ~\(uint64_t\)(\d+)u\)", hdr)
+    assert m and m.group(1) == m.group(2) == "31"
+    for L, want in [(0, 0), (1, 32), (31, 32), (32, 32), (33, 64), (86, 96), (171, 192), (1366, 1376), (21846, 21856)]:
+        assert cw_slot_pitch(L) == want
+    arr = np.array([1, 32, 33, 10923], dtype=np.int64)
+    assert (cw_slot_pitch(arr) == np.array([32, 32, 64, 10944])).all()
